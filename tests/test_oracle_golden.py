@@ -1,0 +1,136 @@
+"""Pin the CPU oracle against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+produced by tools/make_golden.py in the build container).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import CONFIGS, init_params, smin_forward, content_matrix
+from oracle import metrics_oracle as mo
+from vml_b200 import synth
+
+NAMES = ["tiny", "tiny_r2", "charadessta", "tacos", "activitynet"]
+
+
+def _load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    cfg = CONFIGS[name]
+    batch = synth.make_batch(cfg, int(g["B"]), int(g["seed"]))
+    params = init_params(cfg, 43)
+    return g, cfg, batch, params
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return ((a - b).abs() / b.abs().clamp_min(1e-6)).max().item()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_inputs_and_params_are_reproducible(golden_dir, name):
+    g, cfg, batch, params = _load(golden_dir, name)
+    assert int(g["n_params"]) == sum(v.numel() for v in params.values())
+    assert float(g["chk_params"]) == sum(v.double().sum().item() for v in params.values())
+    assert float(g["chk_video"]) == batch["video_features"].double().sum().item()
+    assert float(g["chk_query"]) == batch["query_features"].double().sum().item()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_forward_matches_reference_fp32(golden_dir, name):
+    g, cfg, batch, params = _load(golden_dir, name)
+    with torch.no_grad():
+        out = smin_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS])
+    for key, o in zip(("pm", "ps", "pe", "pa"), out):
+        assert o.dtype == torch.float32 and tuple(o.shape) == g[key].shape
+        # tolerance stated by north_star for the fp32 validation mode: 1e-5 relative
+        assert _rel(o, g[key]) < 1e-5, key
+        # masked entries exactly zero, like the reference
+        assert torch.equal(o == 0, torch.from_numpy(g[key] == 0)), key
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_r2", "charadessta"])
+def test_forward_matches_reference_fp64(golden_dir, name):
+    g, cfg, batch, params = _load(golden_dir, name)
+    p64 = {k: v.double() for k, v in params.items()}
+    with torch.no_grad():
+        out = smin_forward(p64, cfg, batch["video_features"].double(), batch["video_mask"],
+                           batch["query_features"].double(), batch["query_mask"],
+                           batch["length_mask"], batch["moment_mask"])
+    for key, o in zip(("pm64", "ps64", "pe64", "pa64"), out):
+        assert _rel(o, g[key]) < 1e-12, key
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_r2"])
+def test_every_stage_matches_reference(golden_dir, name):
+    g, cfg, batch, params = _load(golden_dir, name)
+    with torch.no_grad():
+        _, inter = smin_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS],
+                                return_intermediates=True)
+    for key, val in inter.items():
+        ref = torch.from_numpy(g[key])
+        assert tuple(val.shape) == tuple(ref.shape), key
+        err = (val - ref).abs().max().item()
+        assert err < 2e-6 * max(1.0, ref.abs().max().item()), (key, err)
+        if key[:2] in ("fc", "fm"):     # invalid cells exactly zero (invariant 3)
+            assert torch.equal(val == 0, ref == 0), key
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_r2"])
+def test_content_matrix_matches_reference(golden_dir, name):
+    g, cfg, _, _ = _load(golden_dir, name)
+    Wc = content_matrix(cfg.T, cfg.L, cfg.C)
+    assert torch.equal(Wc, torch.from_numpy(g["Wc"]))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_content_matrix_nnz(golden_dir, name):
+    g, cfg, _, _ = _load(golden_dir, name)
+    assert int((content_matrix(cfg.T, cfg.L, cfg.C) != 0).sum()) == int(g["Wc_nnz"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_metric_matches_reference(golden_dir, name):
+    g, cfg, batch, _ = _load(golden_dir, name)
+    pm, ps, pe = (torch.from_numpy(g[k]) for k in ("pm", "ps", "pe"))
+    keys = g["metric_keys"].tolist()
+    # (a) with the reference's own top-k order: identical counts
+    m = mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"], top_indices=torch.from_numpy(g["ref_topk"]))
+    assert [m[k] for k in keys] == g["metric_vals"].tolist()
+    # (b) lowest-index tie-break: same indices on tie-free data (length >= 3 => >= 5 valid cells)
+    scores = mo.proposal_scores(pm, ps, pe, batch["moment_mask"])
+    top = mo.topk_lowest_index(scores, 5)
+    srt = scores.sort(dim=1, descending=True)[0][:, :6]
+    tie_free = bool(((srt[:, :-1] - srt[:, 1:]) > 0).all())
+    if tie_free:
+        assert torch.equal(top, torch.from_numpy(g["ref_topk"]))
+    m2 = mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"])
+    if tie_free:
+        assert [m2[k] for k in keys] == g["metric_vals"].tolist()
+    # NMS bypass == plain top-k
+    assert torch.equal(mo.nms_topk(scores, cfg.L, 5, 1.0), top)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_loss_matches_reference(golden_dir, name):
+    g, cfg, batch, _ = _load(golden_dir, name)
+    pm, ps, pe, pa = (torch.from_numpy(g[k]) for k in ("pm", "ps", "pe", "pa"))
+    loss = mo.loss_fn(pm, batch["ym"], batch["sm"], batch["moment_mask"], ps, batch["ys"], batch["ss"],
+                      pe, batch["ye"], batch["se"], pa, batch["ya"], batch["length_mask"])
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+    parts = [mo.scaled_iou_bce(pm, batch["ym"], batch["sm"], batch["moment_mask"]),
+             mo.scaled_iou_bce(ps, batch["ys"], batch["ss"], batch["length_mask"]),
+             mo.scaled_iou_bce(pe, batch["ye"], batch["se"], batch["length_mask"]),
+             mo.scaled_iou_bce(pa, batch["ya"], None, batch["length_mask"])]
+    for a, b in zip(parts, g["loss_parts"].tolist()):
+        assert abs(a.item() - b) < 1e-6 * max(abs(b), 1e-3)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_synth_labels_match_reference_dataset(golden_dir, name):
+    g, cfg, batch, _ = _load(golden_dir, name)
+    assert torch.equal(batch["sm"], torch.from_numpy(g["sm_ref"]))
+    assert torch.equal(batch["ya"], torch.from_numpy(g["ya_ref"]))
+    assert torch.allclose(batch["ss"], torch.from_numpy(g["ss_ref"]), rtol=1e-6, atol=0)
+    assert torch.allclose(batch["se"], torch.from_numpy(g["se_ref"]), rtol=1e-6, atol=0)
+    assert not torch.isnan(batch["sm"]).any()
