@@ -1,0 +1,190 @@
+/*
+ * vml_b200.h -- C ABI of libvml_b200.so: the B200 (sm_100a) implementation of the
+ * SMIN cross-modal proposal-scoring hot path of ChanukyaVardhan/Video-Moment-Localization.
+ *
+ * The reference has no FFI / plugin registry (it is pure PyTorch); its boundary for this
+ * path is the Python contract   models.SMIN.forward  (models.py:367-377),
+ * main.loss_fn (main.py:110-116) and utils.compute_ious (utils.py:10-31).  Each entry
+ * point below names the reference function(s) it replaces.  The Python host side
+ * (video-moment-localization_b200/smin.py etc.) binds these with ctypes and mirrors the
+ * reference interface; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no allocation inside, no global state except a cached driver entry point;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = launched, negative = error (vml_last_error() has the text);
+ *   - `prec`: VML_FP32 = validation mode (CUDA-core fp32 math, fp32 activations),
+ *             VML_BF16 = fast mode (tcgen05 bf16 MMA, fp32 accumulate, bf16 activations);
+ *   - "act" pointers are float* in VML_FP32 and __nv_bfloat16* in VML_BF16.
+ *
+ * Packed moment map.  The reference carries dense (B,L,L,...) tensors whose invalid cells
+ * are exactly zero (invariant 3).  This library stores only the valid
+ * cells: vml_build_cells() compacts moment_mask into a cell list sorted by (b,i,j);
+ * fc is [n_cells, C, D], fm is [n_cells, D].  n_cells lives on the device
+ * (cells->n_cells[0]); buffers are sized for `capacity` cells by the caller.
+ */
+#ifndef VML_B200_H
+#define VML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VML_API __attribute__((visibility("default")))
+#else
+#define VML_API
+#endif
+
+#define VML_FP32 0
+#define VML_BF16 1
+
+#define VML_OK 0
+#define VML_ERR_ARG (-1)
+#define VML_ERR_CUDA (-2)
+#define VML_ERR_UNSUPPORTED (-3)
+
+/* Model dimensions: config/*.yml:5-13 (T, L, C, d, dl, num_smi_layers, input_video_dim,
+ * max_query_length, lstm_hidden_size).  D must equal 2*H (models.py:81). */
+typedef struct {
+  int32_t T, L, C, D, dl, layers, d0, Nq, H;
+} vml_dims_t;
+
+/* Compacted list of valid moment-map cells (device memory, caller-allocated). */
+typedef struct {
+  int32_t* code;      /* [capacity]  (b << 16) | (i << 8) | j, sorted by (b,i,j)            */
+  int32_t* row_start; /* [B*L + 1]   first cell of map row (b,i); row_start[B*L] = n_cells  */
+  int32_t* n_cells;   /* [1]         number of valid cells                                  */
+  int32_t* status;    /* [1]         bit0: capacity overflow                                */
+  int32_t capacity;
+} vml_cells_t;
+
+VML_API const char* vml_last_error(void);
+VML_API int vml_version(void);
+/* Names of all kernels compiled into the library, '\n'-separated (for smoke/bench reports). */
+VML_API const char* vml_kernel_names(void);
+
+/* ---- layout ------------------------------------------------------------------------- */
+
+/* moment_mask[B,L,L] (bool/u8) -> cell list.  Replaces the dense masking of
+ * models.py:117,244,290,337 by compaction. */
+VML_API int vml_build_cells(const uint8_t* moment_mask, int B, int L, vml_cells_t cells, void* stream);
+
+/* packed [n_cells, inner] <-> dense [B, L, L, inner] (invalid cells zero-filled). */
+VML_API int vml_unpack_cells(const void* packed, void* dense, vml_cells_t cells, int B, int L, int inner, int prec,
+                     void* stream);
+VML_API int vml_pack_cells(const void* dense, void* packed, vml_cells_t cells, int B, int L, int inner, int prec,
+                   void* stream);
+
+/* fp32 [rows, k] -> bf16 [rows, k_pad] (zero padded), for TMA-legal operand rows. */
+VML_API int vml_cast_pad_bf16(const float* src, void* dst_bf16, int64_t rows, int k, int k_pad, void* stream);
+
+/* ---- dense contractions --------------------------------------------------------------- */
+
+/* out[M,N] = A[M,K] . W[N,K]^T + bias[N].  VML_FP32: A,W,out float.  VML_BF16: A,W bf16
+ * (K multiple of 8), out bf16 or float (out_fp32 != 0); tcgen05/TMEM kernel.
+ * m_dev, if not NULL, is a device int32; the live row count is min(M, *m_dev * m_scale)
+ * (e.g. n_cells * C).  Replaces the nn.Linear / 1x1-conv call sites of
+ * models.py:21,134-135,204-205,236-239,285-286. */
+VML_API int vml_linear(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
+                       const int32_t* m_dev, int m_scale, int prec, int out_fp32, void* stream);
+
+/* a1: VideoEncoder.forward (models.py:25-36).  fv = (v.W^T + b)*mask + pe[t]*mask.
+ * v: float [B*T,d0] (VML_FP32) or bf16 [B*T,k_pad] (VML_BF16).  fv: act [B*T, D]. */
+VML_API int vml_clip_projection(const void* v, const void* W, const float* bias, const float* pe,
+                        const uint8_t* video_mask, void* fv, int B, vml_dims_t d, int k_pad, int prec,
+                        void* stream);
+
+/* ---- a2: QueryEncoder (models.py:48-64) -------------------------------------------------- */
+
+/* One bi-LSTM layer's recurrence.  gin[B*Nq, 2*4H] float = x.W_ih^T + b_ih + b_hh for
+ * (forward | reverse) directions (gate order i,f,g,o); whh_t[2][H][4H] float = W_hh^T per
+ * direction; qlen[B] int32 valid words.  y[B,Nq,2H] float (zero for t >= qlen, as
+ * pad_packed_sequence); y_bf16 optional copy; fs[B,2H] optional = [h_fwd(len-1) | h_bwd(0)]. */
+VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16,
+                   float* fs, int B, int Nq, int H, void* stream);
+
+/* query_mask[B,Nq] u8 -> qlen[B] int32  (models.py:50, without the D2H copy of :52). */
+VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, int Nq, void* stream);
+
+/* Per-layer query-side tensors of ContentUnit (models.py:249-251,209), hoisted out of the
+ * per-cell path:  w_hat = (wproj)*qmask, kc = w_hat.Wk^T + bk, ktil = kc.Wq  (so that
+ * Q.K^T = c_hat.ktil^T + beta, beta = kc.bq), s_hat = fs.Ws^T + bs.
+ * wproj[B*Nq, ld] float holds fw.Ww^T + bw at column offset col0. */
+VML_API int vml_query_prep(const float* wproj, int ld, int col0, const float* fs, const uint8_t* query_mask,
+                   const float* Wk, const float* bk, const float* Wq, const float* bq, const float* Ws,
+                   const float* bs, float* w_hat, float* ktil, float* beta, float* s_hat, int B,
+                   vml_dims_t d, void* stream);
+
+/* ---- a3+a4: Backbone fusion + ProposalGeneration (models.py:81,88-98,115-126) ----------- */
+
+/* f = fv*fs fused with span pooling; only valid cells are written.
+ * fv act [B,T,D]; fs float [B,D]; fc act [cap,C,D]; fm act [cap,D]; fb float [B,L,D]. */
+VML_API int vml_span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb,
+                       int B, vml_dims_t d, int prec, void* stream);
+
+/* ---- a5+a6: ContentUnit (models.py:207-226,242-276) ----------------------------------------- */
+
+/* middle of the unit: c_hat act [n*C, dl] -> cc_hat act [n*C, dl]
+ * (content-word attention, gate, CxC self-attention). */
+VML_API int vml_content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat,
+                          const float* s_hat, const uint8_t* query_mask, vml_cells_t cells, void* cc_hat,
+                          int B, vml_dims_t d, int prec, void* stream);
+
+/* cu = cc_hat.Wc^T + bc + fc + sigmoid(fm*fs)*fm   (models.py:269-276). */
+VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm,
+                    const float* fs, vml_cells_t cells, void* cu, vml_dims_t d, int prec, void* stream);
+
+/* ---- a7: BoundaryUnit (models.py:137-154,164-196) ------------------------------------------- */
+
+/* qb float [B*L, D] = fb.Wq^T + bq ; kb float [B*Nq, ldk] (+col0) = fw.Wk^T + bk (precomputed).
+ * g_scratch float [B,L,D].  bu float [B,L,D] = f_bb + f_b + f_bm. */
+VML_API int vml_boundary_unit(const float* qb, const float* kb, int ldk, int col0, const float* fw, const float* fs,
+                      const float* fb, const void* fm, const uint8_t* query_mask,
+                      const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* bu, int B,
+                      vml_dims_t d, int prec, void* stream);
+
+/* ---- a8: MomentUnit (models.py:288-303) ------------------------------------------------------ */
+
+/* operand[n, 2D] = [ bu[b,i]*bu[b,j] | mean_c cu[n,c,:] ]  (act) */
+VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d,
+                       int prec, void* stream);
+/* mu = operand.[Wfb|Wfc]^T + (bfb+bfc) + fm */
+VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* bias_sum, const void* fm,
+                   vml_cells_t cells, void* mu, vml_dims_t d, int prec, void* stream);
+
+/* ---- a9: Localization (models.py:335-344) ------------------------------------------------------ */
+
+/* w4 float [4,D] = (pm,ps,pe,pa) weights, b4 float[4].  Outputs dense float, masked to 0. */
+VML_API int vml_localize(const void* fm, const float* fb, const float* w4, const float* b4, vml_cells_t cells,
+                 const uint8_t* length_mask, float* pm, float* ps, float* pe, float* pa, int B,
+                 vml_dims_t d, int prec, void* stream);
+
+/* ---- a10: loss (main.py:89-116, with reduction=None read as 'none') -------------------------- */
+
+/* loss[0] = L_m + L_s + L_e + 0.5 L_a ; parts[4] = the four terms; scratch float [4*B].
+ * Optional gradients d loss / d{pm,ps,pe,pa} (all NULL to skip). */
+VML_API int vml_scaled_iou_bce(const float* pm, const uint8_t* ym, const float* sm, const uint8_t* moment_mask,
+                       const float* ps, const uint8_t* ys, const float* ss, const float* pe,
+                       const uint8_t* ye, const float* se, const float* pa, const uint8_t* ya,
+                       const uint8_t* length_mask, int B, int L, float* loss, float* parts, float* scratch,
+                       float* g_pm, float* g_ps, float* g_pe, float* g_pa, void* stream);
+
+/* ---- a11: compute_ious (utils.py:10-31) --------------------------------------------------------- */
+
+/* score = ((pm*sqrt(ps_i))*sqrt(pe_j))*mask ; top-k (k <= 8) by score, ties -> lowest flat
+ * index ; top_iou = sm[idx] ; counts[n_idx*4 + m_idx] += any(top_iou[:n] > m) for
+ * n in {1,5}, m in {.1,.3,.5,.7} (ACCUMULATES into counts, like the reference's running
+ * sums, main.py:155-156).  nms_num/nms_den: temporal-NMS IoU threshold as a rational;
+ * nms_num >= nms_den disables NMS (the reference has none, utils.py:14). */
+VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask,
+                          const float* sm, int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx,
+                          float* top_score, float* top_iou, int64_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VML_B200_H */

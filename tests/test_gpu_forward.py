@@ -1,0 +1,135 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on the B200:
+    python -m pytest tests -m gpu -x -q
+Tolerances are the ones north_star states: proposal scores within 1e-5 relative in the fp32
+validation mode and 1e-2 relative in bf16; masked entries exactly 0; indices/counts exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import CONFIGS, init_params, smin_forward as oracle_forward
+from oracle import metrics_oracle as mo
+from vml_b200 import lib as L_
+from vml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import dims_of, model_for, rel_err, scaled_err, to_dev, unpack  # noqa: E402
+
+FP32_TOL = 1e-5   # north_star: fp32 validation mode
+BF16_TOL = 1e-2   # north_star: bf16 mode
+
+
+def _oracle(cfg, batch, params, inter=False):
+    with torch.no_grad():
+        return oracle_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS], return_intermediates=inter)
+
+
+@pytest.mark.parametrize("name,B,seed", [("tiny", 5, 104), ("tiny_r2", 5, 105), ("charadessta", 4, 101),
+                                         ("tacos", 3, 102), ("activitynet", 2, 103)])
+def test_forward_fp32_matches_oracle_and_golden(name, B, seed, golden_dir):
+    cfg = CONFIGS[name]
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, B, seed)
+    model = model_for(cfg, "fp32", params)
+    out = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    ref = _oracle(cfg, batch, params)
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    for key, o, r in zip(("pm", "ps", "pe", "pa"), out, ref):
+        assert o.dtype == torch.float32 and o.shape == r.shape
+        assert rel_err(o, r) < FP32_TOL, (key, rel_err(o, r))
+        assert rel_err(o, torch.from_numpy(g[key])) < FP32_TOL, ("golden", key)      # the reference's own output
+        assert torch.equal(o.cpu() == 0, r == 0), f"{key}: masked entries must be exactly 0"
+
+
+@pytest.mark.parametrize("name,B,seed", [("tiny", 5, 104), ("charadessta", 4, 101), ("tacos", 3, 102), ("activitynet", 2, 103)])
+def test_forward_bf16_matches_oracle(name, B, seed):
+    cfg = CONFIGS[name]
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, B, seed)
+    model = model_for(cfg, "bf16", params)
+    out = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    ref = _oracle(cfg, batch, params)
+    for key, o, r in zip(("pm", "ps", "pe", "pa"), out, ref):
+        assert rel_err(o, r) < BF16_TOL, (key, rel_err(o, r))
+        assert torch.equal(o.cpu() == 0, r == 0), key
+
+
+@pytest.mark.parametrize("name,prec", [("tiny", "fp32"), ("tiny_r2", "fp32"), ("charadessta", "fp32"), ("tiny", "bf16"),
+                                       ("charadessta", "bf16")])
+def test_every_stage_matches_oracle(name, prec):
+    """fv/fs/fw, pooled fc/fm/fb and each SMI layer's (cu, mu, bu), packed -> dense."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    params = init_params(cfg, 43)
+    B = 4
+    batch = synth.make_batch(cfg, B, 7)
+    _, inter = _oracle(cfg, batch, params, inter=True)
+    p = L_.PREC[prec]
+    dims = dims_of(cfg)
+    pk = pack_weights(params, dims, p, torch.device("cuda"))
+    ws = Workspace(torch.device("cuda"))
+    keep = {}
+    smin_forward(pk, dims, p, ws, *[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS], keep=keep)
+    tol = 2e-6 if prec == "fp32" else 2e-2
+    cells = keep["cells"]
+    assert scaled_err(keep["fv"].float().view(B, cfg.T, cfg.D), inter["fv"]) < tol
+    assert scaled_err(keep["fs"], inter["fs"]) < 2e-6          # LSTM runs in fp32 in both modes
+    assert scaled_err(keep["fw"], inter["fw"]) < 2e-6
+    for k in range(cfg.layers + 1):
+        fc = unpack(keep[f"fc{k}"], cells, B, cfg.L, cfg.C * cfg.D, p).view(B, cfg.L, cfg.L, cfg.C, cfg.D)
+        fm = unpack(keep[f"fm{k}"], cells, B, cfg.L, cfg.D, p)
+        assert scaled_err(fc, inter[f"fc{k}"]) < tol * (1 + k), (k, "fc", scaled_err(fc, inter[f"fc{k}"]))
+        assert scaled_err(fm, inter[f"fm{k}"]) < tol * (1 + k), (k, "fm", scaled_err(fm, inter[f"fm{k}"]))
+        assert scaled_err(keep[f"fb{k}"], inter[f"fb{k}"]) < tol * (1 + k), (k, "fb")
+        if prec == "fp32":   # invalid cells exactly zero (they are never stored; unpack zero-fills)
+            assert torch.equal(fm.cpu() == 0, inter[f"fm{k}"] == 0)
+
+
+def test_batch_slice_invariance_fp32():
+    """Samples are independent (invariant 4): the data-parallel split is exact."""
+    cfg = CONFIGS["charadessta"]
+    batch = synth.make_batch(cfg, 6, 11)
+    model = model_for(cfg, "fp32")
+    full = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    part = model(*[batch[k][2:5].cuda() for k in synth.MODEL_INPUT_KEYS])
+    for a, b in zip(full, part):
+        assert torch.equal(a[2:5], b)
+
+
+def test_padding_invariance_fp32():
+    """Garbage in clips >= nfeats and words >= len must not change the result (invariant 5)."""
+    cfg = CONFIGS["charadessta"]
+    batch = synth.make_batch(cfg, 4, 12)
+    model = model_for(cfg, "fp32")
+    clean = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    dirty = {k: v.clone() for k, v in batch.items()}
+    vm = batch["video_mask"].bool().expand_as(dirty["video_features"])
+    qm = batch["query_mask"].bool().expand_as(dirty["query_features"])
+    dirty["video_features"][~vm] = 123.0
+    dirty["query_features"][~qm] = -77.0
+    out = model(*[dirty[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    for a, b in zip(clean, out):
+        assert torch.equal(a, b)
+
+
+def test_same_seed_same_init_as_reference_contract():
+    """Construction order mirrors the reference, state_dict keys/shapes match init_params (section 8b)."""
+    cfg = CONFIGS["charadessta"]
+    from vml_b200.smin import SMIN
+    m = SMIN(*cfg.ctor_args())
+    ref = init_params(cfg, 43)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape for k in sd)
+
+
+def test_cpu_input_raises():
+    cfg = CONFIGS["tiny"]
+    from vml_b200.smin import SMIN
+    m = SMIN(*cfg.ctor_args())
+    batch = synth.make_batch(cfg, 2, 1)
+    with pytest.raises(L_.VmlError):
+        m(*[batch[k] for k in synth.MODEL_INPUT_KEYS])

@@ -1,0 +1,165 @@
+"""Loss (a10) and R@n,IoU=m evaluation (a11) parity: integer/index results bit-exact."""
+import pytest
+import torch
+
+from oracle import CONFIGS, init_params, smin_forward as oracle_forward
+from oracle import metrics_oracle as mo
+from vml_b200 import synth
+from vml_b200.evaluate import RecallAccumulator, compute_ious, score_topk_recall
+from vml_b200.losses import bce_loss, loss_fn, loss_terms
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import model_for  # noqa: E402
+
+
+def _scores(cfg, B, seed):
+    """Plausible score tensors: random-init oracle forward on a synthetic batch."""
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, B, seed)
+    with torch.no_grad():
+        pm, ps, pe, pa = oracle_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS])
+    return batch, pm, ps, pe, pa
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 9), ("charadessta", 8), ("tacos", 3)])
+def test_topk_indices_and_counts_exact(name, B):
+    cfg = CONFIGS[name]
+    batch, pm, ps, pe, _ = _scores(cfg, B, 21)
+    g = lambda t: t.cuda()
+    top_idx, top_score, top_iou, counts = score_topk_recall(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]))
+    scores = mo.proposal_scores(pm, ps, pe, batch["moment_mask"])
+    want = mo.topk_lowest_index(scores, 5)
+    assert torch.equal(top_idx.cpu().long(), want)                                   # indices: exact
+    assert torch.equal(top_score.cpu(), torch.gather(scores, 1, want))               # scores: bit-exact (same op order)
+    assert torch.equal(top_iou.cpu(), torch.gather(batch["sm"].view(B, -1), 1, want))
+    ref = mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"])
+    got = compute_ious(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]))
+    assert dict(got) == ref                                                          # R@n, IoU=m counts: exact
+
+
+def test_topk_ties_lowest_index_and_short_videos():
+    """Engineered ties and a sample with < 5 valid cells (masked zeros enter the top-5 in index order)."""
+    B, L = 3, 8
+    pm = torch.full((B, L, L), 0.5)
+    ps = torch.full((B, L), 0.25)
+    pe = torch.full((B, L), 0.25)
+    mask = torch.zeros(B, L, L, dtype=torch.bool)
+    mask[0] = torch.triu(torch.ones(L, L)).bool()
+    mask[1, 0, 0] = mask[1, 0, 1] = mask[1, 1, 1] = True
+    mask[2] = torch.triu(torch.ones(L, L)).bool()
+    pm[2, 3, 5] = 0.9
+    sm = torch.rand(B, L, L, generator=torch.Generator().manual_seed(3))
+    top_idx, _, _, counts = score_topk_recall(pm.cuda(), ps.cuda(), pe.cuda(), mask.cuda(), sm.cuda())
+    scores = mo.proposal_scores(pm, ps, pe, mask)
+    assert torch.equal(top_idx.cpu().long(), mo.topk_lowest_index(scores, 5))
+    assert top_idx[2, 0].item() == 3 * L + 5
+    ref = mo.compute_ious(pm, ps, pe, mask, sm)
+    got = compute_ious(pm.cuda(), ps.cuda(), pe.cuda(), mask.cuda(), sm.cuda())
+    assert dict(got) == ref
+
+
+@pytest.mark.parametrize("thresh", [0.3, 0.5, 0.7])
+def test_nms_matches_oracle_definition(thresh):
+    """Temporal NMS has no reference implementation (utils.py:14): parity is against OUR oracle definition."""
+    cfg = CONFIGS["charadessta"]
+    batch, pm, ps, pe, _ = _scores(cfg, 6, 22)
+    g = lambda t: t.cuda()
+    top_idx, _, _, _ = score_topk_recall(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]), nms_threshold=thresh)
+    scores = mo.proposal_scores(pm, ps, pe, batch["moment_mask"])
+    assert torch.equal(top_idx.cpu().long(), mo.nms_topk(scores, cfg.L, 5, thresh))
+
+
+def test_nms_bypass_equals_reference_behaviour():
+    cfg = CONFIGS["charadessta"]
+    batch, pm, ps, pe, _ = _scores(cfg, 4, 23)
+    g = lambda t: t.cuda()
+    a = score_topk_recall(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]), nms_threshold=1.0)[0]
+    b = score_topk_recall(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]), nms_threshold=2.0)[0]
+    assert torch.equal(a, b)
+
+
+def test_accumulator_sums_batches():
+    cfg = CONFIGS["charadessta"]
+    acc = RecallAccumulator(torch.device("cuda"))
+    total = None
+    for seed in (31, 32, 33):
+        batch, pm, ps, pe, _ = _scores(cfg, 4, seed)
+        acc.update(pm.cuda(), ps.cuda(), pe.cuda(), batch["moment_mask"].cuda(), batch["sm"].cuda())
+        ref = mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"])
+        total = ref if total is None else {k: total[k] + ref[k] for k in ref}
+    assert acc.result(normalize=False) == total
+    assert acc.num_samples == 12
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 5), ("charadessta", 4), ("activitynet", 2)])
+def test_loss_matches_oracle(name, B):
+    cfg = CONFIGS[name]
+    batch, pm, ps, pe, pa = _scores(cfg, B, 41)
+    g = lambda t: t.cuda()
+    args = (pm, batch["ym"], batch["sm"], batch["moment_mask"], ps, batch["ys"], batch["ss"], pe, batch["ye"], batch["se"],
+            pa, batch["ya"], batch["length_mask"])
+    ref = mo.loss_fn(*args)
+    loss, parts = loss_terms(*[g(a) for a in args])
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())      # fp32, 1e-5 relative
+    want = [mo.scaled_iou_bce(pm, batch["ym"], batch["sm"], batch["moment_mask"]),
+            mo.scaled_iou_bce(ps, batch["ys"], batch["ss"], batch["length_mask"]),
+            mo.scaled_iou_bce(pe, batch["ye"], batch["se"], batch["length_mask"]),
+            mo.scaled_iou_bce(pa, batch["ya"], None, batch["length_mask"])]
+    for a, b in zip(parts.cpu().tolist(), want):
+        assert abs(a - b.item()) < 1e-5 * max(abs(b.item()), 1e-3)
+    # single-term drop-in
+    assert abs(bce_loss(g(pm), g(batch["ym"]), g(batch["sm"]), g(batch["moment_mask"])).item() - want[0].item()) < 1e-5
+    assert abs(bce_loss(g(pa), g(batch["ya"]), None, g(batch["length_mask"])).item() - want[3].item()) < 1e-5
+
+
+def test_loss_gradients_match_autograd_of_oracle():
+    cfg = CONFIGS["charadessta"]
+    batch, pm, ps, pe, pa = _scores(cfg, 4, 42)
+    leaves = [t.clone().requires_grad_(True) for t in (pm, ps, pe, pa)]
+    ref = mo.loss_fn(leaves[0], batch["ym"], batch["sm"], batch["moment_mask"], leaves[1], batch["ys"], batch["ss"],
+                     leaves[2], batch["ye"], batch["se"], leaves[3], batch["ya"], batch["length_mask"])
+    ref.backward()
+    dl = [t.detach().cuda().requires_grad_(True) for t in (pm, ps, pe, pa)]
+    g = lambda t: t.cuda()
+    loss = loss_fn(dl[0], g(batch["ym"]), g(batch["sm"]), g(batch["moment_mask"]), dl[1], g(batch["ys"]), g(batch["ss"]),
+                   dl[2], g(batch["ye"]), g(batch["se"]), dl[3], g(batch["ya"]), g(batch["length_mask"]))
+    loss.backward()
+    masks = [batch["moment_mask"], batch["length_mask"], batch["length_mask"], batch["length_mask"]]
+    for a, b, mk in zip(dl, leaves, masks):
+        ga, gb = a.grad.cpu()[mk], b.grad[mk]
+        assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-7)
+        assert torch.all(a.grad.cpu()[~mk] == 0)
+
+
+def test_end_to_end_fp32_indices_and_recall_exact():
+    """fp32 validation mode end to end: CUDA scores -> CUDA top-k == oracle scores -> oracle top-k
+    (well defined because fp32 error ~1e-7 << top-k score gaps ~1e-5)."""
+    cfg = CONFIGS["charadessta"]
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, 8, 51)
+    model = model_for(cfg, "fp32", params)
+    pm, ps, pe, pa = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    got = compute_ious(pm, ps, pe, batch["moment_mask"].cuda(), batch["sm"].cuda())
+    with torch.no_grad():
+        rpm, rps, rpe, _ = oracle_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS])
+    scores = mo.proposal_scores(rpm, rps, rpe, batch["moment_mask"])
+    srt = scores.sort(dim=1, descending=True)[0][:, :6]
+    gaps = (srt[:, :-1] - srt[:, 1:]).min().item()
+    top_idx = score_topk_recall(pm, ps, pe, batch["moment_mask"].cuda(), batch["sm"].cuda())[0]
+    if gaps > 1e-6:   # otherwise the comparison is not well defined for this draw
+        assert torch.equal(top_idx.cpu().long(), mo.topk_lowest_index(scores, 5))
+        assert dict(got) == mo.compute_ious(rpm, rps, rpe, batch["moment_mask"], batch["sm"])
+
+
+def test_bf16_kernel_isolated_indices_exact():
+    """bf16 mode: feed the oracle metric the SAME score tensors the CUDA path produced."""
+    cfg = CONFIGS["charadessta"]
+    batch = synth.make_batch(cfg, 8, 52)
+    model = model_for(cfg, "bf16")
+    pm, ps, pe, pa = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+    top_idx = score_topk_recall(pm, ps, pe, batch["moment_mask"].cuda(), batch["sm"].cuda())[0]
+    scores = mo.proposal_scores(pm.cpu(), ps.cpu(), pe.cpu(), batch["moment_mask"])
+    assert torch.equal(top_idx.cpu().long(), mo.topk_lowest_index(scores, 5))
+    got = compute_ious(pm, ps, pe, batch["moment_mask"].cuda(), batch["sm"].cuda())
+    assert dict(got) == mo.compute_ious(pm.cpu(), ps.cpu(), pe.cpu(), batch["moment_mask"], batch["sm"])

@@ -1,0 +1,86 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares,
+the drop-in module honours the reference's state_dict contract, host logic."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from oracle import CONFIGS, init_params
+from vml_b200 import lib as L_
+from vml_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    if not os.path.exists(L_.LIB_PATH):
+        from vml_b200 import build
+        build.build()
+    return ctypes.CDLL(L_.LIB_PATH)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    names = L_.declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in include/vml_b200.h but not exported"
+    assert set(L_._SIGS) == set(names), "ctypes table and header disagree"
+
+
+def test_library_loads_without_gpu_and_reports_version(built_lib):
+    lib = L_.load()
+    assert lib.vml_version() >= 1
+    assert isinstance(lib.vml_last_error(), bytes)
+
+
+@pytest.mark.parametrize("name", ["charadessta", "activitynet", "tacos", "tiny"])
+def test_state_dict_contract(name):
+    from vml_b200.smin import SMIN
+    cfg = CONFIGS[name]
+    m = SMIN(*cfg.ctor_args())
+    ref = init_params(cfg, 43)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert len(sd) == 47 + 20 * (cfg.layers - 1)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    m.load_state_dict(ref, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == sum(v.numel() for v in ref.values())
+
+
+def test_constructor_validates_like_the_reference_needs():
+    from vml_b200.smin import SMIN
+    with pytest.raises(ValueError):
+        SMIN(64, 16, 4, 512, 128, 3, 1024, 13, 128)      # D != 2H breaks models.py:81
+    with pytest.raises(ValueError):
+        SMIN(60, 16, 4, 512, 128, 3, 1024, 13, 256)      # L must divide T
+
+
+def test_no_cpu_fallback():
+    from vml_b200.smin import SMIN
+    from vml_b200.evaluate import compute_ious
+    from vml_b200.losses import loss_fn
+    cfg = CONFIGS["tiny"]
+    b = synth.make_batch(cfg, 2, 1)
+    m = SMIN(*cfg.ctor_args())
+    with pytest.raises(L_.VmlError):
+        m(*[b[k] for k in synth.MODEL_INPUT_KEYS])
+    z = torch.zeros(2, cfg.L, cfg.L)
+    with pytest.raises(L_.VmlError):
+        compute_ious(z, z[:, 0], z[:, 0], b["moment_mask"], b["sm"])
+    with pytest.raises(L_.VmlError):
+        loss_fn(z, b["ym"], b["sm"], b["moment_mask"], z[:, 0], b["ys"], b["ss"], z[:, 0], b["ye"], b["se"], z[:, 0], b["ya"], b["length_mask"])
+
+
+def test_synth_batch_properties():
+    cfg = CONFIGS["charadessta"]
+    b = synth.make_batch(cfg, 8, 5)
+    r = cfg.T // cfg.L
+    assert b["nfeats"][0] == cfg.T and b["nfeats"][1] % r != 0
+    assert torch.equal(b["length_mask"].sum(1), torch.ceil(b["nfeats"].float() / r).long())
+    assert torch.equal(b["moment_mask"], torch.triu(b["length_mask"][:, :, None] & b["length_mask"][:, None, :]))
+    assert (b["video_features"][~b["video_mask"].bool().expand_as(b["video_features"])] == 0).all()
+    assert (b["query_mask"].sum((1, 2)) >= 3).all()
+    b2 = synth.make_batch(cfg, 8, 5)
+    assert all(torch.equal(b[k], b2[k]) for k in b)
+    assert (b["length_mask"].sum(1) >= 3).all()          # >= 5 valid cells: top-5 well defined

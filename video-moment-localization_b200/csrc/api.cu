@@ -1,0 +1,234 @@
+// extern "C" boundary of libvml_b200.so (see include/vml_b200.h) and the GEMM-backed stages.
+#include <stdarg.h>
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_umma.cuh"
+
+namespace vml {
+
+// ---- error / registry ---------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::mutex g_reg_mu;
+static std::string g_kernels;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void register_kernel(const char* name) {
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  if (g_kernels.find(std::string(name) + "\n") == std::string::npos) g_kernels += std::string(name) + "\n";
+}
+
+// ---- TMA descriptor ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t k, uint64_t row_stride_elems, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VML_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)UG_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (rows=%llu k=%llu ld=%llu)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)k, (unsigned long long)row_stride_elems);
+    return VML_ERR_CUDA; }
+  return VML_OK;
+}
+
+// stage launchers implemented in stages.cu / query_loss_eval.cu
+int build_cells(const uint8_t*, int, int, vml_cells_t, cudaStream_t);
+int unpack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
+int pack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
+int cast_pad(const float*, void*, int64_t, int, int, cudaStream_t);
+int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*, int, vml_dims_t, int, cudaStream_t);
+int content_attention(const void*, const float*, const float*, const float*, const float*, const uint8_t*, vml_cells_t,
+                      void*, int, vml_dims_t, int, cudaStream_t);
+int query_prep(const float*, int, int, const float*, const uint8_t*, const float*, const float*, const float*,
+               const float*, const float*, const float*, float*, float*, float*, float*, int, vml_dims_t, cudaStream_t);
+int boundary_unit(const float*, const float*, int, int, const float*, const float*, const float*, const void*,
+                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, int, vml_dims_t, int, cudaStream_t);
+int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
+int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
+             float*, int, vml_dims_t, int, cudaStream_t);
+int query_lengths(const uint8_t*, int32_t*, int, int, cudaStream_t);
+int lstm_layer(const float*, const float*, const int32_t*, float*, void*, float*, int, int, int, cudaStream_t);
+int scaled_iou_bce(const float*, const uint8_t*, const float*, const uint8_t*, const float*, const uint8_t*, const float*,
+                   const float*, const uint8_t*, const float*, const float*, const uint8_t*, const uint8_t*, int, int,
+                   float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
+int score_topk_recall(const float*, const float*, const float*, const uint8_t*, const float*, int, int, int, int, int,
+                      int32_t*, float*, float*, int64_t*, cudaStream_t);
+
+// generic dispatch: fp32 -> CUDA-core GEMM, bf16 -> tcgen05 GEMM
+template <typename Epi>
+static int gemm_dispatch(const void* A, const void* W, int M, int N, int K, int lda, const int32_t* m_dev, int m_scale,
+                         const Epi& epi, int prec, cudaStream_t st) {
+  if (prec == VML_BF16) return launch_gemm_umma(A, W, M, N, K, lda, K, m_dev, m_scale, epi, st);
+  VML_CHECK_ARG(lda == K);
+  return launch_gemm_simt((const float*)A, (const float*)W, M, N, K, m_dev, m_scale, epi, st);
+}
+
+}  // namespace vml
+
+using namespace vml;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define VML_PREC_OK(p) VML_CHECK_ARG((p) == VML_FP32 || (p) == VML_BF16)
+
+extern "C" {
+
+VML_API const char* vml_last_error(void) { return g_err; }
+VML_API int vml_version(void) { return 1; }
+VML_API const char* vml_kernel_names(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  copy = g_kernels;
+  return copy.c_str();
+}
+
+VML_API int vml_build_cells(const uint8_t* moment_mask, int B, int L, vml_cells_t cells, void* stream) {
+  return build_cells(moment_mask, B, L, cells, ST(stream));
+}
+VML_API int vml_unpack_cells(const void* packed, void* dense, vml_cells_t cells, int B, int L, int inner, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return unpack_cells(packed, dense, cells, B, L, inner, prec, ST(stream));
+}
+VML_API int vml_pack_cells(const void* dense, void* packed, vml_cells_t cells, int B, int L, int inner, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return pack_cells(dense, packed, cells, B, L, inner, prec, ST(stream));
+}
+VML_API int vml_cast_pad_bf16(const float* src, void* dst, int64_t rows, int k, int k_pad, void* stream) {
+  return cast_pad(src, dst, rows, k, k_pad, ST(stream));
+}
+
+VML_API int vml_linear(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
+               const int32_t* m_dev, int m_scale, int prec, int out_fp32, void* stream) {
+  VML_PREC_OK(prec);
+  VML_CHECK_ARG(ldo >= N && ldo % 4 == 0 && m_scale >= 1);
+  if (prec == VML_BF16 && !out_fp32) {
+    EpiBias<bf16> e{bias, (bf16*)out, ldo};
+    return gemm_dispatch(A, W, M, N, K, K, m_dev, m_scale, e, prec, ST(stream));
+  }
+  EpiBias<float> e{bias, (float*)out, ldo};
+  return gemm_dispatch(A, W, M, N, K, K, m_dev, m_scale, e, prec, ST(stream));
+}
+
+VML_API int vml_clip_projection(const void* v, const void* W, const float* bias, const float* pe, const uint8_t* video_mask,
+                        void* fv, int B, vml_dims_t d, int k_pad, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  const int M = B * d.T;
+  if (prec == VML_BF16) {
+    EpiClip<bf16> e{bias, pe, video_mask, d.T, (bf16*)fv, d.D};
+    return launch_gemm_umma(v, W, M, d.D, k_pad, k_pad, k_pad, nullptr, 1, e, ST(stream));
+  }
+  EpiClip<float> e{bias, pe, video_mask, d.T, (float*)fv, d.D};
+  return launch_gemm_simt((const float*)v, (const float*)W, M, d.D, d.d0, nullptr, 1, e, ST(stream));
+}
+
+VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16, float* fs, int B,
+                   int Nq, int H, void* stream) {
+  return lstm_layer(gin, whh_t, qlen, y, y_bf16, fs, B, Nq, H, ST(stream));
+}
+VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, int Nq, void* stream) {
+  return query_lengths(query_mask, qlen, B, Nq, ST(stream));
+}
+VML_API int vml_query_prep(const float* wproj, int ld, int col0, const float* fs, const uint8_t* query_mask, const float* Wk,
+                   const float* bk, const float* Wq, const float* bq, const float* Ws, const float* bs, float* w_hat,
+                   float* ktil, float* beta, float* s_hat, int B, vml_dims_t d, void* stream) {
+  return query_prep(wproj, ld, col0, fs, query_mask, Wk, bk, Wq, bq, Ws, bs, w_hat, ktil, beta, s_hat, B, d, ST(stream));
+}
+
+VML_API int vml_span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb, int B,
+                       vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return span_pool_fuse(fv, fs, cells, fc, fm, fb, B, d, prec, ST(stream));
+}
+
+VML_API int vml_content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat,
+                          const float* s_hat, const uint8_t* query_mask, vml_cells_t cells, void* cc_hat, int B,
+                          vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return content_attention(c_hat, ktil, beta, w_hat, s_hat, query_mask, cells, cc_hat, B, d, prec, ST(stream));
+}
+
+VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm, const float* fs,
+                    vml_cells_t cells, void* cu, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  const int M = cells.capacity * d.C;
+  if (prec == VML_BF16) {
+    EpiContentOut<bf16> e{bc, (const bf16*)fc, (const bf16*)fm, fs, cells.code, d.C, (bf16*)cu, d.D};
+    return gemm_dispatch(cc_hat, Wc, M, d.D, d.dl, d.dl, cells.n_cells, d.C, e, prec, ST(stream));
+  }
+  EpiContentOut<float> e{bc, (const float*)fc, (const float*)fm, fs, cells.code, d.C, (float*)cu, d.D};
+  return gemm_dispatch(cc_hat, Wc, M, d.D, d.dl, d.dl, cells.n_cells, d.C, e, prec, ST(stream));
+}
+
+VML_API int vml_boundary_unit(const float* qb, const float* kb, int ldk, int col0, const float* fw, const float* fs,
+                      const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
+                      vml_cells_t cells, float* g_scratch, float* bu, int B, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return boundary_unit(qb, kb, ldk, col0, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, bu, B, d, prec, ST(stream));
+}
+
+VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return moment_operand(cu, bu, cells, operand, d, prec, ST(stream));
+}
+
+VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* bias_sum, const void* fm, vml_cells_t cells,
+                   void* mu, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  if (prec == VML_BF16) {
+    EpiMomentOut<bf16> e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D};
+    return gemm_dispatch(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, prec, ST(stream));
+  }
+  EpiMomentOut<float> e{bias_sum, (const float*)fm, (float*)mu, d.D};
+  return gemm_dispatch(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, prec, ST(stream));
+}
+
+VML_API int vml_localize(const void* fm, const float* fb, const float* w4, const float* b4, vml_cells_t cells,
+                 const uint8_t* length_mask, float* pm, float* ps, float* pe, float* pa, int B, vml_dims_t d, int prec,
+                 void* stream) {
+  VML_PREC_OK(prec);
+  return localize(fm, fb, w4, b4, cells, length_mask, pm, ps, pe, pa, B, d, prec, ST(stream));
+}
+
+VML_API int vml_scaled_iou_bce(const float* pm, const uint8_t* ym, const float* sm, const uint8_t* moment_mask, const float* ps,
+                       const uint8_t* ys, const float* ss, const float* pe, const uint8_t* ye, const float* se,
+                       const float* pa, const uint8_t* ya, const uint8_t* length_mask, int B, int L, float* loss,
+                       float* parts, float* scratch, float* g_pm, float* g_ps, float* g_pe, float* g_pa, void* stream) {
+  return scaled_iou_bce(pm, ym, sm, moment_mask, ps, ys, ss, pe, ye, se, pa, ya, length_mask, B, L, loss, parts, scratch,
+                        g_pm, g_ps, g_pe, g_pa, ST(stream));
+}
+
+VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask, const float* sm,
+                          int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score,
+                          float* top_iou, int64_t* counts, void* stream) {
+  return score_topk_recall(pm, ps, pe, moment_mask, sm, B, L, k, nms_num, nms_den, top_idx, top_score, top_iou, counts,
+                           ST(stream));
+}
+
+}  // extern "C"

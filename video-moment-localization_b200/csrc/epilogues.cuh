@@ -1,0 +1,108 @@
+// GEMM epilogues shared by the CUDA-core fp32 GEMM (gemm_simt.cuh) and the tcgen05 bf16 GEMM
+// (gemm_umma.cuh).  An epilogue receives N consecutive fp32 accumulators of one output row
+// and finishes the reference op that follows the contraction.
+#pragma once
+#include "common.cuh"
+
+namespace vml {
+
+// out = acc + bias                                   (nn.Linear, models.py:134-135,236-239 ...)
+template <typename OutT>
+struct EpiBias {
+  const float* bias;  // [N] or nullptr
+  OutT* out;
+  int ldo;
+  template <int N>
+  __device__ __forceinline__ void apply(int row, int col0, const float* acc) const {
+    OutT* o = out + (size_t)row * ldo + col0;
+#pragma unroll
+    for (int c = 0; c < N; c += 4) {
+      float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+      if (bias) { v.x += bias[col0 + c]; v.y += bias[col0 + c + 1]; v.z += bias[col0 + c + 2]; v.w += bias[col0 + c + 3]; }
+      st4(o + c, v);
+    }
+  }
+};
+
+// a1  fv = (acc + bias)*mask + pe[t]*mask             (VideoEncoder.forward, models.py:27-34)
+template <typename OutT>
+struct EpiClip {
+  const float* bias;     // [D]
+  const float* pe;       // [T, D]
+  const uint8_t* vmask;  // [B*T]
+  int T;
+  OutT* out;             // [B*T, D]
+  int ldo;
+  template <int N>
+  __device__ __forceinline__ void apply(int row, int col0, const float* acc) const {
+    const float m = vmask[row] ? 1.0f : 0.0f;
+    const float* p = pe + (size_t)(row % T) * ldo + col0;
+    OutT* o = out + (size_t)row * ldo + col0;
+#pragma unroll
+    for (int c = 0; c < N; c += 4) {
+      float4 v;
+      v.x = (acc[c] + bias[col0 + c]) * m + p[c] * m;
+      v.y = (acc[c + 1] + bias[col0 + c + 1]) * m + p[c + 1] * m;
+      v.z = (acc[c + 2] + bias[col0 + c + 2]) * m + p[c + 2] * m;
+      v.w = (acc[c + 3] + bias[col0 + c + 3]) * m + p[c + 3] * m;
+      st4(o + c, v);
+    }
+  }
+};
+
+// a6 tail  cu = (acc + bias) + fc + sigmoid(fm*fs)*fm   (ContentUnit.forward, models.py:269-276)
+// rows are (cell, clip) pairs: row = cell*C + c.
+template <typename ActT>
+struct EpiContentOut {
+  const float* bias;   // [D]
+  const ActT* fc;      // [n*C, D]
+  const ActT* fm;      // [n, D]
+  const float* fs;     // [B, D]
+  const int32_t* code; // [n]
+  int C;
+  ActT* out;           // [n*C, D]
+  int ldo;             // D
+  template <int N>
+  __device__ __forceinline__ void apply(int row, int col0, const float* acc) const {
+    const int cell = row / C;
+    const int b = code[cell] >> 16;
+    const ActT* x = fc + (size_t)row * ldo + col0;
+    const ActT* m = fm + (size_t)cell * ldo + col0;
+    const float* s = fs + (size_t)b * ldo + col0;
+    ActT* o = out + (size_t)row * ldo + col0;
+#pragma unroll
+    for (int c = 0; c < N; c += 4) {
+      float4 xv = ld4(x + c), mv = ld4(m + c), sv = ld4(s + c), v;
+      v.x = (acc[c] + bias[col0 + c]) + xv.x + sigmoidf_(mv.x * sv.x) * mv.x;
+      v.y = (acc[c + 1] + bias[col0 + c + 1]) + xv.y + sigmoidf_(mv.y * sv.y) * mv.y;
+      v.z = (acc[c + 2] + bias[col0 + c + 2]) + xv.z + sigmoidf_(mv.z * sv.z) * mv.z;
+      v.w = (acc[c + 3] + bias[col0 + c + 3]) + xv.w + sigmoidf_(mv.w * sv.w) * mv.w;
+      st4(o + c, v);
+    }
+  }
+};
+
+// a8 tail  mu = (acc + (b_fb + b_fc)) + fm                (MomentUnit.forward, models.py:299-303)
+template <typename ActT>
+struct EpiMomentOut {
+  const float* bias;  // [D] = b_fb + b_fc
+  const ActT* fm;     // [n, D]
+  ActT* out;          // [n, D]
+  int ldo;
+  template <int N>
+  __device__ __forceinline__ void apply(int row, int col0, const float* acc) const {
+    const ActT* m = fm + (size_t)row * ldo + col0;
+    ActT* o = out + (size_t)row * ldo + col0;
+#pragma unroll
+    for (int c = 0; c < N; c += 4) {
+      float4 mv = ld4(m + c), v;
+      v.x = (acc[c] + bias[col0 + c]) + mv.x;
+      v.y = (acc[c + 1] + bias[col0 + c + 1]) + mv.y;
+      v.z = (acc[c + 2] + bias[col0 + c + 2]) + mv.z;
+      v.w = (acc[c + 3] + bias[col0 + c + 3]) + mv.w;
+      st4(o + c, v);
+    }
+  }
+};
+
+}  // namespace vml

@@ -1,0 +1,169 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  out = A[M,K] . W[N,K]^T (+ epilogue), bf16 operands,
+// fp32 accumulation in tensor memory.
+//
+// Persistent, warp-specialised CTA (192 threads):
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
+//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+// Pipelines: smem full/empty ring (STAGES), TMEM full/empty double buffer (2 accumulators),
+// so the epilogue of tile i overlaps the mainloop of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace vml {
+
+constexpr int UG_BM = 128, UG_BK = 64, UG_THREADS = 192;
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int STAGES = BN >= 128 ? 5 : 6;
+  static constexpr int A_BYTES = UG_BM * UG_BK * 2;
+  static constexpr int B_BYTES = BN * UG_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);   // power of two for BN in {16,32,64,128,256}
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
+  using Cfg = UmmaCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (m_dev) M = min(M, *m_dev * m_scale);
+  const int tiles_m = (M + UG_BM - 1) / UG_BM, tiles_n = N / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int k_blocks = (K + UG_BK - 1) / UG_BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * UG_BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * UG_BK, m0);
+          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * UG_BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(UG_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
+          const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < UG_BK / 16; ++k)  // +32 B per K=16 step inside the 128B swizzle atom
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty_bar[stage]);             // frees the smem stage when the MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp % 4;                             // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * UG_BM, n0 = (tile % tiles_n) * BN;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        ptx::tmem_ld32(t_addr + (uint32_t)c, v);
+        ptx::tmem_ld_wait();
+        if (row < M) epi.template apply<32>(row, n0 + c, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+// 2D bf16 tensor map, inner dimension = K (contiguous), 128B swizzle, box = {64, box_rows}.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t k, uint64_t row_stride_elems, uint32_t box_rows);
+
+template <int BN, typename Epi>
+int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int32_t* m_dev,
+                        int m_scale, const Epi& epi, cudaStream_t stream) {
+  using Cfg = UmmaCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, UG_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VML_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  gemm_umma_kernel<BN, Epi><<<grid, UG_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// A: bf16 [M, lda] (K <= lda), W: bf16 [N, ldw].  M is the capacity; live rows = *m_dev * m_scale.
+template <typename Epi>
+int launch_gemm_umma(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int32_t* m_dev,
+                     int m_scale, const Epi& epi, cudaStream_t stream) {
+  VML_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 32 == 0);
+  VML_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (M <= 0) return VML_OK;
+  static bool reg = (register_kernel("gemm_umma_kernel"), true);
+  (void)reg;
+  if (N % 128 == 0) return launch_gemm_umma_bn<128, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  if (N % 64 == 0) return launch_gemm_umma_bn<64, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  return launch_gemm_umma_bn<32, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+}
+
+}  // namespace vml

@@ -1,0 +1,703 @@
+// Non-GEMM stages of the SMIN hot path: cell compaction, fused span pooling + fusion,
+// content-word attention, boundary unit, moment-unit operand build, localization.
+// Each kernel is templated on the activation storage type (float = validation mode,
+// bf16 = fast mode); all arithmetic is fp32.
+#include "common.cuh"
+
+namespace vml {
+
+// =====================================================================================
+// cell compaction:  moment_mask[B,L,L] -> sorted list of valid cells
+// =====================================================================================
+__global__ void cells_count_kernel(const uint8_t* __restrict__ mask, int rows, int L, int32_t* __restrict__ cnt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= rows) return;
+  const uint8_t* m = mask + (size_t)warp * L;
+  int c = 0;
+  for (int j = lane; j < L; j += 32) c += m[j] ? 1 : 0;
+  c = (int)warp_sum((float)c);  // L <= 256: exact in fp32
+  if (lane == 0) cnt[warp] = c;
+}
+
+// single block: exclusive scan of cnt[rows] -> row_start[rows+1]; n_cells = min(total, capacity)
+__global__ void cells_scan_kernel(int32_t* __restrict__ row_start, int rows, int32_t* __restrict__ n_cells,
+                                  int32_t* __restrict__ status, int capacity) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (rows + nt - 1) / nt;
+  const int lo = min(tid * per, rows), hi = min(lo + per, rows);
+  int s = 0;
+  for (int r = lo; r < hi; ++r) s += row_start[r];
+  part[tid] = s;
+  __syncthreads();
+  for (int off = 1; off < nt; off <<= 1) {  // Hillis-Steele inclusive scan
+    int v = tid >= off ? part[tid - off] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int run = part[tid] - s;
+  for (int r = lo; r < hi; ++r) { int c = row_start[r]; row_start[r] = run; run += c; }
+  if (tid == nt - 1) {
+    const int total = part[tid];
+    row_start[rows] = total;
+    n_cells[0] = min(total, capacity);
+    status[0] = total > capacity ? 1 : 0;
+  }
+}
+
+__global__ void cells_fill_kernel(const uint8_t* __restrict__ mask, int rows, int L,
+                                  const int32_t* __restrict__ row_start, int32_t* __restrict__ code, int capacity) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= rows) return;
+  const uint8_t* m = mask + (size_t)warp * L;
+  const int b = warp / L, i = warp % L;
+  int base = row_start[warp];
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    const int j = j0 + lane;
+    const bool on = j < L && m[j];
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (on) {
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (pos < capacity) code[pos] = (b << 16) | (i << 8) | j;
+    }
+    base += __popc(bal);
+  }
+}
+
+int build_cells(const uint8_t* mask, int B, int L, vml_cells_t cells, cudaStream_t st) {
+  VML_CHECK_ARG(B > 0 && B < 32768 && L > 0 && L <= 256 && cells.capacity > 0);
+  static bool reg = (register_kernel("cells_count_kernel"), register_kernel("cells_scan_kernel"),
+                     register_kernel("cells_fill_kernel"), true);
+  (void)reg;
+  const int rows = B * L;
+  const int blocks = ceil_div(rows * 32, 256);
+  cells_count_kernel<<<blocks, 256, 0, st>>>(mask, rows, L, cells.row_start);
+  cells_scan_kernel<<<1, 1024, 0, st>>>(cells.row_start, rows, cells.n_cells, cells.status, cells.capacity);
+  cells_fill_kernel<<<blocks, 256, 0, st>>>(mask, rows, L, cells.row_start, cells.code, cells.capacity);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// packed <-> dense helpers ---------------------------------------------------------------
+template <typename T>
+__global__ void unpack_cells_kernel(const T* __restrict__ packed, T* __restrict__ dense, const int32_t* __restrict__ code,
+                                    const int32_t* __restrict__ n_cells, int L, int inner) {
+  const int n = *n_cells;
+  for (int c = blockIdx.x; c < n; c += gridDim.x) {
+    int b, i, j; decode_cell(code[c], b, i, j);
+    const T* s = packed + (size_t)c * inner;
+    T* d = dense + (((size_t)b * L + i) * L + j) * inner;
+    for (int e = threadIdx.x; e < inner; e += blockDim.x) d[e] = s[e];
+  }
+}
+template <typename T>
+__global__ void pack_cells_kernel(const T* __restrict__ dense, T* __restrict__ packed, const int32_t* __restrict__ code,
+                                  const int32_t* __restrict__ n_cells, int L, int inner) {
+  const int n = *n_cells;
+  for (int c = blockIdx.x; c < n; c += gridDim.x) {
+    int b, i, j; decode_cell(code[c], b, i, j);
+    T* d = packed + (size_t)c * inner;
+    const T* s = dense + (((size_t)b * L + i) * L + j) * inner;
+    for (int e = threadIdx.x; e < inner; e += blockDim.x) d[e] = s[e];
+  }
+}
+
+int unpack_cells(const void* packed, void* dense, vml_cells_t cells, int B, int L, int inner, int prec, cudaStream_t st) {
+  static bool reg = (register_kernel("unpack_cells_kernel"), true); (void)reg;
+  const size_t esz = prec == VML_BF16 ? 2 : 4;
+  VML_CUDA(cudaMemsetAsync(dense, 0, (size_t)B * L * L * inner * esz, st));
+  const int grid = min(cells.capacity, kNumSMs * 16);
+  if (prec == VML_BF16) unpack_cells_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)packed, (bf16*)dense, cells.code, cells.n_cells, L, inner);
+  else unpack_cells_kernel<float><<<grid, 128, 0, st>>>((const float*)packed, (float*)dense, cells.code, cells.n_cells, L, inner);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+int pack_cells(const void* dense, void* packed, vml_cells_t cells, int B, int L, int inner, int prec, cudaStream_t st) {
+  static bool reg = (register_kernel("pack_cells_kernel"), true); (void)reg;
+  const int grid = min(cells.capacity, kNumSMs * 16);
+  if (prec == VML_BF16) pack_cells_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)dense, (bf16*)packed, cells.code, cells.n_cells, L, inner);
+  else pack_cells_kernel<float><<<grid, 128, 0, st>>>((const float*)dense, (float*)packed, cells.code, cells.n_cells, L, inner);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// fp32 -> bf16 with zero padding of the row to k_pad -------------------------------------
+__global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int k, int k_pad) {
+  const int64_t total = rows * (k_pad / 4);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / (k_pad / 4);
+    const int c = (int)(e % (k_pad / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 3 < k) v = *reinterpret_cast<const float4*>(src + r * k + c);
+    else {
+      if (c < k) v.x = src[r * k + c];
+      if (c + 1 < k) v.y = src[r * k + c + 1];
+      if (c + 2 < k) v.z = src[r * k + c + 2];
+    }
+    st4(dst + r * k_pad + c, v);
+  }
+}
+int cast_pad(const float* src, void* dst, int64_t rows, int k, int k_pad, cudaStream_t st) {
+  VML_CHECK_ARG(k % 4 == 0 && k_pad % 4 == 0 && k_pad >= k);
+  static bool reg = (register_kernel("cast_pad_kernel"), true); (void)reg;
+  if (rows <= 0) return VML_OK;
+  const int64_t total = rows * (k_pad / 4);
+  const int64_t want = ceil_div64(total, 256), cap = (int64_t)kNumSMs * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  cast_pad_kernel<<<grid, 256, 0, st>>>(src, (bf16*)dst, rows, k, k_pad);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// =====================================================================================
+// a3+a4  fused  f = fv*fs  +  span pooling over clips   (models.py:81,88-98,115-126)
+//
+// One CTA per (sample, D-slice).  The slice of the fused clip sequence is turned into an
+// inclusive prefix sum over t in shared memory (fp32); every pooled clip of every valid cell
+// is then a difference of two prefix rows times fp32(1/clip_size) -- exactly the non-zero
+// pattern of the reference's dense Wc -- and only valid (b,i,j) cells are stored, with
+// 128-bit stores.  fm = mean_c fc (always / C), fb = average pool over T/L clips.
+// =====================================================================================
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, const int32_t* __restrict__ code,
+                 const int32_t* __restrict__ row_start, ActT* __restrict__ fc, ActT* __restrict__ fm,
+                 float* __restrict__ fb, int T, int L, int C, int D, int dslice, int capacity) {
+  extern __shared__ __align__(16) float P[];  // [(T+1)][dslice]
+  const int b = blockIdx.x, d0 = blockIdx.y * dslice;
+  const int tid = threadIdx.x;
+  const int r = T / L;
+
+  // prefix sums of fv*fs along t, one column per thread (coalesced across the slice)
+  for (int d = tid; d < dslice; d += blockDim.x) {
+    const float s = fs[(size_t)b * D + d0 + d];
+    const ActT* col = fv + (size_t)b * T * D + d0 + d;
+    float run = 0.f;
+    P[d] = 0.f;
+    int t = 0;
+    for (; t + 8 <= T; t += 8) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = to_f(col[(size_t)(t + u) * D]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { run += x[u] * s; P[(size_t)(t + u + 1) * dslice + d] = run; }
+    }
+    for (; t < T; ++t) { run += to_f(col[(size_t)t * D]) * s; P[(size_t)(t + 1) * dslice + d] = run; }
+  }
+  __syncthreads();
+
+  const int groups = dslice / 8;             // 8 columns per thread
+  const int g = tid % groups, lane_cell = tid / groups, cells_per_iter = blockDim.x / groups;
+  const int dd = g * 8;
+
+  // fb: unmasked average pool (models.py:120-125)
+  const float inv_r = 1.0f / (float)r;
+  for (int l = lane_cell; l < L; l += cells_per_iter) {
+    const float* hi = P + (size_t)((l + 1) * r) * dslice + dd;
+    const float* lo = P + (size_t)(l * r) * dslice + dd;
+    f8 a = ld8(hi), c = ld8(lo), o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = (a.v[e] - c.v[e]) * inv_r;
+    st8(fb + ((size_t)b * L + l) * D + d0 + dd, o);
+  }
+
+  const int n_lo = row_start[b * L], n_hi = min(row_start[(b + 1) * L], capacity);
+  const float inv_C = 1.0f / (float)C;
+  for (int n = n_lo + lane_cell; n < n_hi; n += cells_per_iter) {
+    const int cd = code[n];
+    const int i = (cd >> 8) & 0xff, j = cd & 0xff;
+    const int nf = (j - i + 1) * r;
+    const int cs = max(1, nf / C);
+    const int nclips = min(C, nf);           // <= 0 below the diagonal -> all-zero cell
+    const float w = 1.0f / (float)cs;        // fp32(1/clip_size), as the reference's Wc
+    f8 mean;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mean.v[e] = 0.f;
+    const int s0 = i * r;
+    ActT* fc_row = fc + ((size_t)n * C) * D + d0 + dd;
+    for (int c = 0; c < C; ++c) {
+      f8 o;
+      if (c < nclips) {
+        f8 a = ld8(P + (size_t)(s0 + (c + 1) * cs) * dslice + dd);
+        f8 z = ld8(P + (size_t)(s0 + c * cs) * dslice + dd);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { o.v[e] = (a.v[e] - z.v[e]) * w; mean.v[e] += o.v[e]; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = 0.f;
+      }
+      st8(fc_row + (size_t)c * D, o);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mean.v[e] *= inv_C;
+    st8(fm + (size_t)n * D + d0 + dd, mean);
+  }
+}
+
+int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb, int B,
+                   vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.T % d.L == 0 && d.D % 8 == 0 && d.C >= 1);
+  static bool reg = (register_kernel("span_pool_kernel"), true); (void)reg;
+  // largest D-slice (multiple of 8 dividing D) whose prefix table fits in 200 KB and that
+  // still yields >= 2 CTAs per SM
+  int dslice = d.D;
+  auto fits = [&](int s) { return (size_t)(d.T + 1) * s * 4 <= 200 * 1024; };
+  while (dslice > 8 && (dslice % 16 == 0) && (!fits(dslice) || (int64_t)B * (d.D / dslice) < 2 * kNumSMs)) dslice /= 2;
+  VML_CHECK_ARG(fits(dslice) && d.D % dslice == 0 && dslice % 8 == 0 && dslice / 8 <= 256);
+  const size_t smem = (size_t)(d.T + 1) * dslice * 4;
+  dim3 grid(B, d.D / dslice);
+  if (prec == VML_BF16) {
+    VML_CUDA(cudaFuncSetAttribute(span_pool_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    span_pool_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)fv, fs, cells.code, cells.row_start, (bf16*)fc,
+                                                    (bf16*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
+  } else {
+    VML_CUDA(cudaFuncSetAttribute(span_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    span_pool_kernel<float><<<grid, 256, smem, st>>>((const float*)fv, fs, cells.code, cells.row_start, (float*)fc,
+                                                     (float*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
+  }
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// =====================================================================================
+// a5+a6 (middle)  content-word attention, gate, CxC self-attention
+//   (ContentAttention.forward models.py:207-226; ContentUnit.forward models.py:253-266)
+// One warp per cell (C = 4 clips x dl features); lane k owns query word k in the score phase
+// and dl/32 feature columns elsewhere.  Q.K^T is evaluated as c_hat.ktil^T + beta with the
+// per-sample ktil = (w_hat.Wk^T + bk).Wq hoisted to vml_query_prep.
+// =====================================================================================
+template <typename ActT, int DPL>
+__global__ void __launch_bounds__(256)
+content_attention_kernel(const ActT* __restrict__ c_hat, const float* __restrict__ ktil, const float* __restrict__ beta,
+                         const float* __restrict__ w_hat, const float* __restrict__ s_hat,
+                         const uint8_t* __restrict__ qmask, const int32_t* __restrict__ row_start,
+                         ActT* __restrict__ cc_hat, int L, int Nq, int capacity) {
+  constexpr int C = 4, DL = DPL * 32, KS = DL + 1;
+  extern __shared__ __align__(16) float sm[];
+  float* s_k = sm;                      // [Nq][DL+1]   ktil (padded: lane k reads row k)
+  float* s_w = s_k + Nq * KS;           // [Nq][DL]     w_hat
+  float* s_s = s_w + Nq * DL;           // [DL]         s_hat
+  float* s_b = s_s + DL;                // [32]         beta
+  float* s_m = s_b + 32;                // [32]         qmask as float
+  float* s_c = s_m + 32;                // [warps][C][DL] c_hat staging
+  float* s_p = s_c + 8 * C * DL;        // [warps][C][32] attention probabilities
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+
+  for (int e = tid; e < Nq * DL; e += blockDim.x) {
+    const int k = e / DL, dcol = e % DL;
+    s_k[k * KS + dcol] = ktil[((size_t)b * Nq + k) * DL + dcol];
+    s_w[e] = w_hat[((size_t)b * Nq) * DL + e];
+  }
+  for (int e = tid; e < DL; e += blockDim.x) s_s[e] = s_hat[(size_t)b * DL + e];
+  if (tid < 32) {
+    s_b[tid] = tid < Nq ? beta[(size_t)b * Nq + tid] : 0.f;
+    s_m[tid] = tid < Nq ? (qmask[(size_t)b * Nq + tid] ? 1.f : 0.f) : 0.f;
+  }
+  __syncthreads();
+
+  const int n_lo = row_start[b * L], n_hi = min(row_start[(b + 1) * L], capacity);
+  float* my_c = s_c + warp * C * DL;
+  float* my_p = s_p + warp * C * 32;
+  const float sqrt_dl = sqrtf((float)DL);
+  const int dcol = lane * DPL;
+
+  for (int n = n_lo + blockIdx.x * 8 + warp; n < n_hi; n += gridDim.x * 8) {
+    float ch[C][DPL];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const ActT* src = c_hat + ((size_t)n * C + c) * DL + dcol;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) { ch[c][e] = to_f(src[e]); my_c[c * DL + dcol + e] = ch[c][e]; }
+    }
+    __syncwarp();
+    // scores: lane k <-> word k
+    float sc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) sc[c] = 0.f;
+    if (lane < Nq) {
+      const float* kr = s_k + lane * KS;
+      for (int dd = 0; dd < DL; ++dd) {
+        const float kv = kr[dd];
+#pragma unroll
+        for (int c = 0; c < C; ++c) sc[c] = fmaf(my_c[c * DL + dd], kv, sc[c]);
+      }
+    }
+    const float mk = s_m[lane], bt = s_b[lane];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float s = (sc[c] + bt) / sqrt_dl;
+      s = s * mk;
+      if (mk == 0.f) s = -1e9f;                      // masked_fill(mask == 0, -1e9)
+      if (lane >= Nq) s = -INFINITY;                 // not a word at all
+      const float mx = warp_max(s);
+      const float ex = lane < Nq ? expf(s - mx) : 0.f;
+      const float den = warp_sum(ex);
+      my_p[c * 32 + lane] = ex / den;
+    }
+    __syncwarp();
+    // attended words + gate
+    float g[C][DPL];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) g[c][e] = 0.f;
+    for (int k = 0; k < Nq; ++k) {
+      float wv[DPL];
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) wv[e] = s_w[k * DL + dcol + e];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float p = my_p[c * 32 + k];
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) g[c][e] = fmaf(p, wv[e], g[c][e]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) g[c][e] = ch[c][e] * (g[c][e] + s_s[dcol + e]);
+    // CxC self-attention over the clips of this cell
+    float a[C][C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int c2 = c; c2 < C; ++c2) {
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) p = fmaf(g[c][e], g[c2][e], p);
+        p = warp_sum(p) / sqrt_dl;
+        a[c][c2] = p; a[c2][c] = p;
+      }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float mx = a[c][0];
+#pragma unroll
+      for (int c2 = 1; c2 < C; ++c2) mx = fmaxf(mx, a[c][c2]);
+      float den = 0.f;
+#pragma unroll
+      for (int c2 = 0; c2 < C; ++c2) { a[c][c2] = expf(a[c][c2] - mx); den += a[c][c2]; }
+#pragma unroll
+      for (int c2 = 0; c2 < C; ++c2) a[c][c2] /= den;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      ActT* dst = cc_hat + ((size_t)n * C + c) * DL + dcol;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) {
+        float o = 0.f;
+#pragma unroll
+        for (int c2 = 0; c2 < C; ++c2) o = fmaf(a[c][c2], ch[c2][e], o);
+        dst[e] = from_f<ActT>(o);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <typename ActT, int DPL>
+static int launch_content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat,
+                                    const float* s_hat, const uint8_t* qmask, vml_cells_t cells, void* cc_hat, int B,
+                                    vml_dims_t d, cudaStream_t st) {
+  constexpr int DL = DPL * 32;
+  const size_t smem = sizeof(float) * ((size_t)d.Nq * (DL + 1) + (size_t)d.Nq * DL + DL + 64 + 8 * 4 * DL + 8 * 4 * 32);
+  VML_CUDA(cudaFuncSetAttribute(content_attention_kernel<ActT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int vmax = d.L * (d.L + 1) / 2;
+  int chunks = ceil_div(vmax, 8 * 4);             // ~4 cells per warp
+  while ((int64_t)chunks * B > (int64_t)kNumSMs * 16 && chunks > 1) chunks = (chunks + 1) / 2;
+  dim3 grid(chunks, B);
+  content_attention_kernel<ActT, DPL><<<grid, 256, smem, st>>>((const ActT*)c_hat, ktil, beta, w_hat, s_hat, qmask,
+                                                               cells.row_start, (ActT*)cc_hat, d.L, d.Nq, cells.capacity);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+int content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat, const float* s_hat,
+                      const uint8_t* qmask, vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.C == 4 && d.Nq <= 32 && (d.dl == 32 || d.dl == 64 || d.dl == 128));
+  static bool reg = (register_kernel("content_attention_kernel"), true); (void)reg;
+#define VML_CA(T, P) return launch_content_attention<T, P>(c_hat, ktil, beta, w_hat, s_hat, qmask, cells, cc_hat, B, d, st)
+  if (prec == VML_BF16) { if (d.dl == 128) VML_CA(bf16, 4); if (d.dl == 64) VML_CA(bf16, 2); VML_CA(bf16, 1); }
+  if (d.dl == 128) VML_CA(float, 4); if (d.dl == 64) VML_CA(float, 2); VML_CA(float, 1);
+#undef VML_CA
+}
+
+// =====================================================================================
+// query-side precompute for the ContentUnit (models.py:249-251 and the key half of :209)
+// =====================================================================================
+__global__ void query_prep_kernel(const float* __restrict__ wproj, int ld, int col0, const float* __restrict__ fs,
+                                  const uint8_t* __restrict__ qmask, const float* __restrict__ Wk, const float* __restrict__ bk,
+                                  const float* __restrict__ Wq, const float* __restrict__ bq, const float* __restrict__ Ws,
+                                  const float* __restrict__ bs, float* __restrict__ w_hat, float* __restrict__ ktil,
+                                  float* __restrict__ beta, float* __restrict__ s_hat, int Nq, int D, int dl) {
+  extern __shared__ float sq[];
+  float* s_w = sq;             // [Nq][dl]  w_hat
+  float* s_kc = s_w + Nq * dl; // [Nq][dl]  kc
+  const int b = blockIdx.x, m = threadIdx.x;  // blockDim.x == dl
+  for (int k = 0; k < Nq; ++k) {
+    const float q = qmask[(size_t)b * Nq + k] ? 1.f : 0.f;
+    const float v = wproj[((size_t)b * Nq + k) * ld + col0 + m] * q;
+    s_w[k * dl + m] = v;
+    w_hat[((size_t)b * Nq + k) * dl + m] = v;
+  }
+  __syncthreads();
+  for (int k = 0; k < Nq; ++k) {          // kc[k][m] = w_hat[k].Wk[m] + bk[m]
+    float acc = 0.f;
+    const float* wr = Wk + (size_t)m * dl;
+    for (int e = 0; e < dl; ++e) acc = fmaf(s_w[k * dl + e], wr[e], acc);
+    s_kc[k * dl + m] = acc + bk[m];
+  }
+  __syncthreads();
+  for (int k = 0; k < Nq; ++k) {          // ktil[k][m] = sum_e kc[k][e] * Wq[e][m]
+    float acc = 0.f;
+    for (int e = 0; e < dl; ++e) acc = fmaf(s_kc[k * dl + e], Wq[(size_t)e * dl + m], acc);
+    ktil[((size_t)b * Nq + k) * dl + m] = acc;
+  }
+  if (m < Nq) {                           // beta[k] = kc[k].bq
+    float acc = 0.f;
+    for (int e = 0; e < dl; ++e) acc = fmaf(s_kc[m * dl + e], bq[e], acc);
+    beta[(size_t)b * Nq + m] = acc;
+  }
+  {                                       // s_hat[m] = fs.Ws[m] + bs[m]
+    float acc = 0.f;
+    const float* wr = Ws + (size_t)m * D;
+    const float* f = fs + (size_t)b * D;
+    for (int e = 0; e < D; ++e) acc = fmaf(f[e], wr[e], acc);
+    s_hat[(size_t)b * dl + m] = acc + bs[m];
+  }
+}
+
+int query_prep(const float* wproj, int ld, int col0, const float* fs, const uint8_t* qmask, const float* Wk,
+               const float* bk, const float* Wq, const float* bq, const float* Ws, const float* bs, float* w_hat,
+               float* ktil, float* beta, float* s_hat, int B, vml_dims_t d, cudaStream_t st) {
+  VML_CHECK_ARG(d.dl >= d.Nq && d.dl <= 1024);
+  static bool reg = (register_kernel("query_prep_kernel"), true); (void)reg;
+  const size_t smem = sizeof(float) * 2 * d.Nq * d.dl;
+  query_prep_kernel<<<B, d.dl, smem, st>>>(wproj, ld, col0, fs, qmask, Wk, bk, Wq, bq, Ws, bs, w_hat, ktil, beta,
+                                          s_hat, d.Nq, d.D, d.dl);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// =====================================================================================
+// a7  BoundaryUnit  (Attention.forward models.py:137-154; BoundaryUnit.forward :164-196)
+// =====================================================================================
+// gate:  G[b,l,:] = fb * (softmax(q.k^T/sqrt(D))·fw * lmask + fs)
+__global__ void __launch_bounds__(128)
+boundary_gate_kernel(const float* __restrict__ qb, const float* __restrict__ kb, int ldk, int col0,
+                     const float* __restrict__ fw, const float* __restrict__ fs, const float* __restrict__ fb,
+                     const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ lmask, float* __restrict__ G,
+                     int L, int Nq, int D) {
+  __shared__ float s_p[32];
+  const int row = blockIdx.x, b = row / L;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const float* q = qb + (size_t)row * D;
+  for (int k = warp; k < Nq; k += 4) {
+    const float* kr = kb + ((size_t)b * Nq + k) * ldk + col0;
+    float acc = 0.f;
+    for (int e = lane; e < D; e += 32) acc = fmaf(q[e], kr[e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_p[k] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float mk = lane < Nq ? (qmask[(size_t)b * Nq + lane] ? 1.f : 0.f) : 0.f;
+    float s = lane < Nq ? s_p[lane] / sqrtf((float)D) : 0.f;
+    s = s * mk;
+    if (mk == 0.f) s = -1e9f;
+    if (lane >= Nq) s = -INFINITY;
+    const float mx = warp_max(s);
+    const float ex = lane < Nq ? expf(s - mx) : 0.f;
+    const float den = warp_sum(ex);
+    __syncwarp();
+    s_p[lane] = ex / den;
+  }
+  __syncthreads();
+  const float lm = lmask[row] ? 1.f : 0.f;
+  for (int e = tid; e < D; e += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < Nq; ++k) acc = fmaf(s_p[k], fw[((size_t)b * Nq + k) * D + e], acc);
+    G[(size_t)row * D + e] = fb[(size_t)row * D + e] * (acc * lm + fs[(size_t)b * D + e]);
+  }
+}
+
+// row:  A_b[i,:] = softmax_j(G_i.G_j/sqrt(D)) (masked) ; bu[i] = A_b[i,:].fb + fb[i] + sum_j A_b[i,j] sigmoid(fm_ij*fs)*fm_ij
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, const float* __restrict__ fs,
+                    const ActT* __restrict__ fm, const uint8_t* __restrict__ lmask, const int32_t* __restrict__ code,
+                    const int32_t* __restrict__ row_start, float* __restrict__ bu, int L, int D, int capacity) {
+  extern __shared__ float s_a[];  // [L]
+  const int row = blockIdx.x, b = row / L;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, nw = blockDim.x / 32;
+  const float* fbi = fb + (size_t)row * D;
+  if (!lmask[row]) {  // A_b row is zeroed by the row mask: bu = 0 + fb + 0
+    for (int e = tid; e < D; e += blockDim.x) bu[(size_t)row * D + e] = fbi[e];
+    return;
+  }
+  const float* gi = G + (size_t)row * D;
+  for (int j = warp; j < L; j += nw) {
+    const float* gj = G + ((size_t)b * L + j) * D;
+    float acc = 0.f;
+    for (int e = lane; e < D; e += 32) acc = fmaf(gi[e], gj[e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float s = acc / sqrtf((float)D);
+      const float mk = lmask[b * L + j] ? 1.f : 0.f;
+      s = s * mk;
+      if (mk == 0.f) s = -1e9f;
+      s_a[j] = s;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int j = lane; j < L; j += 32) mx = fmaxf(mx, s_a[j]);
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int j = lane; j < L; j += 32) { const float ex = expf(s_a[j] - mx); s_a[j] = ex; den += ex; }
+    den = warp_sum(den);
+    for (int j = lane; j < L; j += 32) s_a[j] = s_a[j] / den;
+  }
+  __syncthreads();
+  const int n_lo = row_start[row], n_hi = min(row_start[row + 1], capacity);
+  for (int e = tid; e < D; e += blockDim.x) {
+    float bb = 0.f;
+    for (int j = 0; j < L; ++j) bb = fmaf(s_a[j], fb[((size_t)b * L + j) * D + e], bb);
+    const float s = fs[(size_t)b * D + e];
+    float bm = 0.f;
+    for (int n = n_lo; n < n_hi; ++n) {
+      const int j = code[n] & 0xff;
+      const float m = to_f(fm[(size_t)n * D + e]);
+      bm = fmaf(s_a[j], sigmoidf_(m * s) * m, bm);
+    }
+    bu[(size_t)row * D + e] = (bb + fbi[e]) + bm;
+  }
+}
+
+int boundary_unit(const float* qb, const float* kb, int ldk, int col0, const float* fw, const float* fs,
+                  const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
+                  float* g_scratch, float* bu, int B, vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.Nq <= 32);
+  static bool reg = (register_kernel("boundary_gate_kernel"), register_kernel("boundary_row_kernel"), true); (void)reg;
+  boundary_gate_kernel<<<B * d.L, 128, 0, st>>>(qb, kb, ldk, col0, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
+  const size_t smem = sizeof(float) * d.L;
+  if (prec == VML_BF16)
+    boundary_row_kernel<bf16><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const bf16*)fm, lmask, cells.code,
+                                                          cells.row_start, bu, d.L, d.D, cells.capacity);
+  else
+    boundary_row_kernel<float><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const float*)fm, lmask, cells.code,
+                                                           cells.row_start, bu, d.L, d.D, cells.capacity);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// =====================================================================================
+// a8 operand:  [ bu_i * bu_j | mean_c cu ]   (MomentUnit.forward models.py:292-301)
+// =====================================================================================
+template <typename ActT>
+__global__ void __launch_bounds__(128)
+moment_operand_kernel(const ActT* __restrict__ cu, const float* __restrict__ bu, const int32_t* __restrict__ code,
+                      const int32_t* __restrict__ n_cells, ActT* __restrict__ op, int L, int C, int D) {
+  const int n_total = *n_cells;
+  const int per = D / 8;  // 8-column groups per half
+  for (int n = blockIdx.x; n < n_total; n += gridDim.x) {
+    int b, i, j; decode_cell(code[n], b, i, j);
+    for (int t = threadIdx.x; t < 2 * per; t += blockDim.x) {
+      f8 o;
+      if (t < per) {
+        const int dd = t * 8;
+        f8 x = ld8(bu + ((size_t)b * L + i) * D + dd), y = ld8(bu + ((size_t)b * L + j) * D + dd);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = x.v[e] * y.v[e];
+        st8(op + (size_t)n * 2 * D + dd, o);
+      } else {
+        const int dd = (t - per) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = 0.f;
+        for (int c = 0; c < C; ++c) {
+          f8 x = ld8(cu + ((size_t)n * C + c) * D + dd);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] += x.v[e];
+        }
+        const float inv = 1.0f / (float)C;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] *= inv;
+        st8(op + (size_t)n * 2 * D + D + dd, o);
+      }
+    }
+  }
+}
+
+int moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* op, vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.D % 8 == 0);
+  static bool reg = (register_kernel("moment_operand_kernel"), true); (void)reg;
+  const int grid = min(cells.capacity, kNumSMs * 16);
+  if (prec == VML_BF16)
+    moment_operand_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)cu, bu, cells.code, cells.n_cells, (bf16*)op, d.L, d.C, d.D);
+  else
+    moment_operand_kernel<float><<<grid, 128, 0, st>>>((const float*)cu, bu, cells.code, cells.n_cells, (float*)op, d.L, d.C, d.D);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+// =====================================================================================
+// a9  Localization (models.py:335-344): sigmoid(1x1 conv) heads, masked
+// =====================================================================================
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+localize_pm_kernel(const ActT* __restrict__ fm, const float* __restrict__ w, const float* __restrict__ bias,
+                   const int32_t* __restrict__ code, const int32_t* __restrict__ n_cells, float* __restrict__ pm, int L, int D) {
+  const int n_total = *n_cells;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  for (int n = blockIdx.x * nw + warp; n < n_total; n += gridDim.x * nw) {
+    float acc = 0.f;
+    for (int e = lane * 4; e < D; e += 128) {
+      float4 x = ld4(fm + (size_t)n * D + e), ww = ld4(w + e);
+      acc = fmaf(x.x, ww.x, acc); acc = fmaf(x.y, ww.y, acc); acc = fmaf(x.z, ww.z, acc); acc = fmaf(x.w, ww.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      int b, i, j; decode_cell(code[n], b, i, j);
+      pm[((size_t)b * L + i) * L + j] = sigmoidf_(acc + bias[0]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+localize_boundary_kernel(const float* __restrict__ fb, const float* __restrict__ w4, const float* __restrict__ b4,
+                         const uint8_t* __restrict__ lmask, float* __restrict__ ps, float* __restrict__ pe,
+                         float* __restrict__ pa, int rows, int D) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    const float x = fb[(size_t)row * D + e];
+    a1 = fmaf(x, w4[D + e], a1); a2 = fmaf(x, w4[2 * D + e], a2); a3 = fmaf(x, w4[3 * D + e], a3);
+  }
+  a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  if (lane == 0) {
+    const float m = lmask[row] ? 1.f : 0.f;
+    ps[row] = sigmoidf_(a1 + b4[1]) * m;
+    pe[row] = sigmoidf_(a2 + b4[2]) * m;
+    pa[row] = sigmoidf_(a3 + b4[3]) * m;
+  }
+}
+
+int localize(const void* fm, const float* fb, const float* w4, const float* b4, vml_cells_t cells, const uint8_t* lmask,
+             float* pm, float* ps, float* pe, float* pa, int B, vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.D % 4 == 0);
+  static bool reg = (register_kernel("localize_pm_kernel"), register_kernel("localize_boundary_kernel"), true); (void)reg;
+  VML_CUDA(cudaMemsetAsync(pm, 0, sizeof(float) * (size_t)B * d.L * d.L, st));
+  const int grid = min(ceil_div(cells.capacity, 8), kNumSMs * 8);
+  if (prec == VML_BF16)
+    localize_pm_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)fm, w4, b4, cells.code, cells.n_cells, pm, d.L, d.D);
+  else
+    localize_pm_kernel<float><<<grid, 256, 0, st>>>((const float*)fm, w4, b4, cells.code, cells.n_cells, pm, d.L, d.D);
+  localize_boundary_kernel<<<ceil_div(B * d.L, 4), 128, 0, st>>>(fb, w4, b4, lmask, ps, pe, pa, B * d.L, d.D);
+  VML_LAUNCH_CHECK();
+  return VML_OK;
+}
+
+}  // namespace vml

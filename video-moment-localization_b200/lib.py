@@ -1,0 +1,108 @@
+"""ctypes binding of libvml_b200.so (C ABI declared in include/vml_b200.h).
+
+There is no fallback: ``load()`` raises if the shared library has not been built
+(``python -m vml_b200.build`` / ``__graft_entry__.build()``), and every wrapper raises
+``VmlError`` when a launcher returns a negative status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvml_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "vml_b200.h")
+
+FP32, BF16 = 0, 1
+PREC = {"fp32": FP32, "bf16": BF16}
+
+
+class VmlError(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("T", "L", "C", "D", "dl", "layers", "d0", "Nq", "H")]
+
+
+class Cells(C.Structure):
+    _fields_ = [("code", C.c_void_p), ("row_start", C.c_void_p), ("n_cells", C.c_void_p),
+                ("status", C.c_void_p), ("capacity", C.c_int32)]
+
+
+_P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
+
+# name -> argtypes (return type is int unless listed in _RET)
+_SIGS = {
+    "vml_last_error": [],
+    "vml_version": [],
+    "vml_kernel_names": [],
+    "vml_build_cells": [_P, _I, _I, Cells, _P],
+    "vml_unpack_cells": [_P, _P, Cells, _I, _I, _I, _I, _P],
+    "vml_pack_cells": [_P, _P, Cells, _I, _I, _I, _I, _P],
+    "vml_cast_pad_bf16": [_P, _P, _I64, _I, _I, _P],
+    "vml_linear": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
+    "vml_clip_projection": [_P, _P, _P, _P, _P, _P, _I, Dims, _I, _I, _P],
+    "vml_lstm_layer": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vml_query_lengths": [_P, _P, _I, _I, _P],
+    "vml_query_prep": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, Dims, _P],
+    "vml_span_pool_fuse": [_P, _P, Cells, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_content_attention": [_P, _P, _P, _P, _P, _P, Cells, _P, _I, Dims, _I, _P],
+    "vml_content_out": [_P, _P, _P, _P, _P, _P, Cells, _P, Dims, _I, _P],
+    "vml_boundary_unit": [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _I, Dims, _I, _P],
+    "vml_moment_operand": [_P, _P, Cells, _P, Dims, _I, _P],
+    "vml_moment_out": [_P, _P, _P, _P, Cells, _P, Dims, _I, _P],
+    "vml_localize": [_P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_scaled_iou_bce": [_P] * 13 + [_I, _I] + [_P] * 7 + [_P],
+    "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+}
+_RET = {"vml_last_error": C.c_char_p, "vml_kernel_names": C.c_char_p}
+
+_lib = None
+
+
+def declared_symbols():
+    """Entry points declared in include/vml_b200.h (used by the CPU export test)."""
+    with open(HEADER) as f:
+        return sorted(set(re.findall(r"\b(vml_[a-z0-9_]+)\s*\(", f.read())))
+
+
+def load():
+    """Load the CUDA library; raises (loudly) when it is missing -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VmlError(f"{LIB_PATH} not found: build it with `python -m vml_b200.build` "
+                       "(__graft_entry__.build()).  vml_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _RET.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise VmlError(f"{what} failed ({rc}): {load().vml_last_error().decode()}")
+
+
+def kernel_names():
+    return [k for k in load().vml_kernel_names().decode().split("\n") if k]
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)
