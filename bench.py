@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the SMIN proposal-scoring hot path (forward + R@n,IoU=m evaluation).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config charadessta|tacos|activitynet] [--precision bf16|fp32]
+
+Contract (see DESIGN.md section "Measurement"):
+  * a step = one batch of 64 (video, query) pairs of the named config through
+    ``SMIN.forward`` + ``compute_ious`` (device-resident counters);
+  * ``value``  = queries/s with inputs already resident in HBM, CUDA-event timed;
+  * ``e2e``    = same metric through the public API with PINNED HOST inputs: every step
+    copies its inputs H2D and reads the 8 hit counters back D2H inside the timed region;
+  * ``roofline`` = the dominant stage (largest share of the step), timed live with CUDA
+    events on the launching stream in a separate instrumented pass over the same steps;
+  * ``cpu_baseline`` = the CPU oracle port (oracle/) on this box's host cores, bounded sample;
+  * ``--impl reference`` times that CPU port alone on the same config.
+Multi-GPU: one process per GPU (torchrun), the (video, query) batch is sharded by rank, no
+data-path collective; one NCCL all-reduce of the 8 counters + sample count at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "queries/sec scored (fwd+eval)"
+L2_BYTES = 126 * 1024 * 1024
+BATCH = 64
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per stage: valid cells only
+# ---------------------------------------------------------------------------------------------
+def stage_work(cfg, B, n_cells, prec_bytes):
+    T, L, C, D, dl, d0, Nq = cfg.T, cfg.L, cfg.C, cfg.D, cfg.dl, cfg.d0, cfg.Nq
+    a = prec_bytes
+    w = {}
+    w["clip_cast"] = ("hbm", B * T * d0 * (4 + 2))
+    w["clip_projection"] = ("tensor", 2.0 * B * T * d0 * D)
+    w["span_pool_fuse"] = ("hbm", a * (B * T * D + n_cells * C * D + n_cells * D) + 4 * (B * D + B * L * D))
+    w["content_in_gemm"] = ("tensor", 2.0 * n_cells * C * D * dl)
+    w["content_attention"] = ("hbm", 2 * a * n_cells * C * dl)
+    w["content_out_gemm"] = ("tensor", 2.0 * n_cells * C * dl * D)
+    w["moment_operand"] = ("hbm", a * (n_cells * C * D + n_cells * 2 * D))
+    w["moment_out_gemm"] = ("tensor", 4.0 * n_cells * D * D)
+    w["boundary_unit"] = ("hbm", a * n_cells * D + 4 * 3 * B * L * D)
+    w["localize"] = ("hbm", a * n_cells * D + 4 * B * L * D)
+    return w
+
+
+def run_reference(args, cfg, rank, world):
+    """CPU arm: the oracle port (the reference is pure Python and cannot travel; oracle/ is its
+    pinned restatement) on all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import smin_forward as oracle_forward
+    from vml_b200.configs import init_params
+    from oracle import metrics_oracle as mo
+    from vml_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, BATCH, 1000)
+
+    def step():
+        with torch.no_grad():
+            pm, ps, pe, pa = oracle_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS])
+        return mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    qps = BATCH * args.steps / dt
+    sample = f"{args.steps} step(s) of one {cfg.name} batch of {BATCH} queries (fp32, torch CPU, {torch.get_num_threads()} threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg.name}: forward + R@n,IoU=m eval, batch {BATCH}, CPU oracle port of the reference path"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="charadessta", choices=["charadessta", "tacos", "activitynet"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import vml_b200  # noqa: F401
+    from vml_b200.configs import CONFIGS
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        args.steps = min(args.steps, 20)      # bounded: ~1.5 s per step on 8 cores
+        run_reference(args, cfg, rank, world)
+        return
+
+    args.steps = args.steps if args.steps is not None else 200
+    args.warmup = max(3, args.warmup if args.warmup is not None else 10)
+
+    from vml_b200 import lib, synth
+    from vml_b200.evaluate import RecallAccumulator
+    from vml_b200.smin import SMIN
+    from vml_b200.configs import init_params
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    peaks = load_peaks()
+
+    model = SMIN(*cfg.ctor_args(), device=dev, precision=args.precision)
+    model.load_state_dict(init_params(cfg, 43))
+    model = model.to(dev)
+
+    # rotating set of resident batches larger than L2 (timing rule: inputs > L2)
+    keys = synth.MODEL_INPUT_KEYS + ("sm",)
+    one = synth.make_batch(cfg, BATCH, 1000 + 97 * rank)
+    batch_bytes = sum(one[k].numel() * one[k].element_size() for k in keys)
+    n_rot = max(2, min(24, -(-2 * L2_BYTES // batch_bytes)))
+    host = [one] + [synth.make_batch(cfg, BATCH, 1000 + 97 * rank + 1 + i) for i in range(n_rot - 1)]
+    pinned = [{k: b[k].pin_memory() for k in keys} for b in host]
+    resident = [{k: b[k].to(dev) for k in keys} for b in host]
+    n_cells = [int(b["moment_mask"].sum().item()) for b in host]
+
+    acc = RecallAccumulator(dev)
+
+    def step(b, mark=None):
+        pm, ps, pe, pa = model(*[b[k] for k in synth.MODEL_INPUT_KEYS], mark=mark)
+        acc.update(pm, ps, pe, b["moment_mask"], b["sm"])
+        if mark:
+            mark("eval_topk_recall")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---------------- device-resident throughput ------------------------------------------------
+    for i in range(args.warmup):
+        step(resident[i % n_rot])
+    barrier()
+    launches0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            step(resident[i % n_rot])
+        e1.record()
+        barrier()
+    launches = lib.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    # ---------------- end to end: pinned host -> device -> counters back ------------------------
+    stage_bufs = [{k: torch.empty_like(resident[0][k]) for k in keys} for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d = batch_bytes
+    d2h = 8 * 8
+
+    result_host = [torch.zeros(2, 4, dtype=torch.int64).pin_memory() for _ in range(2)]
+    result_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_run(n):
+        """Double-buffered: the copy stream uploads batch i+1 while batch i computes; every step's
+        H2D copy and counter read-back happen inside the timed region."""
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        main_stream = torch.cuda.current_stream()
+
+        def upload(i):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[s])
+                for k in keys:
+                    stage_bufs[s][k].copy_(pinned[i % n_rot][k], non_blocking=True)
+                ready[s].record(copy_stream)
+        for s in range(2):
+            done[s].record(main_stream)
+        upload(0)
+        seen = None
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            main_stream.wait_event(ready[i % 2])
+            step(stage_bufs[i % 2])
+            done[i % 2].record(main_stream)
+            result_host[i % 2].copy_(acc.counts, non_blocking=True)   # D2H read of this step's result
+            result_ev[i % 2].record(main_stream)
+            if i > 0:                                                 # consume step i-1's counters (one step of lag)
+                result_ev[(i - 1) % 2].synchronize()
+                seen = result_host[(i - 1) % 2].sum().item()
+        result_ev[(n - 1) % 2].synchronize()
+        seen = result_host[(n - 1) % 2].sum().item()
+        return seen
+
+    e2e_run(max(3, min(args.warmup, 10)))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
+
+    # ---------------- instrumented pass: per-stage CUDA-event times ------------------------------
+    inst_steps = min(args.steps, 50)
+    events = []
+
+    def make_mark(lst):
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            lst.append((name, ev))
+        return mark
+
+    barrier()
+    for i in range(inst_steps):
+        lst = []
+        start = torch.cuda.Event(enable_timing=True)
+        start.record()
+        step(resident[i % n_rot], mark=make_mark(lst))
+        events.append((start, lst))
+    torch.cuda.synchronize()
+    stage_ms, stage_calls = {}, {}
+    for start, lst in events:
+        prev = start
+        for name, ev in lst:
+            stage_ms[name] = stage_ms.get(name, 0.0) + prev.elapsed_time(ev)
+            stage_calls[name] = stage_calls.get(name, 0) + 1
+            prev = ev
+    per_step = {k: v / inst_steps for k, v in stage_ms.items()}
+    calls_per_step = {k: stage_calls[k] / inst_steps for k in stage_calls}
+    total_inst = sum(per_step.values())
+    mean_cells = sum(n_cells[i % n_rot] for i in range(inst_steps)) / inst_steps
+    work = stage_work(cfg, BATCH, mean_cells, 2 if args.precision == "bf16" else 4)
+    stages = {}
+    for name, ms in sorted(per_step.items(), key=lambda kv: -kv[1]):
+        ent = {"ms_per_step": round(ms, 5), "share": round(ms / total_inst, 4), "launch_groups_per_step": calls_per_step[name]}
+        if name in work:
+            bound, amount = work[name]
+            per_launch_ms = ms / calls_per_step[name]
+            if bound == "hbm":
+                ach = amount / (per_launch_ms * 1e-3) / 1e9
+                ent.update(bound="hbm", achieved=round(ach, 1), unit="GB/s", frac=round(ach / peaks["hbm_gbs"], 4))
+            else:
+                ach = amount / (per_launch_ms * 1e-3) / 1e12
+                ent.update(bound="tensor", achieved=round(ach, 2), unit="TFLOP/s", frac=round(ach / peaks["bf16_tflops"], 4))
+        stages[name] = ent
+    top = next((n for n in stages if "bound" in stages[n]), None)
+    roofline = None
+    if top:
+        t = stages[top]
+        roofline = {"kernel": top, "bound": t["bound"], "achieved": t["achieved"],
+                    "peak": peaks["hbm_gbs"] if t["bound"] == "hbm" else peaks["bf16_tflops"], "unit": t["unit"],
+                    "frac": t["frac"], "traffic": None, "share_of_step": t["share"], "peak_source": peaks["source"]}
+
+    # ---------------- counters across ranks (the only collective) -----------------------------------
+    total_counts = acc.counts.clone()
+    nsamp = torch.tensor([acc.num_samples], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(total_counts)
+        dist.all_reduce(nsamp)
+
+    # ---------------- CPU baseline (rank 0, N == 1) ------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import smin_forward as oracle_forward
+        from oracle import metrics_oracle as mo
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        params = init_params(cfg, 43)
+        b = host[0]
+
+        def cpu_step():
+            with torch.no_grad():
+                o = oracle_forward(params, cfg, *[b[k] for k in synth.MODEL_INPUT_KEYS])
+            return mo.compute_ious(o[0], o[1], o[2], b["moment_mask"], b["sm"])
+        cpu_step()
+        n_cpu = 3
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            cpu_step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": BATCH * n_cpu / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                        "sample": f"{n_cpu} x one {cfg.name} batch of {BATCH} queries after 1 warm-up, fp32 torch CPU oracle port, "
+                                  f"{torch.get_num_threads()} threads"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"{cfg.name}: SMIN forward + R@n,IoU=m eval, batch {BATCH} per GPU, random-init weights "
+                                   f"(T={cfg.T} L={cfg.L} C={cfg.C} D={cfg.D} dl={cfg.dl} d0={cfg.d0} Nq={cfg.Nq}, {cfg.layers} SMI layers)",
+                       "global_batch": BATCH * world, "parallelism": f"dp{world} (batch sharded by rank, no data-path collective)",
+                       "l2": f"inputs rotate over {n_rot} resident batches ({n_rot * batch_bytes / 2**20:.0f} MiB > 126 MiB L2)",
+                       "mean_valid_cells_per_batch": mean_cells},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "pipeline": "double-buffered pinned H2D on a copy stream; counters read back every step, consumed with one step of lag"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "stages": stages,
+            "cpu_baseline": cpu_baseline,
+            "recall_counts": total_counts.cpu().tolist(), "num_samples": int(nsamp.item()),
+            "kernels": lib.kernel_names(),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,8 @@ typedef struct {
 
 VML_API const char* vml_last_error(void);
 VML_API int vml_version(void);
+/* Number of kernels this library has launched since it was loaded (bench evidence). */
+VML_API int64_t vml_launch_count(void);
 /* Names of all kernels compiled into the library, '\n'-separated (for smoke/bench reports). */
 VML_API const char* vml_kernel_names(void);
 

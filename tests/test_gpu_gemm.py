@@ -17,7 +17,8 @@ def _rand(shape, seed):
 def test_linear_fp32_simt(M, N, K):
     a, w, b = _rand((M, K), 1), _rand((N, K), 2) / K ** 0.5, _rand((N,), 3)
     out = torch.empty(M, N, device="cuda")
-    call("vml_linear", ptr(a.cuda()), ptr(w.cuda()), ptr(b.cuda()), ptr(out), M, N, K, N, None, 1, L_.FP32, 1, stream_ptr())
+    ad, wd, bd = a.cuda(), w.cuda(), b.cuda()
+    call("vml_linear", ptr(ad), ptr(wd), ptr(bd), ptr(out), M, N, K, N, None, 1, L_.FP32, 1, stream_ptr())
     ref = (a.double() @ w.double().t() + b.double())
     assert (out.cpu().double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
 
@@ -30,7 +31,8 @@ def test_linear_bf16_umma(M, N, K, out_fp32):
     w = (_rand((N, K), 5) / K ** 0.5).to(torch.bfloat16)
     b = _rand((N,), 6)
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    call("vml_linear", ptr(a.cuda()), ptr(w.cuda()), ptr(b.cuda()), ptr(out), M, N, K, N, None, 1, L_.BF16, out_fp32, stream_ptr())
+    ad, wd, bd = a.cuda(), w.cuda(), b.cuda()
+    call("vml_linear", ptr(ad), ptr(wd), ptr(bd), ptr(out), M, N, K, N, None, 1, L_.BF16, out_fp32, stream_ptr())
     torch.cuda.synchronize()
     ref = a.double() @ w.double().t() + b.double()
     err = (out.cpu().double() - ref).abs().max().item()
@@ -45,12 +47,14 @@ def test_linear_bf16_dynamic_row_count():
     w = (_rand((N, K), 8) / K ** 0.5).to(torch.bfloat16)
     out = torch.full((M, N), -7.0, device="cuda", dtype=torch.bfloat16)
     n_dev = torch.tensor([live], device="cuda", dtype=torch.int32)
-    call("vml_linear", ptr(a.cuda()), ptr(w.cuda()), None, ptr(out), M, N, K, N, ptr(n_dev), scale, L_.BF16, 0, stream_ptr())
+    ad, wd = a.cuda(), w.cuda()
+    call("vml_linear", ptr(ad), ptr(wd), None, ptr(out), M, N, K, N, ptr(n_dev), scale, L_.BF16, 0, stream_ptr())
     ref = a.double() @ w.double().t()
     rows = live * scale
     assert (out[:rows].cpu().double() - ref[:rows]).abs().max().item() < 1e-2 * ref.abs().max().item()
     assert torch.all(out[rows:] == -7.0)
     out32 = torch.full((M, N), -7.0, device="cuda")
-    call("vml_linear", ptr(a.float().cuda()), ptr(w.float().cuda()), None, ptr(out32), M, N, K, N, ptr(n_dev), scale, L_.FP32, 1, stream_ptr())
+    af, wf = a.float().cuda(), w.float().cuda()
+    call("vml_linear", ptr(af), ptr(wf), None, ptr(out32), M, N, K, N, ptr(n_dev), scale, L_.FP32, 1, stream_ptr())
     assert (out32[:rows].cpu().double() - ref[:rows]).abs().max().item() < 1e-4
     assert torch.all(out32[rows:] == -7.0)

@@ -1,6 +1,7 @@
 // extern "C" boundary of libvml_b200.so (see include/vml_b200.h) and the GEMM-backed stages.
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -15,6 +16,8 @@ namespace vml {
 static thread_local char g_err[1024] = "";
 static std::mutex g_reg_mu;
 static std::string g_kernels;
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -102,6 +105,7 @@ extern "C" {
 
 VML_API const char* vml_last_error(void) { return g_err; }
 VML_API int vml_version(void) { return 1; }
+VML_API int64_t vml_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 VML_API const char* vml_kernel_names(void) {
   static thread_local std::string copy;
   std::lock_guard<std::mutex> lk(g_reg_mu);

@@ -13,6 +13,7 @@ using bf16 = __nv_bfloat16;
 
 void set_error(const char* fmt, ...);
 void register_kernel(const char* name);
+void count_launches(int n);
 
 #define VML_CHECK_ARG(cond)                                                        \
   do {                                                                             \
@@ -31,7 +32,12 @@ void register_kernel(const char* name);
     }                                                                                          \
   } while (0)
 
-#define VML_LAUNCH_CHECK() VML_CUDA(cudaGetLastError())
+// n kernels were just enqueued by this launcher
+#define VML_LAUNCHED(n)          \
+  do {                           \
+    ::vml::count_launches(n);    \
+    VML_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // ---- activation element access (float or bf16 storage, fp32 math) -----------------------
 __device__ __forceinline__ float to_f(float x) { return x; }

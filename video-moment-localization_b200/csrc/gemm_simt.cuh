@@ -71,7 +71,7 @@ int launch_gemm_simt(const float* A, const float* W, int M, int N, int K, const 
   int64_t tiles = (int64_t)ceil_div(M, SG_BM) * ceil_div(N, SG_BN);
   int grid = (int)(tiles < (int64_t)kNumSMs * 8 ? tiles : (int64_t)kNumSMs * 8);
   gemm_simt_kernel<Epi><<<grid, SG_THREADS, 0, stream>>>(A, W, M, N, K, m_dev, m_scale, epi);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 

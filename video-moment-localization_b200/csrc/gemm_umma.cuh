@@ -148,7 +148,7 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
   const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   gemm_umma_kernel<BN, Epi><<<grid, UG_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 

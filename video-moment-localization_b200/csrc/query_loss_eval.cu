@@ -84,7 +84,7 @@ __global__ void lstm_layer_kernel(const float* __restrict__ gin, const float* __
 int query_lengths(const uint8_t* qmask, int32_t* qlen, int B, int Nq, cudaStream_t st) {
   static bool reg = (register_kernel("query_lengths_kernel"), true); (void)reg;
   query_lengths_kernel<<<ceil_div(B, 128), 128, 0, st>>>(qmask, qlen, B, Nq);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -95,7 +95,7 @@ int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float*
   constexpr int BT = 4;
   dim3 grid(ceil_div(B, BT), 2);
   lstm_layer_kernel<BT><<<grid, H, sizeof(float) * BT * H, st>>>(gin, whh_t, qlen, y, (bf16*)y16, fs, B, Nq, H);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -201,7 +201,7 @@ int scaled_iou_bce(const float* pm, const uint8_t* ym, const float* sm, const ui
   static bool reg = (register_kernel("loss_sample_kernel"), register_kernel("loss_finalize_kernel"), true); (void)reg;
   loss_sample_kernel<<<B, 256, 0, st>>>(pm, ym, sm, mmask, ps, ys, ss, pe, ye, se, pa, ya, lmask, B, L, scratch, g_pm, g_ps, g_pe, g_pa);
   loss_finalize_kernel<<<1, 32, 0, st>>>(scratch, B, loss, parts);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(2);
   return VML_OK;
 }
 
@@ -309,7 +309,7 @@ int score_topk_recall(const float* pm, const float* ps, const float* pe, const u
   VML_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_topk_kernel<<<B, 256, smem, st>>>(pm, ps, pe, mmask, sm, L, k, nms_num, nms_den, top_idx, top_score, top_iou,
                                           (unsigned long long*)counts);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 

@@ -75,7 +75,7 @@ int build_cells(const uint8_t* mask, int B, int L, vml_cells_t cells, cudaStream
   cells_count_kernel<<<blocks, 256, 0, st>>>(mask, rows, L, cells.row_start);
   cells_scan_kernel<<<1, 1024, 0, st>>>(cells.row_start, rows, cells.n_cells, cells.status, cells.capacity);
   cells_fill_kernel<<<blocks, 256, 0, st>>>(mask, rows, L, cells.row_start, cells.code, cells.capacity);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(3);
   return VML_OK;
 }
 
@@ -110,7 +110,7 @@ int unpack_cells(const void* packed, void* dense, vml_cells_t cells, int B, int 
   const int grid = min(cells.capacity, kNumSMs * 16);
   if (prec == VML_BF16) unpack_cells_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)packed, (bf16*)dense, cells.code, cells.n_cells, L, inner);
   else unpack_cells_kernel<float><<<grid, 128, 0, st>>>((const float*)packed, (float*)dense, cells.code, cells.n_cells, L, inner);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 int pack_cells(const void* dense, void* packed, vml_cells_t cells, int B, int L, int inner, int prec, cudaStream_t st) {
@@ -118,7 +118,7 @@ int pack_cells(const void* dense, void* packed, vml_cells_t cells, int B, int L,
   const int grid = min(cells.capacity, kNumSMs * 16);
   if (prec == VML_BF16) pack_cells_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)dense, (bf16*)packed, cells.code, cells.n_cells, L, inner);
   else pack_cells_kernel<float><<<grid, 128, 0, st>>>((const float*)dense, (float*)packed, cells.code, cells.n_cells, L, inner);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -146,7 +146,7 @@ int cast_pad(const float* src, void* dst, int64_t rows, int k, int k_pad, cudaSt
   const int64_t want = ceil_div64(total, 256), cap = (int64_t)kNumSMs * 16;
   const int grid = (int)(want < cap ? want : cap);
   cast_pad_kernel<<<grid, 256, 0, st>>>(src, (bf16*)dst, rows, k, k_pad);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -256,7 +256,7 @@ int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc,
     span_pool_kernel<float><<<grid, 256, smem, st>>>((const float*)fv, fs, cells.code, cells.row_start, (float*)fc,
                                                      (float*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
   }
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -408,7 +408,7 @@ static int launch_content_attention(const void* c_hat, const float* ktil, const 
   dim3 grid(chunks, B);
   content_attention_kernel<ActT, DPL><<<grid, 256, smem, st>>>((const ActT*)c_hat, ktil, beta, w_hat, s_hat, qmask,
                                                                cells.row_start, (ActT*)cc_hat, d.L, d.Nq, cells.capacity);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -475,7 +475,7 @@ int query_prep(const float* wproj, int ld, int col0, const float* fs, const uint
   const size_t smem = sizeof(float) * 2 * d.Nq * d.dl;
   query_prep_kernel<<<B, d.dl, smem, st>>>(wproj, ld, col0, fs, qmask, Wk, bk, Wq, bq, Ws, bs, w_hat, ktil, beta,
                                           s_hat, d.Nq, d.D, d.dl);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -588,7 +588,7 @@ int boundary_unit(const float* qb, const float* kb, int ldk, int col0, const flo
   else
     boundary_row_kernel<float><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const float*)fm, lmask, cells.code,
                                                            cells.row_start, bu, d.L, d.D, cells.capacity);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(2);
   return VML_OK;
 }
 
@@ -637,7 +637,7 @@ int moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* op,
     moment_operand_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)cu, bu, cells.code, cells.n_cells, (bf16*)op, d.L, d.C, d.D);
   else
     moment_operand_kernel<float><<<grid, 128, 0, st>>>((const float*)cu, bu, cells.code, cells.n_cells, (float*)op, d.L, d.C, d.D);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(1);
   return VML_OK;
 }
 
@@ -696,7 +696,7 @@ int localize(const void* fm, const float* fb, const float* w4, const float* b4, 
   else
     localize_pm_kernel<float><<<grid, 256, 0, st>>>((const float*)fm, w4, b4, cells.code, cells.n_cells, pm, d.L, d.D);
   localize_boundary_kernel<<<ceil_div(B * d.L, 4), 128, 0, st>>>(fb, w4, b4, lmask, ps, pe, pa, B * d.L, d.D);
-  VML_LAUNCH_CHECK();
+  VML_LAUNCHED(2);
   return VML_OK;
 }
 

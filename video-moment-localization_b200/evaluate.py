@@ -36,8 +36,10 @@ def score_topk_recall(pm, ps, pe, moment_mask, sm, k: int = 5, nms_threshold: fl
     top_score = torch.empty(B, k, device=dev, dtype=torch.float32)
     top_iou = torch.empty(B, k, device=dev, dtype=torch.float32)
     fr = Fraction(nms_threshold).limit_denominator(1000) if nms_threshold < 1.0 else Fraction(1, 1)
-    call("vml_score_topk_recall", ptr(pm.float().contiguous()), ptr(ps.float().contiguous()), ptr(pe.float().contiguous()),
-         ptr(_as_u8(moment_mask)), ptr(sm.float().contiguous()), B, L, k, fr.numerator, fr.denominator,
+    # keep every converted operand referenced until the launch is enqueued
+    pm_, ps_, pe_, sm_ = (t.float().contiguous() for t in (pm, ps, pe, sm))
+    mask_ = _as_u8(moment_mask)
+    call("vml_score_topk_recall", ptr(pm_), ptr(ps_), ptr(pe_), ptr(mask_), ptr(sm_), B, L, k, fr.numerator, fr.denominator,
          ptr(top_idx), ptr(top_score), ptr(top_iou), ptr(counts), stream_ptr())
     return top_idx, top_score, top_iou, counts
 

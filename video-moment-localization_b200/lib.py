@@ -37,6 +37,7 @@ _P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
 _SIGS = {
     "vml_last_error": [],
     "vml_version": [],
+    "vml_launch_count": [],
     "vml_kernel_names": [],
     "vml_build_cells": [_P, _I, _I, Cells, _P],
     "vml_unpack_cells": [_P, _P, Cells, _I, _I, _I, _I, _P],
@@ -57,7 +58,7 @@ _SIGS = {
     "vml_scaled_iou_bce": [_P] * 13 + [_I, _I] + [_P] * 7 + [_P],
     "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
 }
-_RET = {"vml_last_error": C.c_char_p, "vml_kernel_names": C.c_char_p}
+_RET = {"vml_last_error": C.c_char_p, "vml_kernel_names": C.c_char_p, "vml_launch_count": C.c_int64}
 
 _lib = None
 
@@ -92,6 +93,10 @@ def check(rc: int, what: str):
 
 def kernel_names():
     return [k for k in load().vml_kernel_names().decode().split("\n") if k]
+
+
+def launch_count() -> int:
+    return int(load().vml_launch_count())
 
 
 def ptr(t):

@@ -26,8 +26,11 @@ def _launch(pm, ym, sm, moment_mask, ps, ys, ss, pe, ye, se, pa, ya, length_mask
     f = lambda t: t.detach().float().contiguous()
     pm_, ps_, pe_, pa_ = f(pm), f(ps), f(pe), f(pa)
     grads = [torch.empty_like(t) for t in (pm_, ps_, pe_, pa_)] if want_grad else [None] * 4
-    call("vml_scaled_iou_bce", ptr(pm_), ptr(_u8(ym)), ptr(f(sm)), ptr(_u8(moment_mask)), ptr(ps_), ptr(_u8(ys)), ptr(f(ss)),
-         ptr(pe_), ptr(_u8(ye)), ptr(f(se)), ptr(pa_), ptr(_u8(ya)), ptr(_u8(length_mask)), B, L,
+    # converted operands must stay referenced until the launch is enqueued
+    ym_, mm_, ys_, ye_, ya_, lm_ = (_u8(t) for t in (ym, moment_mask, ys, ye, ya, length_mask))
+    sm_, ss_, se_ = f(sm), f(ss), f(se)
+    call("vml_scaled_iou_bce", ptr(pm_), ptr(ym_), ptr(sm_), ptr(mm_), ptr(ps_), ptr(ys_), ptr(ss_),
+         ptr(pe_), ptr(ye_), ptr(se_), ptr(pa_), ptr(ya_), ptr(lm_), B, L,
          out.data_ptr(), out.data_ptr() + 4, ptr(scratch), *[ptr(g) for g in grads], stream_ptr())
     return out, grads
 

@@ -184,9 +184,11 @@ def make_cells(ws: Workspace, B: int, L: int, capacity: Optional[int] = None) ->
 
 
 def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace, video_features, video_mask,
-                 query_features, query_mask, length_mask, moment_mask, keep: Optional[dict] = None):
+                 query_features, query_mask, length_mask, moment_mask, keep: Optional[dict] = None, mark=None):
     """The whole hot path, stage by stage.  ``keep`` (tests only)
-    receives references to intermediates."""
+    receives references to intermediates; ``mark(name)`` (bench only) is called after each
+    stage has been enqueued so the caller can record CUDA events on the launching stream."""
+    mark = mark or (lambda name: None)
     dev = video_features.device
     B = video_features.shape[0]
     T, Lm, Cc, D, dl, layers, d0, Nq, H = (dims.T, dims.L, dims.C, dims.D, dims.dl, dims.layers, dims.d0, dims.Nq, dims.H)
@@ -206,9 +208,11 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
         kp = pk["ve_kpad"]
         v16 = ws.get("v16", (B * T, kp), torch.bfloat16)
         call("vml_cast_pad_bf16", ptr(vf), ptr(v16), B * T, d0, kp, st)
+        mark("clip_cast")
         call("vml_clip_projection", ptr(v16), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(fv), B, dims, kp, prec, st)
     else:
         call("vml_clip_projection", ptr(vf), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(fv), B, dims, d0, prec, st)
+    mark("clip_projection")
 
     # ---- a2 query encoder ------------------------------------------------------------------
     qlen = ws.get("qlen", (B,), torch.int32)
@@ -221,6 +225,7 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
     call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), None, None, B, Nq, H, st)
     call("vml_linear", ptr(y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin), B * Nq, 8 * H, 2 * H, 8 * H, None, 1, L_.FP32, 1, st)
     call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), None, ptr(fs), B, Nq, H, st)
+    mark("query_lstm")
 
     # query-side projections of every SMI layer, hoisted (fw / fs do not change across layers)
     ncat = layers * (dl + D)
@@ -234,15 +239,18 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
         call("vml_query_prep", ptr(wproj), ncat, k * (dl + D), ptr(fs), ptr(qmask), ptr(pk[f"ck_w{k}"]), ptr(pk[f"ck_b{k}"]),
              ptr(pk[f"cq_w{k}"]), ptr(pk[f"cq_b{k}"]), ptr(pk[f"cs_w{k}"]), ptr(pk[f"cs_b{k}"]), ptr(w_hat[k]), ptr(ktil[k]),
              ptr(beta[k]), ptr(s_hat[k]), B, dims, st)
+    mark("query_prep")
 
     # ---- cells + a3/a4 span pooling ---------------------------------------------------------
     cells = make_cells(ws, B, Lm)
     cap = cells.capacity
     call("vml_build_cells", ptr(mmask), B, Lm, cells, st)
+    mark("build_cells")
     fc = [ws.get("fc_a", (cap, Cc, D), act), ws.get("fc_b", (cap, Cc, D), act)]
     fm = [ws.get("fm_a", (cap, D), act), ws.get("fm_b", (cap, D), act)]
     fb = [ws.get("fb_a", (B, Lm, D), f32), ws.get("fb_b", (B, Lm, D), f32)]
     call("vml_span_pool_fuse", ptr(fv), ptr(fs), cells, ptr(fc[0]), ptr(fm[0]), ptr(fb[0]), B, dims, prec, st)
+    mark("span_pool_fuse")
     if keep is not None:
         keep.update(fv=fv, fs=fs, fw=fw, cells=cells, fc0=fc[0].clone(), fm0=fm[0].clone(), fb0=fb[0].clone())
 
@@ -259,16 +267,22 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
         call("vml_linear", ptr(fb[cur]), ptr(pk[f"bq_w{k}"]), ptr(pk[f"bq_b{k}"]), ptr(qb), B * Lm, D, D, D, None, 1, L_.FP32, 1, st)
         call("vml_boundary_unit", ptr(qb), ptr(wproj), ncat, k * (dl + D) + dl, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
              ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(fb[nxt]), B, dims, prec, st)
+        mark("boundary_unit")
         # a5+a6 content unit
         call("vml_linear", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl, n_dev, Cc,
              prec, 0, st)
+        mark("content_in_gemm")
         call("vml_content_attention", ptr(c_hat), ptr(ktil[k]), ptr(beta[k]), ptr(w_hat[k]), ptr(s_hat[k]), ptr(qmask), cells,
              ptr(cc_hat), B, dims, prec, st)
+        mark("content_attention")
         call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]), ptr(fs),
              cells, ptr(fc[nxt]), dims, prec, st)
+        mark("content_out_gemm")
         # a8 moment unit
         call("vml_moment_operand", ptr(fc[nxt]), ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
+        mark("moment_operand")
         call("vml_moment_out", ptr(mu_op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(fm[cur]), cells, ptr(fm[nxt]), dims, prec, st)
+        mark("moment_out_gemm")
         cur = nxt
         if keep is not None:
             keep[f"fc{k + 1}"], keep[f"fm{k + 1}"], keep[f"fb{k + 1}"] = fc[cur].clone(), fm[cur].clone(), fb[cur].clone()
@@ -280,6 +294,7 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
     pa = torch.empty(B, Lm, device=dev, dtype=f32)
     call("vml_localize", ptr(fm[cur]), ptr(fb[cur]), ptr(pk["loc_w"]), ptr(pk["loc_b"]), cells, ptr(lmask), ptr(pm), ptr(ps),
          ptr(pe), ptr(pa), B, dims, prec, st)
+    mark("localize")
     return pm, ps, pe, pa
 
 
@@ -315,7 +330,7 @@ class SMIN(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def forward(self, video_features, video_mask, query_features, query_mask, length_mask, moment_mask):
+    def forward(self, video_features, video_mask, query_features, query_mask, length_mask, moment_mask, mark=None):
         if not video_features.is_cuda:
             raise L_.VmlError("vml_b200.SMIN runs on CUDA (sm_100a) only; there is no CPU path. "
                               "Move the module and its inputs to a B200 device.")
@@ -328,4 +343,4 @@ class SMIN(nn.Module):
             pk = self._weights(dev, prec)
             ws = self._ws.setdefault(str(dev), Workspace(dev))
             return smin_forward(pk, self._dims, prec, ws, video_features.float(), video_mask, query_features.float(),
-                                query_mask, length_mask, moment_mask)
+                                query_mask, length_mask, moment_mask, mark=mark)
