@@ -105,21 +105,13 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
 /* One bi-LSTM layer's recurrence.  gin[B*Nq, 2*4H] float = x.W_ih^T + b_ih + b_hh for
  * (forward | reverse) directions (gate order i,f,g,o); whh_t[2][H][4H] float = W_hh^T per
  * direction; qlen[B] int32 valid words.  y[B,Nq,2H] float (zero for t >= qlen, as
- * pad_packed_sequence); y_bf16 optional copy; fs[B,2H] optional = [h_fwd(len-1) | h_bwd(0)]. */
+ * pad_packed_sequence); y_bf16 optional copy; fs[B,2H] optional = [h_fwd(len-1) | h_bwd(0)]
+ * (+ optional bf16 copy).  One 8-CTA cluster per (direction, 8 samples); W_hh stays in smem. */
 VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16,
-                   float* fs, int B, int Nq, int H, void* stream);
+                           float* fs, void* fs_bf16, int B, int Nq, int H, void* stream);
 
 /* query_mask[B,Nq] u8 -> qlen[B] int32  (models.py:50, without the D2H copy of :52). */
 VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, int Nq, void* stream);
-
-/* Per-layer query-side tensors of ContentUnit (models.py:249-251,209), hoisted out of the
- * per-cell path:  w_hat = (wproj)*qmask, kc = w_hat.Wk^T + bk, ktil = kc.Wq  (so that
- * Q.K^T = c_hat.ktil^T + beta, beta = kc.bq), s_hat = fs.Ws^T + bs.
- * wproj[B*Nq, ld] float holds fw.Ww^T + bw at column offset col0. */
-VML_API int vml_query_prep(const float* wproj, int ld, int col0, const float* fs, const uint8_t* query_mask,
-                   const float* Wk, const float* bk, const float* Wq, const float* bq, const float* Ws,
-                   const float* bs, float* w_hat, float* ktil, float* beta, float* s_hat, int B,
-                   vml_dims_t d, void* stream);
 
 /* ---- a3+a4: Backbone fusion + ProposalGeneration (models.py:81,88-98,115-126) ----------- */
 
@@ -131,10 +123,13 @@ VML_API int vml_span_pool_fuse(const void* fv, const float* fs, vml_cells_t cell
 /* ---- a5+a6: ContentUnit (models.py:207-226,242-276) ----------------------------------------- */
 
 /* middle of the unit: c_hat act [n*C, dl] -> cc_hat act [n*C, dl]
- * (content-word attention, gate, CxC self-attention). */
-VML_API int vml_content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat,
-                          const float* s_hat, const uint8_t* query_mask, vml_cells_t cells, void* cc_hat,
-                          int B, vml_dims_t d, int prec, void* stream);
+ * (content-word attention, gate, CxC self-attention).  Query-side tensors come from the folded
+ * query projection qproj float [B*Nq, ld]: w_hat (models.py:249) at column off_what, the
+ * W_q-folded keys ktil at off_ktil and their bias term beta at off_beta, so that
+ * Q.K^T (models.py:209-211) = c_hat.ktil^T + beta; s_hat float [B, s_ld] (models.py:251). */
+VML_API int vml_content_attention(const void* c_hat, const float* qproj, int ld, int off_what, int off_ktil,
+                                  int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask,
+                                  vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, int prec, void* stream);
 
 /* cu = cc_hat.Wc^T + bc + fc + sigmoid(fm*fs)*fm   (models.py:269-276). */
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm,
@@ -142,9 +137,10 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 
 /* ---- a7: BoundaryUnit (models.py:137-154,164-196) ------------------------------------------- */
 
-/* qb float [B*L, D] = fb.Wq^T + bq ; kb float [B*Nq, ldk] (+col0) = fw.Wk^T + bk (precomputed).
+/* Boundary-word scores use the W_q-folded keys kbt (column off_kbt of qproj) and their bias
+ * term beta_b (column off_betab): (fb.Wq^T+bq).(fw.Wk^T+bk)^T = fb.kbt^T + beta_b.
  * g_scratch float [B,L,D].  bu float [B,L,D] = f_bb + f_b + f_bm. */
-VML_API int vml_boundary_unit(const float* qb, const float* kb, int ldk, int col0, const float* fw, const float* fs,
+VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask,
                       const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* bu, int B,
                       vml_dims_t d, int prec, void* stream);

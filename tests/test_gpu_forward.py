@@ -76,8 +76,8 @@ def test_every_stage_matches_oracle(name, prec):
     tol = 2e-6 if prec == "fp32" else 2e-2
     cells = keep["cells"]
     assert scaled_err(keep["fv"].float().view(B, cfg.T, cfg.D), inter["fv"]) < tol
-    assert scaled_err(keep["fs"], inter["fs"]) < 2e-6          # LSTM runs in fp32 in both modes
-    assert scaled_err(keep["fw"], inter["fw"]) < 2e-6
+    assert scaled_err(keep["fs"], inter["fs"]) < tol           # recurrence is fp32 in both modes; bf16 mode feeds it bf16 input projections
+    assert scaled_err(keep["fw"], inter["fw"]) < tol
     for k in range(cfg.layers + 1):
         fc = unpack(keep[f"fc{k}"], cells, B, cfg.L, cfg.C * cfg.D, p).view(B, cfg.L, cfg.L, cfg.C, cfg.D)
         fm = unpack(keep[f"fm{k}"], cells, B, cfg.L, cfg.D, p)

@@ -69,17 +69,15 @@ int unpack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream
 int pack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
 int cast_pad(const float*, void*, int64_t, int, int, cudaStream_t);
 int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*, int, vml_dims_t, int, cudaStream_t);
-int content_attention(const void*, const float*, const float*, const float*, const float*, const uint8_t*, vml_cells_t,
+int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
                       void*, int, vml_dims_t, int, cudaStream_t);
-int query_prep(const float*, int, int, const float*, const uint8_t*, const float*, const float*, const float*,
-               const float*, const float*, const float*, float*, float*, float*, float*, int, vml_dims_t, cudaStream_t);
-int boundary_unit(const float*, const float*, int, int, const float*, const float*, const float*, const void*,
+int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
                   const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, int, vml_dims_t, int, cudaStream_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
              float*, int, vml_dims_t, int, cudaStream_t);
 int query_lengths(const uint8_t*, int32_t*, int, int, cudaStream_t);
-int lstm_layer(const float*, const float*, const int32_t*, float*, void*, float*, int, int, int, cudaStream_t);
+int lstm_layer(const float*, const float*, const int32_t*, float*, void*, float*, void*, int, int, int, cudaStream_t);
 int scaled_iou_bce(const float*, const uint8_t*, const float*, const uint8_t*, const float*, const uint8_t*, const float*,
                    const float*, const uint8_t*, const float*, const float*, const uint8_t*, const uint8_t*, int, int,
                    float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
@@ -152,30 +150,25 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
   return launch_gemm_simt((const float*)v, (const float*)W, M, d.D, d.d0, nullptr, 1, e, ST(stream));
 }
 
-VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16, float* fs, int B,
-                   int Nq, int H, void* stream) {
-  return lstm_layer(gin, whh_t, qlen, y, y_bf16, fs, B, Nq, H, ST(stream));
+VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16, float* fs,
+                   void* fs_bf16, int B, int Nq, int H, void* stream) {
+  return lstm_layer(gin, whh_t, qlen, y, y_bf16, fs, fs_bf16, B, Nq, H, ST(stream));
 }
 VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, int Nq, void* stream) {
   return query_lengths(query_mask, qlen, B, Nq, ST(stream));
 }
-VML_API int vml_query_prep(const float* wproj, int ld, int col0, const float* fs, const uint8_t* query_mask, const float* Wk,
-                   const float* bk, const float* Wq, const float* bq, const float* Ws, const float* bs, float* w_hat,
-                   float* ktil, float* beta, float* s_hat, int B, vml_dims_t d, void* stream) {
-  return query_prep(wproj, ld, col0, fs, query_mask, Wk, bk, Wq, bq, Ws, bs, w_hat, ktil, beta, s_hat, B, d, ST(stream));
-}
-
 VML_API int vml_span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb, int B,
                        vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
   return span_pool_fuse(fv, fs, cells, fc, fm, fb, B, d, prec, ST(stream));
 }
 
-VML_API int vml_content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat,
-                          const float* s_hat, const uint8_t* query_mask, vml_cells_t cells, void* cc_hat, int B,
+VML_API int vml_content_attention(const void* c_hat, const float* qproj, int ld, int off_what, int off_ktil, int off_beta,
+                          const float* s_hat, int s_ld, const uint8_t* query_mask, vml_cells_t cells, void* cc_hat, int B,
                           vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
-  return content_attention(c_hat, ktil, beta, w_hat, s_hat, query_mask, cells, cc_hat, B, d, prec, ST(stream));
+  return content_attention(c_hat, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, cc_hat, B, d, prec,
+                           ST(stream));
 }
 
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm, const float* fs,
@@ -190,11 +183,12 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
   return gemm_dispatch(cc_hat, Wc, M, d.D, d.dl, d.dl, cells.n_cells, d.C, e, prec, ST(stream));
 }
 
-VML_API int vml_boundary_unit(const float* qb, const float* kb, int ldk, int col0, const float* fw, const float* fs,
+VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
                       vml_cells_t cells, float* g_scratch, float* bu, int B, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
-  return boundary_unit(qb, kb, ldk, col0, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, bu, B, d, prec, ST(stream));
+  return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, bu, B, d, prec,
+                       ST(stream));
 }
 
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {

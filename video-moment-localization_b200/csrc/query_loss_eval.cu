@@ -1,4 +1,6 @@
 // Query encoder recurrence (a2), scaled-IoU BCE loss (a10) and R@n,IoU=m evaluation (a11).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace vml {
@@ -15,70 +17,118 @@ __global__ void query_lengths_kernel(const uint8_t* __restrict__ qmask, int32_t*
   qlen[b] = s;
 }
 
-template <int BT>
-__global__ void lstm_layer_kernel(const float* __restrict__ gin, const float* __restrict__ whh_t,
-                                  const int32_t* __restrict__ qlen, float* __restrict__ y, bf16* __restrict__ y16,
-                                  float* __restrict__ fs, int B, int Nq, int H) {
-  extern __shared__ float sh[];  // [BT][H]
-  const int dir = blockIdx.y, b0 = blockIdx.x * BT, u = threadIdx.x;
+// One thread-block CLUSTER of 8 CTAs per (direction, tile of 8 samples).  CTA r keeps the
+// recurrent weights of hidden units [r*H/8, (r+1)*H/8) (all four gates) resident in shared
+// memory for the whole sequence (H=256: 128 KB fp32), so a time step costs no global weight
+// traffic.  Per step: (A) thread (u, ks) accumulates the 4 gates of unit u for all 8 samples
+// over K-slice ks; (B) thread (u, s) reduces the 8 slices, applies the cell update for
+// (unit u, sample s) and writes h_t into the h buffer of every CTA of the cluster through
+// distributed shared memory; one cluster barrier per step.
+constexpr int LSTM_CL = 8;   // CTAs per cluster == K-slices == samples per tile
+
+__global__ void __cluster_dims__(LSTM_CL, 1, 1)
+lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh_t, const int32_t* __restrict__ qlen,
+                    float* __restrict__ y, bf16* __restrict__ y16, float* __restrict__ fs, bf16* __restrict__ fs16, int B, int Nq,
+                    int H) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int BT = LSTM_CL;
+  extern __shared__ __align__(16) float lsm[];
+  const int UH = H / LSTM_CL, KS = H / LSTM_CL;
+  float* Wsl = lsm;                       // [H][4][UH]
+  float* hbuf = Wsl + (size_t)H * 4 * UH; // [2][H][BT]
+  float* part = hbuf + 2 * H * BT;        // [8 ks][BT][4][UH]
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / LSTM_CL;   // cluster id
+  const int dir = cid & 1, b0 = (cid >> 1) * BT;
+  const int tid = threadIdx.x;            // blockDim.x == H == UH * 8
+  const int u = tid % UH, ks = tid / UH;  // phase A role: (unit, K-slice); phase B role: (unit, sample = ks)
+  const int unit = rank * UH + u;
+
   const float* W = whh_t + (size_t)dir * H * 4 * H;
-  int len[BT];
-  int maxlen = 0;
-  float c[BT], h[BT];
-#pragma unroll
-  for (int s = 0; s < BT; ++s) {
-    len[s] = (b0 + s < B) ? min(qlen[b0 + s], Nq) : 0;
-    maxlen = max(maxlen, len[s]);
-    c[s] = 0.f; h[s] = 0.f;
-    sh[s * H + u] = 0.f;
+  for (int e = tid; e < H * 4 * UH; e += blockDim.x) {
+    const int k = e / (4 * UH), g = (e / UH) % 4, uu = e % UH;
+    Wsl[e] = W[(size_t)k * 4 * H + g * H + rank * UH + uu];
   }
-  __syncthreads();
+  for (int e = tid; e < 2 * H * BT; e += blockDim.x) hbuf[e] = 0.f;
+
+  const int s = ks;                        // phase-B sample slot
+  const int bs = b0 + s;
+  const int my_len = bs < B ? min(qlen[bs], Nq) : 0;
+  int maxlen = 0;
+  for (int t = 0; t < BT; ++t) maxlen = max(maxlen, (b0 + t < B) ? min(qlen[b0 + t], Nq) : 0);
+  float c_state = 0.f, h_state = 0.f;
+  float* remote_h[LSTM_CL];
+#pragma unroll
+  for (int r = 0; r < LSTM_CL; ++r) remote_h[r] = cluster.map_shared_rank(hbuf, r);
+  cluster.sync();
+
   for (int step = 0; step < maxlen; ++step) {
+    const int cur = step & 1, nxt = cur ^ 1;
+    const bool act = step < my_len;
+    const int t = dir == 0 ? step : my_len - 1 - step;
+    float gpre[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {                              // issue early; consumed in phase B
+      const float* g = gin + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gpre[q] = g[q * H];
+    }
+    // ---- phase A: partial gates over K-slice ks, all BT samples ---------------------------
     float acc[BT][4];
 #pragma unroll
-    for (int s = 0; s < BT; ++s) {
-      const bool act = step < len[s];
-      const int t = dir == 0 ? step : len[s] - 1 - step;
-      const float* g = gin + ((size_t)(b0 + s) * Nq + (act ? t : 0)) * 8 * H + (size_t)dir * 4 * H + u;
+    for (int a = 0; a < BT; ++a)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[s][q] = act ? g[q * H] : 0.f;
-    }
-    for (int k = 0; k < H; ++k) {
-      const float* wr = W + (size_t)k * 4 * H + u;
-      const float w0 = wr[0], w1 = wr[H], w2 = wr[2 * H], w3 = wr[3 * H];
+      for (int q = 0; q < 4; ++q) acc[a][q] = 0.f;
+    const float* hb = hbuf + (size_t)cur * H * BT;
+    for (int kk = 0; kk < KS; ++kk) {
+      const int k = ks * KS + kk;
+      const float* wr = Wsl + (size_t)k * 4 * UH + u;
+      const float w0 = wr[0], w1 = wr[UH], w2 = wr[2 * UH], w3 = wr[3 * UH];
+      const float4 ha = *reinterpret_cast<const float4*>(hb + k * BT);
+      const float4 hc = *reinterpret_cast<const float4*>(hb + k * BT + 4);
+      const float hv[BT] = {ha.x, ha.y, ha.z, ha.w, hc.x, hc.y, hc.z, hc.w};
 #pragma unroll
-      for (int s = 0; s < BT; ++s) {
-        const float hv = sh[s * H + k];
-        acc[s][0] = fmaf(hv, w0, acc[s][0]); acc[s][1] = fmaf(hv, w1, acc[s][1]);
-        acc[s][2] = fmaf(hv, w2, acc[s][2]); acc[s][3] = fmaf(hv, w3, acc[s][3]);
+      for (int a = 0; a < BT; ++a) {
+        acc[a][0] = fmaf(hv[a], w0, acc[a][0]); acc[a][1] = fmaf(hv[a], w1, acc[a][1]);
+        acc[a][2] = fmaf(hv[a], w2, acc[a][2]); acc[a][3] = fmaf(hv[a], w3, acc[a][3]);
       }
     }
-    __syncthreads();
 #pragma unroll
-    for (int s = 0; s < BT; ++s) {
-      if (step < len[s]) {
-        const int t = dir == 0 ? step : len[s] - 1 - step;
-        const float ig = sigmoidf_(acc[s][0]), fg = sigmoidf_(acc[s][1]), gg = tanhf(acc[s][2]), og = sigmoidf_(acc[s][3]);
-        c[s] = fg * c[s] + ig * gg;
-        h[s] = og * tanhf(c[s]);
-        sh[s * H + u] = h[s];
-        const size_t o = ((size_t)(b0 + s) * Nq + t) * 2 * H + (size_t)dir * H + u;
-        y[o] = h[s];
-        if (y16) y16[o] = __float2bfloat16_rn(h[s]);
-      }
-    }
+    for (int a = 0; a < BT; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part[(((size_t)ks * BT + a) * 4 + q) * UH + u] = acc[a][q];
     __syncthreads();
+    // ---- phase B: reduce slices, cell update for (unit, sample s), broadcast h -------------
+    if (act) {
+      float gate[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = gpre[q];
+#pragma unroll
+        for (int p = 0; p < LSTM_CL; ++p) v += part[(((size_t)p * BT + s) * 4 + q) * UH + u];
+        gate[q] = v;
+      }
+      const float ig = sigmoidf_(gate[0]), fg = sigmoidf_(gate[1]), gg = tanhf(gate[2]), og = sigmoidf_(gate[3]);
+      c_state = fg * c_state + ig * gg;
+      h_state = og * tanhf(c_state);
+      const size_t o = ((size_t)bs * Nq + t) * 2 * H + (size_t)dir * H + unit;
+      y[o] = h_state;
+      if (y16) y16[o] = __float2bfloat16_rn(h_state);
+    }
+#pragma unroll
+    for (int r = 0; r < LSTM_CL; ++r) remote_h[r][(size_t)nxt * H * BT + (size_t)unit * BT + s] = h_state;
+    cluster.sync();                         // h_t visible everywhere; part[] and hbuf[cur] reusable
   }
-#pragma unroll
-  for (int s = 0; s < BT; ++s) {
-    if (b0 + s >= B) continue;
-    for (int t = len[s]; t < Nq; ++t) {   // pad_packed_sequence: zeros past the length
-      const size_t o = ((size_t)(b0 + s) * Nq + t) * 2 * H + (size_t)dir * H + u;
+  if (bs < B) {
+    for (int t = my_len; t < Nq; ++t) {     // pad_packed_sequence: zeros past the length
+      const size_t o = ((size_t)bs * Nq + t) * 2 * H + (size_t)dir * H + unit;
       y[o] = 0.f;
       if (y16) y16[o] = __float2bfloat16_rn(0.f);
     }
-    if (fs) fs[(size_t)(b0 + s) * 2 * H + (size_t)dir * H + u] = h[s];  // fwd: h(len-1); bwd: h(0)
+    if (fs) fs[(size_t)bs * 2 * H + (size_t)dir * H + unit] = h_state;  // fwd: h(len-1); bwd: h(0)
+    if (fs16) fs16[(size_t)bs * 2 * H + (size_t)dir * H + unit] = __float2bfloat16_rn(h_state);
   }
+  cluster.sync();                           // no CTA may exit while peers can still address its smem
 }
 
 int query_lengths(const uint8_t* qmask, int32_t* qlen, int B, int Nq, cudaStream_t st) {
@@ -88,13 +138,16 @@ int query_lengths(const uint8_t* qmask, int32_t* qlen, int B, int Nq, cudaStream
   return VML_OK;
 }
 
-int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y16, float* fs, int B, int Nq,
-               int H, cudaStream_t st) {
+int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y16, float* fs, void* fs16, int B,
+               int Nq, int H, cudaStream_t st) {
   VML_CHECK_ARG(H % 32 == 0 && H <= 1024);
-  static bool reg = (register_kernel("lstm_layer_kernel"), true); (void)reg;
-  constexpr int BT = 4;
-  dim3 grid(ceil_div(B, BT), 2);
-  lstm_layer_kernel<BT><<<grid, H, sizeof(float) * BT * H, st>>>(gin, whh_t, qlen, y, (bf16*)y16, fs, B, Nq, H);
+  static bool reg = (register_kernel("lstm_cluster_kernel"), true); (void)reg;
+  const int UH = H / LSTM_CL;
+  const size_t smem = sizeof(float) * ((size_t)H * 4 * UH + 2 * (size_t)H * LSTM_CL + (size_t)LSTM_CL * LSTM_CL * 4 * UH);
+  VML_CHECK_ARG(smem <= 227 * 1024);
+  VML_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int clusters = 2 * ceil_div(B, LSTM_CL);
+  lstm_cluster_kernel<<<clusters * LSTM_CL, H, smem, st>>>(gin, whh_t, qlen, y, (bf16*)y16, fs, (bf16*)fs16, B, Nq, H);
   VML_LAUNCHED(1);
   return VML_OK;
 }

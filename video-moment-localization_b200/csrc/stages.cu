@@ -264,13 +264,14 @@ int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc,
 // a5+a6 (middle)  content-word attention, gate, CxC self-attention
 //   (ContentAttention.forward models.py:207-226; ContentUnit.forward models.py:253-266)
 // One warp per cell (C = 4 clips x dl features); lane k owns query word k in the score phase
-// and dl/32 feature columns elsewhere.  Q.K^T is evaluated as c_hat.ktil^T + beta with the
-// per-sample ktil = (w_hat.Wk^T + bk).Wq hoisted to vml_query_prep.
+// and dl/32 feature columns elsewhere.  Q.K^T is evaluated as c_hat.ktil^T + beta, where the
+// per-word ktil / beta / w_hat (and the per-sentence s_hat) are columns of the single folded
+// query projection `qproj` (weights folded at pack time, see smin.py:pack_weights).
 // =====================================================================================
 template <typename ActT, int DPL>
 __global__ void __launch_bounds__(256)
-content_attention_kernel(const ActT* __restrict__ c_hat, const float* __restrict__ ktil, const float* __restrict__ beta,
-                         const float* __restrict__ w_hat, const float* __restrict__ s_hat,
+content_attention_kernel(const ActT* __restrict__ c_hat, const float* __restrict__ qproj, int ld, int off_what,
+                         int off_ktil, int off_beta, const float* __restrict__ s_hat, int s_ld,
                          const uint8_t* __restrict__ qmask, const int32_t* __restrict__ row_start,
                          ActT* __restrict__ cc_hat, int L, int Nq, int capacity) {
   constexpr int C = 4, DL = DPL * 32, KS = DL + 1;
@@ -286,12 +287,13 @@ content_attention_kernel(const ActT* __restrict__ c_hat, const float* __restrict
 
   for (int e = tid; e < Nq * DL; e += blockDim.x) {
     const int k = e / DL, dcol = e % DL;
-    s_k[k * KS + dcol] = ktil[((size_t)b * Nq + k) * DL + dcol];
-    s_w[e] = w_hat[((size_t)b * Nq) * DL + e];
+    const float* qr = qproj + ((size_t)b * Nq + k) * ld;
+    s_k[k * KS + dcol] = qr[off_ktil + dcol];
+    s_w[e] = qr[off_what + dcol];
   }
-  for (int e = tid; e < DL; e += blockDim.x) s_s[e] = s_hat[(size_t)b * DL + e];
+  for (int e = tid; e < DL; e += blockDim.x) s_s[e] = s_hat[(size_t)b * s_ld + e];
   if (tid < 32) {
-    s_b[tid] = tid < Nq ? beta[(size_t)b * Nq + tid] : 0.f;
+    s_b[tid] = tid < Nq ? qproj[((size_t)b * Nq + tid) * ld + off_beta] : 0.f;
     s_m[tid] = tid < Nq ? (qmask[(size_t)b * Nq + tid] ? 1.f : 0.f) : 0.f;
   }
   __syncthreads();
@@ -396,9 +398,9 @@ content_attention_kernel(const ActT* __restrict__ c_hat, const float* __restrict
 }
 
 template <typename ActT, int DPL>
-static int launch_content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat,
-                                    const float* s_hat, const uint8_t* qmask, vml_cells_t cells, void* cc_hat, int B,
-                                    vml_dims_t d, cudaStream_t st) {
+static int launch_content_attention(const void* c_hat, const float* qproj, int ld, int off_what, int off_ktil,
+                                    int off_beta, const float* s_hat, int s_ld, const uint8_t* qmask,
+                                    vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, cudaStream_t st) {
   constexpr int DL = DPL * 32;
   const size_t smem = sizeof(float) * ((size_t)d.Nq * (DL + 1) + (size_t)d.Nq * DL + DL + 64 + 8 * 4 * DL + 8 * 4 * 32);
   VML_CUDA(cudaFuncSetAttribute(content_attention_kernel<ActT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -406,98 +408,45 @@ static int launch_content_attention(const void* c_hat, const float* ktil, const 
   int chunks = ceil_div(vmax, 8 * 4);             // ~4 cells per warp
   while ((int64_t)chunks * B > (int64_t)kNumSMs * 16 && chunks > 1) chunks = (chunks + 1) / 2;
   dim3 grid(chunks, B);
-  content_attention_kernel<ActT, DPL><<<grid, 256, smem, st>>>((const ActT*)c_hat, ktil, beta, w_hat, s_hat, qmask,
-                                                               cells.row_start, (ActT*)cc_hat, d.L, d.Nq, cells.capacity);
+  content_attention_kernel<ActT, DPL><<<grid, 256, smem, st>>>((const ActT*)c_hat, qproj, ld, off_what, off_ktil, off_beta,
+                                                               s_hat, s_ld, qmask, cells.row_start, (ActT*)cc_hat, d.L,
+                                                               d.Nq, cells.capacity);
   VML_LAUNCHED(1);
   return VML_OK;
 }
 
-int content_attention(const void* c_hat, const float* ktil, const float* beta, const float* w_hat, const float* s_hat,
-                      const uint8_t* qmask, vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, int prec, cudaStream_t st) {
+int content_attention(const void* c_hat, const float* qproj, int ld, int off_what, int off_ktil, int off_beta,
+                      const float* s_hat, int s_ld, const uint8_t* qmask, vml_cells_t cells, void* cc_hat, int B,
+                      vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.C == 4 && d.Nq <= 32 && (d.dl == 32 || d.dl == 64 || d.dl == 128));
   static bool reg = (register_kernel("content_attention_kernel"), true); (void)reg;
-#define VML_CA(T, P) return launch_content_attention<T, P>(c_hat, ktil, beta, w_hat, s_hat, qmask, cells, cc_hat, B, d, st)
+#define VML_CA(T, P) \
+  return launch_content_attention<T, P>(c_hat, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, cc_hat, B, d, st)
   if (prec == VML_BF16) { if (d.dl == 128) VML_CA(bf16, 4); if (d.dl == 64) VML_CA(bf16, 2); VML_CA(bf16, 1); }
   if (d.dl == 128) VML_CA(float, 4); if (d.dl == 64) VML_CA(float, 2); VML_CA(float, 1);
 #undef VML_CA
 }
 
 // =====================================================================================
-// query-side precompute for the ContentUnit (models.py:249-251 and the key half of :209)
-// =====================================================================================
-__global__ void query_prep_kernel(const float* __restrict__ wproj, int ld, int col0, const float* __restrict__ fs,
-                                  const uint8_t* __restrict__ qmask, const float* __restrict__ Wk, const float* __restrict__ bk,
-                                  const float* __restrict__ Wq, const float* __restrict__ bq, const float* __restrict__ Ws,
-                                  const float* __restrict__ bs, float* __restrict__ w_hat, float* __restrict__ ktil,
-                                  float* __restrict__ beta, float* __restrict__ s_hat, int Nq, int D, int dl) {
-  extern __shared__ float sq[];
-  float* s_w = sq;             // [Nq][dl]  w_hat
-  float* s_kc = s_w + Nq * dl; // [Nq][dl]  kc
-  const int b = blockIdx.x, m = threadIdx.x;  // blockDim.x == dl
-  for (int k = 0; k < Nq; ++k) {
-    const float q = qmask[(size_t)b * Nq + k] ? 1.f : 0.f;
-    const float v = wproj[((size_t)b * Nq + k) * ld + col0 + m] * q;
-    s_w[k * dl + m] = v;
-    w_hat[((size_t)b * Nq + k) * dl + m] = v;
-  }
-  __syncthreads();
-  for (int k = 0; k < Nq; ++k) {          // kc[k][m] = w_hat[k].Wk[m] + bk[m]
-    float acc = 0.f;
-    const float* wr = Wk + (size_t)m * dl;
-    for (int e = 0; e < dl; ++e) acc = fmaf(s_w[k * dl + e], wr[e], acc);
-    s_kc[k * dl + m] = acc + bk[m];
-  }
-  __syncthreads();
-  for (int k = 0; k < Nq; ++k) {          // ktil[k][m] = sum_e kc[k][e] * Wq[e][m]
-    float acc = 0.f;
-    for (int e = 0; e < dl; ++e) acc = fmaf(s_kc[k * dl + e], Wq[(size_t)e * dl + m], acc);
-    ktil[((size_t)b * Nq + k) * dl + m] = acc;
-  }
-  if (m < Nq) {                           // beta[k] = kc[k].bq
-    float acc = 0.f;
-    for (int e = 0; e < dl; ++e) acc = fmaf(s_kc[m * dl + e], bq[e], acc);
-    beta[(size_t)b * Nq + m] = acc;
-  }
-  {                                       // s_hat[m] = fs.Ws[m] + bs[m]
-    float acc = 0.f;
-    const float* wr = Ws + (size_t)m * D;
-    const float* f = fs + (size_t)b * D;
-    for (int e = 0; e < D; ++e) acc = fmaf(f[e], wr[e], acc);
-    s_hat[(size_t)b * dl + m] = acc + bs[m];
-  }
-}
-
-int query_prep(const float* wproj, int ld, int col0, const float* fs, const uint8_t* qmask, const float* Wk,
-               const float* bk, const float* Wq, const float* bq, const float* Ws, const float* bs, float* w_hat,
-               float* ktil, float* beta, float* s_hat, int B, vml_dims_t d, cudaStream_t st) {
-  VML_CHECK_ARG(d.dl >= d.Nq && d.dl <= 1024);
-  static bool reg = (register_kernel("query_prep_kernel"), true); (void)reg;
-  const size_t smem = sizeof(float) * 2 * d.Nq * d.dl;
-  query_prep_kernel<<<B, d.dl, smem, st>>>(wproj, ld, col0, fs, qmask, Wk, bk, Wq, bq, Ws, bs, w_hat, ktil, beta,
-                                          s_hat, d.Nq, d.D, d.dl);
-  VML_LAUNCHED(1);
-  return VML_OK;
-}
-
-// =====================================================================================
 // a7  BoundaryUnit  (Attention.forward models.py:137-154; BoundaryUnit.forward :164-196)
 // =====================================================================================
-// gate:  G[b,l,:] = fb * (softmax(q.k^T/sqrt(D))·fw * lmask + fs)
+// gate:  G[b,l,:] = fb * (softmax(q.k^T/sqrt(D))·fw * lmask + fs), with q.k^T = fb.kbt^T + beta_b
+// (W_q folded into the per-word keys kbt at pack time, so no per-layer projection of fb).
 __global__ void __launch_bounds__(128)
-boundary_gate_kernel(const float* __restrict__ qb, const float* __restrict__ kb, int ldk, int col0,
+boundary_gate_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab,
                      const float* __restrict__ fw, const float* __restrict__ fs, const float* __restrict__ fb,
                      const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ lmask, float* __restrict__ G,
                      int L, int Nq, int D) {
   __shared__ float s_p[32];
   const int row = blockIdx.x, b = row / L;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const float* q = qb + (size_t)row * D;
+  const float* q = fb + (size_t)row * D;
   for (int k = warp; k < Nq; k += 4) {
-    const float* kr = kb + ((size_t)b * Nq + k) * ldk + col0;
+    const float* kr = qproj + ((size_t)b * Nq + k) * ld;
     float acc = 0.f;
-    for (int e = lane; e < D; e += 32) acc = fmaf(q[e], kr[e], acc);
+    for (int e = lane; e < D; e += 32) acc = fmaf(q[e], kr[off_kbt + e], acc);
     acc = warp_sum(acc);
-    if (lane == 0) s_p[k] = acc;
+    if (lane == 0) s_p[k] = acc + kr[off_betab];
   }
   __syncthreads();
   if (warp == 0) {
@@ -575,12 +524,12 @@ boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, c
   }
 }
 
-int boundary_unit(const float* qb, const float* kb, int ldk, int col0, const float* fw, const float* fs,
+int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                   const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
                   float* g_scratch, float* bu, int B, vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.Nq <= 32);
   static bool reg = (register_kernel("boundary_gate_kernel"), register_kernel("boundary_row_kernel"), true); (void)reg;
-  boundary_gate_kernel<<<B * d.L, 128, 0, st>>>(qb, kb, ldk, col0, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
+  boundary_gate_kernel<<<B * d.L, 128, 0, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
   const size_t smem = sizeof(float) * d.L;
   if (prec == VML_BF16)
     boundary_row_kernel<bf16><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const bf16*)fm, lmask, cells.code,

@@ -104,53 +104,90 @@ def _round_up(x, m):
 
 
 # ---------------------------------------------------------------------------------------
-# weight packing (layout transforms only; done once per parameter version)
+# weight packing (layout transforms + algebraic folding of weight-only products; done once
+# per parameter version, in fp64)
 # ---------------------------------------------------------------------------------------
+def query_layout(dims: Dims):
+    """Column layout of the folded query projection qproj[B*Nq + B, ld]:
+    per SMI layer k a block [ w_hat (dl) | ktil (dl) | kbt (D) | beta, beta_b, 6 pad ],
+    then s_hat of every layer (dl each); ld padded to a multiple of 128."""
+    blk = 2 * dims.dl + dims.D + 8
+    n = dims.layers * blk + dims.layers * dims.dl
+    lay = {"blk": blk, "n": n, "ld": _round_up(n, 128), "s0": dims.layers * blk}
+    return lay
+
+
 def pack_weights(sd: Dict[str, torch.Tensor], dims: Dims, prec: int, device) -> Dict[str, torch.Tensor]:
-    """Re-lay the reference-named parameters for the kernels: concatenated LSTM input
-    projections, transposed recurrent weights, concatenated query-side projections,
-    [W_fb | W_fc] for the moment unit, bf16 copies (K padded to a TMA-legal stride)."""
+    """Re-lay the reference-named parameters for the kernels.
+
+    * LSTM: input projections of both directions concatenated, b_ih + b_hh summed, W_hh transposed.
+    * Query side: every projection of the (layer-invariant) word states fw and sentence state fs
+      is folded into ONE matrix (see ``query_layout``):
+        w_hat  = fw.Ww^T + bw                                        (models.py:249, valid words)
+        ktil   = (w_hat.Wk^T + bk).Wq      so that  Q.K^T = c_hat.ktil^T + beta   (models.py:209-211)
+        beta   = (w_hat.Wk^T + bk).bq
+        kbt    = (fw.WK^T + bK).WQ         so that  (fb.WQ^T+bQ).(fw.WK^T+bK)^T = fb.kbt^T + beta_b
+        beta_b = (fw.WK^T + bK).bQ                                   (models.py:139-141)
+        s_hat  = fs.Ws^T + bs                                        (models.py:251)
+      The products of weight matrices are formed here in fp64.  Masked words never contribute
+      (their softmax weight is exactly 0), so the reference's ``* query_mask`` on w_hat is moot.
+    * Moment unit: [W_fb | W_fc] concatenated along K, biases summed.
+    * bf16 mode: bf16 copies of the GEMM operands, K padded to a TMA-legal stride."""
+    f64 = lambda t: t.detach().to(device=device, dtype=torch.float64)
     f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+    wdt = torch.bfloat16 if prec == L_.BF16 else torch.float32
     H, D, dl, layers = dims.H, dims.D, dims.dl, dims.layers
     pk: Dict[str, torch.Tensor] = {}
+
+    def gemm_weight(w, k_to=None):
+        """[N,K] -> operand dtype, K zero-padded to k_to."""
+        w = w.to(torch.float32)
+        if k_to is not None and k_to != w.shape[1]:
+            w = torch.nn.functional.pad(w, (0, k_to - w.shape[1]))
+        return w.to(wdt).contiguous()
+
     ve = "backbone.videoencoder."
     pk["ve_b"] = f32(sd[ve + "ve.bias"])
     pk["pe"] = f32(sd[ve + "pe.weight"])
-    w_ve = f32(sd[ve + "ve.weight"])
-    if prec == L_.BF16:
-        kp = _round_up(dims.d0, 8)
-        w = torch.zeros(D, kp, device=device, dtype=torch.bfloat16)
-        w[:, : dims.d0] = w_ve.to(torch.bfloat16)
-        pk["ve_w"] = w
-        pk["ve_kpad"] = kp
-    else:
-        pk["ve_w"] = w_ve
-        pk["ve_kpad"] = dims.d0
+    pk["ve_kpad"] = _round_up(dims.d0, 8) if prec == L_.BF16 else dims.d0
+    pk["ve_w"] = gemm_weight(f32(sd[ve + "ve.weight"]), pk["ve_kpad"])
     ls = "backbone.queryencoder.lstm."
+    pk["q_kpad"] = _round_up(300, 8) if prec == L_.BF16 else 300
     for layer in range(2):
         wih = torch.cat([f32(sd[f"{ls}weight_ih_l{layer}"]), f32(sd[f"{ls}weight_ih_l{layer}_reverse"])], 0)
         bias = torch.cat([f32(sd[f"{ls}bias_ih_l{layer}"]) + f32(sd[f"{ls}bias_hh_l{layer}"]),
                           f32(sd[f"{ls}bias_ih_l{layer}_reverse"]) + f32(sd[f"{ls}bias_hh_l{layer}_reverse"])], 0)
         whh_t = torch.stack([f32(sd[f"{ls}weight_hh_l{layer}"]).t().contiguous(),
                              f32(sd[f"{ls}weight_hh_l{layer}_reverse"]).t().contiguous()], 0)
-        pk[f"lstm_wih{layer}"], pk[f"lstm_b{layer}"], pk[f"lstm_whht{layer}"] = wih.contiguous(), bias, whh_t.contiguous()
-    qw, qb = [], []
+        pk[f"lstm_wih{layer}"] = gemm_weight(wih, pk["q_kpad"] if layer == 0 else None)
+        pk[f"lstm_b{layer}"], pk[f"lstm_whht{layer}"] = bias.contiguous(), whh_t.contiguous()
+
+    lay = query_layout(dims)
+    qw = torch.zeros(lay["ld"], D, device=device, dtype=torch.float64)
+    qb = torch.zeros(lay["ld"], device=device, dtype=torch.float64)
     for k in range(layers):
         cu, bu, mu = f"smis.{k}.content_unit.", f"smis.{k}.boundary_unit.attn_layer.", f"smis.{k}.moment_unit."
-        qw += [f32(sd[cu + "linear_w_hat.weight"]), f32(sd[bu + "W_k.weight"])]
-        qb += [f32(sd[cu + "linear_w_hat.bias"]), f32(sd[bu + "W_k.bias"])]
-        for nm, key in (("ck_w", "attn_layer.W_k.weight"), ("ck_b", "attn_layer.W_k.bias"), ("cq_w", "attn_layer.W_q.weight"),
-                        ("cq_b", "attn_layer.W_q.bias"), ("cs_w", "linear_s_hat.weight"), ("cs_b", "linear_s_hat.bias"),
-                        ("chat_b", "linear_c_hat.bias"), ("cout_b", "linear_c.bias")):
-            pk[f"{nm}{k}"] = f32(sd[cu + key])
-        chat_w, cout_w = f32(sd[cu + "linear_c_hat.weight"]), f32(sd[cu + "linear_c.weight"])
-        mu_w = torch.cat([f32(sd[mu + "conv_layer_fb.weight"]).view(D, D), f32(sd[mu + "conv_layer_fc.weight"]).view(D, D)], 1)
+        Ww, bw = f64(sd[cu + "linear_w_hat.weight"]), f64(sd[cu + "linear_w_hat.bias"])
+        Wk, bk = f64(sd[cu + "attn_layer.W_k.weight"]), f64(sd[cu + "attn_layer.W_k.bias"])
+        Wq, bq = f64(sd[cu + "attn_layer.W_q.weight"]), f64(sd[cu + "attn_layer.W_q.bias"])
+        WK, bK = f64(sd[bu + "W_k.weight"]), f64(sd[bu + "W_k.bias"])
+        WQ, bQ = f64(sd[bu + "W_q.weight"]), f64(sd[bu + "W_q.bias"])
+        kc_w, kc_b = Wk @ Ww, Wk @ bw + bk                    # kc = fw.kc_w^T + kc_b
+        o = k * lay["blk"]
+        qw[o: o + dl], qb[o: o + dl] = Ww, bw                                        # w_hat
+        qw[o + dl: o + 2 * dl], qb[o + dl: o + 2 * dl] = Wq.t() @ kc_w, Wq.t() @ kc_b    # ktil
+        qw[o + 2 * dl: o + 2 * dl + D], qb[o + 2 * dl: o + 2 * dl + D] = WQ.t() @ WK, WQ.t() @ bK   # kbt
+        qw[o + 2 * dl + D], qb[o + 2 * dl + D] = kc_w.t() @ bq, kc_b @ bq            # beta
+        qw[o + 2 * dl + D + 1], qb[o + 2 * dl + D + 1] = WK.t() @ bQ, bK @ bQ        # beta_b
+        so = lay["s0"] + k * dl
+        qw[so: so + dl], qb[so: so + dl] = f64(sd[cu + "linear_s_hat.weight"]), f64(sd[cu + "linear_s_hat.bias"])
+        pk[f"chat_b{k}"], pk[f"cout_b{k}"] = f32(sd[cu + "linear_c_hat.bias"]), f32(sd[cu + "linear_c.bias"])
+        pk[f"chat_w{k}"] = gemm_weight(f32(sd[cu + "linear_c_hat.weight"]))
+        pk[f"cout_w{k}"] = gemm_weight(f32(sd[cu + "linear_c.weight"]))
+        pk[f"mu_w{k}"] = gemm_weight(torch.cat([f32(sd[mu + "conv_layer_fb.weight"]).view(D, D),
+                                                f32(sd[mu + "conv_layer_fc.weight"]).view(D, D)], 1))
         pk[f"mu_b{k}"] = f32(sd[mu + "conv_layer_fb.bias"]) + f32(sd[mu + "conv_layer_fc.bias"])
-        pk[f"bq_w{k}"], pk[f"bq_b{k}"] = f32(sd[bu + "W_q.weight"]), f32(sd[bu + "W_q.bias"])
-        if prec == L_.BF16:
-            chat_w, cout_w, mu_w = (t.to(torch.bfloat16).contiguous() for t in (chat_w, cout_w, mu_w))
-        pk[f"chat_w{k}"], pk[f"cout_w{k}"], pk[f"mu_w{k}"] = chat_w, cout_w, mu_w.contiguous()
-    pk["qcat_w"], pk["qcat_b"] = torch.cat(qw, 0).contiguous(), torch.cat(qb, 0).contiguous()
+    pk["qcat_w"], pk["qcat_b"] = gemm_weight(qw), qb.to(torch.float32).contiguous()
     lo = "localization.conv_layer_"
     pk["loc_w"] = torch.stack([f32(sd[lo + n + ".weight"]).reshape(D) for n in ("pm", "ps", "pe", "pa")], 0).contiguous()
     pk["loc_b"] = torch.cat([f32(sd[lo + n + ".bias"]).reshape(1) for n in ("pm", "ps", "pe", "pa")], 0).contiguous()
@@ -215,31 +252,37 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
     mark("clip_projection")
 
     # ---- a2 query encoder ------------------------------------------------------------------
+    bf = prec == L_.BF16
     qlen = ws.get("qlen", (B,), torch.int32)
     call("vml_query_lengths", ptr(qmask), ptr(qlen), B, Nq, st)
     gin = ws.get("gin", (B * Nq, 8 * H), f32)
     y0 = ws.get("lstm_y0", (B, Nq, 2 * H), f32)
-    fw = ws.get("fw", (B, Nq, 2 * H), f32)
-    fs = ws.get("fs", (B, 2 * H), f32)
-    call("vml_linear", ptr(qf), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, 300, 8 * H, None, 1, L_.FP32, 1, st)
-    call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), None, None, B, Nq, H, st)
-    call("vml_linear", ptr(y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin), B * Nq, 8 * H, 2 * H, 8 * H, None, 1, L_.FP32, 1, st)
-    call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), None, ptr(fs), B, Nq, H, st)
+    fwfs = ws.get("fwfs", (B * Nq + B, 2 * H), f32)            # word states, then sentence states
+    fw, fs = fwfs[: B * Nq].view(B, Nq, 2 * H), fwfs[B * Nq:]
+    y0h = ws.get("lstm_y0_bf16", (B, Nq, 2 * H), torch.bfloat16) if bf else None
+    fwfs_h = ws.get("fwfs_bf16", (B * Nq + B, 2 * H), torch.bfloat16) if bf else None
+    if bf:
+        qk = pk["q_kpad"]
+        q16 = ws.get("q16", (B * Nq, qk), torch.bfloat16)
+        call("vml_cast_pad_bf16", ptr(qf), ptr(q16), B * Nq, 300, qk, st)
+        call("vml_linear", ptr(q16), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, qk, 8 * H, None, 1, prec, 1, st)
+    else:
+        call("vml_linear", ptr(qf), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, 300, 8 * H, None, 1, prec, 1, st)
+    call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), ptr(y0h), None, None, B, Nq, H, st)
+    call("vml_linear", ptr(y0h if bf else y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin), B * Nq, 8 * H, 2 * H, 8 * H,
+         None, 1, prec, 1, st)
+    call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), ptr(fwfs_h), ptr(fs),
+         None if not bf else fwfs_h.data_ptr() + B * Nq * 2 * H * 2, B, Nq, H, st)
     mark("query_lstm")
 
-    # query-side projections of every SMI layer, hoisted (fw / fs do not change across layers)
-    ncat = layers * (dl + D)
-    wproj = ws.get("wproj", (B * Nq, ncat), f32)
-    call("vml_linear", ptr(fw), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(wproj), B * Nq, ncat, D, ncat, None, 1, L_.FP32, 1, st)
-    w_hat = ws.get("w_hat", (layers, B, Nq, dl), f32)
-    ktil = ws.get("ktil", (layers, B, Nq, dl), f32)
-    beta = ws.get("beta", (layers, B, Nq), f32)
-    s_hat = ws.get("s_hat", (layers, B, dl), f32)
-    for k in range(layers):
-        call("vml_query_prep", ptr(wproj), ncat, k * (dl + D), ptr(fs), ptr(qmask), ptr(pk[f"ck_w{k}"]), ptr(pk[f"ck_b{k}"]),
-             ptr(pk[f"cq_w{k}"]), ptr(pk[f"cq_b{k}"]), ptr(pk[f"cs_w{k}"]), ptr(pk[f"cs_b{k}"]), ptr(w_hat[k]), ptr(ktil[k]),
-             ptr(beta[k]), ptr(s_hat[k]), B, dims, st)
-    mark("query_prep")
+    # every query-side projection of every SMI layer in one GEMM (fw / fs do not change across layers)
+    lay = query_layout(dims)
+    ld = lay["ld"]
+    qproj = ws.get("qproj", (B * Nq + B, ld), f32)
+    call("vml_linear", ptr(fwfs_h if bf else fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(qproj), B * Nq + B, ld, D, ld,
+         None, 1, prec, 1, st)
+    s_hat_base = qproj.data_ptr() + (B * Nq * ld + lay["s0"]) * 4
+    mark("query_proj")
 
     # ---- cells + a3/a4 span pooling ---------------------------------------------------------
     cells = make_cells(ws, B, Lm)
@@ -256,7 +299,6 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
 
     c_hat = ws.get("c_hat", (cap * Cc, dl), act)
     cc_hat = ws.get("cc_hat", (cap * Cc, dl), act)
-    qb = ws.get("bu_q", (B * Lm, D), f32)
     g_scr = ws.get("bu_g", (B, Lm, D), f32)
     mu_op = ws.get("mu_op", (cap, 2 * D), act)
     n_dev = cells.n_cells
@@ -264,16 +306,16 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
     for k in range(layers):
         nxt = cur ^ 1
         # a7 boundary unit
-        call("vml_linear", ptr(fb[cur]), ptr(pk[f"bq_w{k}"]), ptr(pk[f"bq_b{k}"]), ptr(qb), B * Lm, D, D, D, None, 1, L_.FP32, 1, st)
-        call("vml_boundary_unit", ptr(qb), ptr(wproj), ncat, k * (dl + D) + dl, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
+        o = k * lay["blk"]
+        call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
              ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(fb[nxt]), B, dims, prec, st)
         mark("boundary_unit")
         # a5+a6 content unit
         call("vml_linear", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl, n_dev, Cc,
              prec, 0, st)
         mark("content_in_gemm")
-        call("vml_content_attention", ptr(c_hat), ptr(ktil[k]), ptr(beta[k]), ptr(w_hat[k]), ptr(s_hat[k]), ptr(qmask), cells,
-             ptr(cc_hat), B, dims, prec, st)
+        call("vml_content_attention", ptr(c_hat), ptr(qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
+             ptr(qmask), cells, ptr(cc_hat), B, dims, prec, st)
         mark("content_attention")
         call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]), ptr(fs),
              cells, ptr(fc[nxt]), dims, prec, st)
