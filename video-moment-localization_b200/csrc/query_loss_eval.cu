@@ -23,7 +23,10 @@ __global__ void query_lengths_kernel(const uint8_t* __restrict__ qmask, int32_t*
 // traffic.  Per step: (A) thread (u, ks) accumulates the 4 gates of unit u for all 8 samples
 // over K-slice ks; (B) thread (u, s) reduces the 8 slices, applies the cell update for
 // (unit u, sample s) and writes h_t into the h buffer of every CTA of the cluster through
-// distributed shared memory; one cluster barrier per step.
+// distributed shared memory; one cluster barrier per step.  Inside the loop there are no
+// global stores (outputs are staged in shared memory and written once at the end, so the
+// barrier's release fence only covers the DSMEM stores) and the next step's input-projection
+// values are prefetched one step ahead.
 constexpr int LSTM_CL = 8;   // CTAs per cluster == K-slices == samples per tile
 
 __global__ void __cluster_dims__(LSTM_CL, 1, 1)
@@ -36,8 +39,9 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
   extern __shared__ __align__(16) float lsm[];
   const int UH = H / LSTM_CL, KS = H / LSTM_CL;
   float* Wsl = lsm;                       // [H][4][UH]
-  float* hbuf = Wsl + (size_t)H * 4 * UH; // [2][H][BT]
+  float* hbuf = Wsl + (size_t)H * 4 * UH; // [2][BT][H]   (sample-major: a warp's DSMEM store is 128 contiguous bytes)
   float* part = hbuf + 2 * H * BT;        // [8 ks][BT][4][UH]
+  float* ybuf = part + LSTM_CL * BT * 4 * UH;  // [Nq][BT][UH] staged outputs of this CTA's units
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / LSTM_CL;   // cluster id
   const int dir = cid & 1, b0 = (cid >> 1) * BT;
@@ -46,11 +50,11 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
   const int unit = rank * UH + u;
 
   const float* W = whh_t + (size_t)dir * H * 4 * H;
-  for (int e = tid; e < H * 4 * UH; e += blockDim.x) {
-    const int k = e / (4 * UH), g = (e / UH) % 4, uu = e % UH;
-    Wsl[e] = W[(size_t)k * 4 * H + g * H + rank * UH + uu];
-  }
+  for (int k = ks; k < H; k += LSTM_CL)   // rows of W^T: 4 gate segments of UH contiguous floats
+#pragma unroll
+    for (int g = 0; g < 4; ++g) Wsl[((size_t)k * 4 + g) * UH + u] = W[(size_t)k * 4 * H + g * H + unit];
   for (int e = tid; e < 2 * H * BT; e += blockDim.x) hbuf[e] = 0.f;
+  for (int e = tid; e < Nq * BT * UH; e += blockDim.x) ybuf[e] = 0.f;   // zeros past the length (pad_packed_sequence)
 
   const int s = ks;                        // phase-B sample slot
   const int bs = b0 + s;
@@ -58,21 +62,32 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
   int maxlen = 0;
   for (int t = 0; t < BT; ++t) maxlen = max(maxlen, (b0 + t < B) ? min(qlen[b0 + t], Nq) : 0);
   float c_state = 0.f, h_state = 0.f;
+  // DSMEM destinations: element (s, unit) of every peer's h buffer; lanes of a warp hold
+  // consecutive units of one sample
   float* remote_h[LSTM_CL];
 #pragma unroll
-  for (int r = 0; r < LSTM_CL; ++r) remote_h[r] = cluster.map_shared_rank(hbuf, r);
+  for (int r = 0; r < LSTM_CL; ++r) remote_h[r] = cluster.map_shared_rank(hbuf, r) + (size_t)s * H + unit;
+
+  auto load_gin = [&](int step, float (&g)[4]) {
+    if (step < my_len) {
+      const int t = dir == 0 ? step : my_len - 1 - step;
+      const float* p = gin + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] = p[q * H];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] = 0.f;
+    }
+  };
+  float gnext[4];
+  load_gin(0, gnext);
   cluster.sync();
 
   for (int step = 0; step < maxlen; ++step) {
     const int cur = step & 1, nxt = cur ^ 1;
     const bool act = step < my_len;
-    const int t = dir == 0 ? step : my_len - 1 - step;
-    float gpre[4] = {0.f, 0.f, 0.f, 0.f};
-    if (act) {                              // issue early; consumed in phase B
-      const float* g = gin + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) gpre[q] = g[q * H];
-    }
+    float gpre[4] = {gnext[0], gnext[1], gnext[2], gnext[3]};
+    load_gin(step + 1, gnext);              // prefetch: consumed one step later
     // ---- phase A: partial gates over K-slice ks, all BT samples ---------------------------
     float acc[BT][4];
 #pragma unroll
@@ -80,17 +95,21 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[a][q] = 0.f;
     const float* hb = hbuf + (size_t)cur * H * BT;
-    for (int kk = 0; kk < KS; ++kk) {
-      const int k = ks * KS + kk;
-      const float* wr = Wsl + (size_t)k * 4 * UH + u;
-      const float w0 = wr[0], w1 = wr[UH], w2 = wr[2 * UH], w3 = wr[3 * UH];
-      const float4 ha = *reinterpret_cast<const float4*>(hb + k * BT);
-      const float4 hc = *reinterpret_cast<const float4*>(hb + k * BT + 4);
-      const float hv[BT] = {ha.x, ha.y, ha.z, ha.w, hc.x, hc.y, hc.z, hc.w};
+    for (int kk = 0; kk < KS; kk += 4) {
+      const int k0 = ks * KS + kk;
+      float4 h4[BT];
 #pragma unroll
-      for (int a = 0; a < BT; ++a) {
-        acc[a][0] = fmaf(hv[a], w0, acc[a][0]); acc[a][1] = fmaf(hv[a], w1, acc[a][1]);
-        acc[a][2] = fmaf(hv[a], w2, acc[a][2]); acc[a][3] = fmaf(hv[a], w3, acc[a][3]);
+      for (int a = 0; a < BT; ++a) h4[a] = *reinterpret_cast<const float4*>(hb + (size_t)a * H + k0);   // warp-uniform: broadcast
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* wr = Wsl + (size_t)(k0 + j) * 4 * UH + u;
+        const float w0 = wr[0], w1 = wr[UH], w2 = wr[2 * UH], w3 = wr[3 * UH];
+#pragma unroll
+        for (int a = 0; a < BT; ++a) {
+          const float hv = j == 0 ? h4[a].x : j == 1 ? h4[a].y : j == 2 ? h4[a].z : h4[a].w;
+          acc[a][0] = fmaf(hv, w0, acc[a][0]); acc[a][1] = fmaf(hv, w1, acc[a][1]);
+          acc[a][2] = fmaf(hv, w2, acc[a][2]); acc[a][3] = fmaf(hv, w3, acc[a][3]);
+        }
       }
     }
 #pragma unroll
@@ -111,20 +130,24 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
       const float ig = sigmoidf_(gate[0]), fg = sigmoidf_(gate[1]), gg = tanhf(gate[2]), og = sigmoidf_(gate[3]);
       c_state = fg * c_state + ig * gg;
       h_state = og * tanhf(c_state);
-      const size_t o = ((size_t)bs * Nq + t) * 2 * H + (size_t)dir * H + unit;
-      y[o] = h_state;
-      if (y16) y16[o] = __float2bfloat16_rn(h_state);
+      const int t = dir == 0 ? step : my_len - 1 - step;
+      ybuf[((size_t)t * BT + s) * UH + u] = h_state;
     }
 #pragma unroll
-    for (int r = 0; r < LSTM_CL; ++r) remote_h[r][(size_t)nxt * H * BT + (size_t)unit * BT + s] = h_state;
+    for (int r = 0; r < LSTM_CL; ++r) remote_h[r][(size_t)nxt * H * BT] = h_state;
     cluster.sync();                         // h_t visible everywhere; part[] and hbuf[cur] reusable
   }
-  if (bs < B) {
-    for (int t = my_len; t < Nq; ++t) {     // pad_packed_sequence: zeros past the length
-      const size_t o = ((size_t)bs * Nq + t) * 2 * H + (size_t)dir * H + unit;
-      y[o] = 0.f;
-      if (y16) y16[o] = __float2bfloat16_rn(0.f);
+  // ---- write the staged outputs: y[b, t, dir*H + unit] for this CTA's UH units --------------
+  for (int e = tid; e < Nq * BT * UH; e += blockDim.x) {
+    const int uu = e % UH, ss = (e / UH) % BT, t = e / (UH * BT);
+    if (b0 + ss < B) {
+      const size_t o = ((size_t)(b0 + ss) * Nq + t) * 2 * H + (size_t)dir * H + rank * UH + uu;
+      const float v = ybuf[e];
+      y[o] = v;
+      if (y16) y16[o] = __float2bfloat16_rn(v);
     }
+  }
+  if (bs < B) {
     if (fs) fs[(size_t)bs * 2 * H + (size_t)dir * H + unit] = h_state;  // fwd: h(len-1); bwd: h(0)
     if (fs16) fs16[(size_t)bs * 2 * H + (size_t)dir * H + unit] = __float2bfloat16_rn(h_state);
   }
@@ -143,7 +166,8 @@ int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float*
   VML_CHECK_ARG(H % 32 == 0 && H <= 1024);
   static bool reg = (register_kernel("lstm_cluster_kernel"), true); (void)reg;
   const int UH = H / LSTM_CL;
-  const size_t smem = sizeof(float) * ((size_t)H * 4 * UH + 2 * (size_t)H * LSTM_CL + (size_t)LSTM_CL * LSTM_CL * 4 * UH);
+  const size_t smem = sizeof(float) * ((size_t)H * 4 * UH + 2 * (size_t)H * LSTM_CL + (size_t)LSTM_CL * LSTM_CL * 4 * UH +
+                                       (size_t)Nq * LSTM_CL * UH);
   VML_CHECK_ARG(smem <= 227 * 1024);
   VML_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int clusters = 2 * ceil_div(B, LSTM_CL);
