@@ -84,3 +84,17 @@ def test_synth_batch_properties():
     b2 = synth.make_batch(cfg, 8, 5)
     assert all(torch.equal(b[k], b2[k]) for k in b)
     assert (b["length_mask"].sum(1) >= 3).all()          # >= 5 valid cells: top-5 well defined
+
+
+def test_dropin_modules_resolve_like_main_py_imports():
+    """`from models import SMIN` / `from utils import compute_ious` (main.py:3,5) resolve to this
+    implementation when the dropin directory precedes the reference on sys.path."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dropin = os.path.join(root, "video-moment-localization_b200", "dropin")
+    code = ("from models import SMIN; from utils import compute_ious, get_tokens; import vml_b200.smin as s, vml_b200.evaluate as e;"
+            "assert SMIN is s.SMIN and compute_ious is e.compute_ious; assert get_tokens('A man, walks.') == ['a','man','walks']; print('ok')")
+    env = dict(os.environ, PYTHONPATH=dropin)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr

@@ -2,6 +2,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace vml {
 
@@ -23,10 +24,11 @@ __global__ void query_lengths_kernel(const uint8_t* __restrict__ qmask, int32_t*
 // traffic.  Per step: (A) thread (u, ks) accumulates the 4 gates of unit u for all 8 samples
 // over K-slice ks; (B) thread (u, s) reduces the 8 slices, applies the cell update for
 // (unit u, sample s) and writes h_t into the h buffer of every CTA of the cluster through
-// distributed shared memory; one cluster barrier per step.  Inside the loop there are no
-// global stores (outputs are staged in shared memory and written once at the end, so the
-// barrier's release fence only covers the DSMEM stores) and the next step's input-projection
-// values are prefetched one step ahead.
+// distributed shared memory with st.async, whose completion is counted (complete_tx) on an
+// mbarrier of the DESTINATION CTA: a CTA starts step t+1 as soon as the 8 KB of h_t have landed
+// in its own buffer -- no cluster-wide barrier, no release fence in the loop.  Outputs are
+// staged in shared memory and written once at the end; the next step's input-projection values
+// are prefetched one step ahead.
 constexpr int LSTM_CL = 8;   // CTAs per cluster == K-slices == samples per tile
 
 __global__ void __cluster_dims__(LSTM_CL, 1, 1)
@@ -42,6 +44,7 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
   float* hbuf = Wsl + (size_t)H * 4 * UH; // [2][BT][H]   (sample-major: a warp's DSMEM store is 128 contiguous bytes)
   float* part = hbuf + 2 * H * BT;        // [8 ks][BT][4][UH]
   float* ybuf = part + LSTM_CL * BT * 4 * UH;  // [Nq][BT][UH] staged outputs of this CTA's units
+  __shared__ __align__(8) uint64_t hbar[2];    // one per h buffer: counts the bytes of h_t that have landed
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / LSTM_CL;   // cluster id
   const int dir = cid & 1, b0 = (cid >> 1) * BT;
@@ -62,11 +65,16 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
   int maxlen = 0;
   for (int t = 0; t < BT; ++t) maxlen = max(maxlen, (b0 + t < B) ? min(qlen[b0 + t], Nq) : 0);
   float c_state = 0.f, h_state = 0.f;
-  // DSMEM destinations: element (s, unit) of every peer's h buffer; lanes of a warp hold
-  // consecutive units of one sample
-  float* remote_h[LSTM_CL];
+  // DSMEM destinations: element (s, unit) of every peer's h buffer (lanes of a warp hold
+  // consecutive units of one sample) and the peer's mbarriers, as shared::cluster addresses
+  uint32_t remote_h[LSTM_CL], remote_bar[LSTM_CL];
 #pragma unroll
-  for (int r = 0; r < LSTM_CL; ++r) remote_h[r] = cluster.map_shared_rank(hbuf, r) + (size_t)s * H + unit;
+  for (int r = 0; r < LSTM_CL; ++r) {
+    remote_h[r] = ptx::mapa(ptx::smem_u32(hbuf + (size_t)s * H + unit), r);
+    remote_bar[r] = ptx::mapa(ptx::smem_u32(&hbar[0]), r);
+  }
+  if (tid == 0) { ptx::mbar_init(&hbar[0], 1); ptx::mbar_init(&hbar[1], 1); ptx::fence_barrier_init(); }
+  const uint32_t step_bytes = (uint32_t)(H * BT * sizeof(float));
 
   auto load_gin = [&](int step, float (&g)[4]) {
     if (step < my_len) {
@@ -88,6 +96,7 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
     const bool act = step < my_len;
     float gpre[4] = {gnext[0], gnext[1], gnext[2], gnext[3]};
     load_gin(step + 1, gnext);              // prefetch: consumed one step later
+    if (tid == 0) ptx::mbar_arrive_expect_tx(&hbar[nxt], step_bytes);   // arm this step's receive barrier
     // ---- phase A: partial gates over K-slice ks, all BT samples ---------------------------
     float acc[BT][4];
 #pragma unroll
@@ -134,8 +143,9 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
       ybuf[((size_t)t * BT + s) * UH + u] = h_state;
     }
 #pragma unroll
-    for (int r = 0; r < LSTM_CL; ++r) remote_h[r][(size_t)nxt * H * BT] = h_state;
-    cluster.sync();                         // h_t visible everywhere; part[] and hbuf[cur] reusable
+    for (int r = 0; r < LSTM_CL; ++r)
+      ptx::st_async_f32(remote_h[r] + (uint32_t)(nxt * H * BT * sizeof(float)), h_state, remote_bar[r] + (uint32_t)(nxt * 8));
+    ptx::mbar_wait(&hbar[nxt], (uint32_t)((step >> 1) & 1));   // all of h_t has landed in MY buffer
   }
   // ---- write the staged outputs: y[b, t, dir*H + unit] for this CTA's UH units --------------
   for (int e = tid; e < Nq * BT * UH; e += blockDim.x) {
