@@ -131,25 +131,40 @@ VML_API int vml_content_attention(const void* c_hat, const float* qproj, int ld,
                                   int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask,
                                   vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, int prec, void* stream);
 
-/* cu = cc_hat.Wc^T + bc + fc + sigmoid(fm*fs)*fm   (models.py:269-276). */
+/* Fused front half of the unit (VML_BF16, dl = 128, C = 4, Nq <= 24): c_hat = fc.W^T + bias on
+ * tcgen05, then attention / gate / clip self-attention in the same kernel; c_hat never leaves
+ * the SM.  fc bf16 [cap*4, D], W bf16 [128, D], cc_hat bf16 [cap*4, 128]. */
+VML_API int vml_content_in_attention(const void* fc, const void* W, const float* bias, const float* qproj, int ld,
+                                     int off_what, int off_ktil, int off_beta, const float* s_hat, int s_ld,
+                                     const uint8_t* query_mask, vml_cells_t cells, void* cc_hat, int B,
+                                     vml_dims_t d, void* stream);
+
+/* cu = cc_hat.Wc^T + bc + fc + sigmoid(fm*fs)*fm   (models.py:269-276).  VML_BF16 with fbar and
+ * mu_operand non-NULL selects the fused epilogue: the gate term is read from fbar (see
+ * vml_boundary_unit) and mean_c cu (models.py:297) is written to mu_operand[n, D:2D]. */
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm,
-                    const float* fs, vml_cells_t cells, void* cu, vml_dims_t d, int prec, void* stream);
+                            const float* fs, const void* fbar, void* mu_operand, vml_cells_t cells, void* cu,
+                            vml_dims_t d, int prec, void* stream);
 
 /* ---- a7: BoundaryUnit (models.py:137-154,164-196) ------------------------------------------- */
 
 /* Boundary-word scores use the W_q-folded keys kbt (column off_kbt of qproj) and their bias
  * term beta_b (column off_betab): (fb.Wq^T+bq).(fw.Wk^T+bk)^T = fb.kbt^T + beta_b.
- * g_scratch float [B,L,D].  bu float [B,L,D] = f_bb + f_b + f_bm. */
+ * g_scratch float [B,L,D].  bu float [B,L,D] = f_bb + f_b + f_bm.
+ * fbar (optional, act [n, D]) receives sigmoid(fm*fs)*fm per cell (models.py:191 == :272-274),
+ * which the fused content-out epilogue reuses instead of recomputing it per clip. */
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask,
-                      const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* bu, int B,
-                      vml_dims_t d, int prec, void* stream);
+                      const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* bu, void* fbar,
+                      int B, vml_dims_t d, int prec, void* stream);
 
 /* ---- a8: MomentUnit (models.py:288-303) ------------------------------------------------------ */
 
 /* operand[n, 2D] = [ bu[b,i]*bu[b,j] | mean_c cu[n,c,:] ]  (act) */
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d,
                        int prec, void* stream);
+/* operand[n, 0:D] = bu[b,i]*bu[b,j] only (the other half comes from the fused content-out epilogue) */
+VML_API int vml_moment_pair(const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream);
 /* mu = operand.[Wfb|Wfc]^T + (bfb+bfc) + fm */
 VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* bias_sum, const void* fm,
                    vml_cells_t cells, void* mu, vml_dims_t d, int prec, void* stream);

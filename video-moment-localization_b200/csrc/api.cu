@@ -72,7 +72,10 @@ int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*,
 int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
                       void*, int, vml_dims_t, int, cudaStream_t);
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
-                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, int, vml_dims_t, int, cudaStream_t);
+                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, void*, int, vml_dims_t, int, cudaStream_t);
+int moment_pair(const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
+int content_fused(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
+                  vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
              float*, int, vml_dims_t, int, cudaStream_t);
@@ -171,10 +174,22 @@ VML_API int vml_content_attention(const void* c_hat, const float* qproj, int ld,
                            ST(stream));
 }
 
+VML_API int vml_content_in_attention(const void* fc, const void* W, const float* bias, const float* qproj, int ld, int off_what,
+                             int off_ktil, int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask,
+                             vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, void* stream) {
+  return content_fused(fc, W, bias, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, cc_hat, B, d,
+                       ST(stream));
+}
+
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm, const float* fs,
-                    vml_cells_t cells, void* cu, vml_dims_t d, int prec, void* stream) {
+                    const void* fbar, void* mu_operand, vml_cells_t cells, void* cu, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
   const int M = cells.capacity * d.C;
+  if (prec == VML_BF16 && fbar && mu_operand) {
+    VML_CHECK_ARG(d.C == 4 && d.D % 32 == 0);
+    EpiContentOutFused e{bc, (const bf16*)fc, (const bf16*)fbar, (bf16*)cu, (bf16*)mu_operand, d.D};
+    return launch_gemm_umma(cc_hat, Wc, M, d.D, d.dl, d.dl, d.dl, cells.n_cells, d.C, e, ST(stream));
+  }
   if (prec == VML_BF16) {
     EpiContentOut<bf16> e{bc, (const bf16*)fc, (const bf16*)fm, fs, cells.code, d.C, (bf16*)cu, d.D};
     return gemm_dispatch(cc_hat, Wc, M, d.D, d.dl, d.dl, cells.n_cells, d.C, e, prec, ST(stream));
@@ -185,15 +200,20 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
-                      vml_cells_t cells, float* g_scratch, float* bu, int B, vml_dims_t d, int prec, void* stream) {
+                      vml_cells_t cells, float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
-  return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, bu, B, d, prec,
-                       ST(stream));
+  return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, bu, fbar, B, d,
+                       prec, ST(stream));
 }
 
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
   return moment_operand(cu, bu, cells, operand, d, prec, ST(stream));
+}
+
+VML_API int vml_moment_pair(const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return moment_pair(bu, cells, operand, d, prec, ST(stream));
 }
 
 VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* bias_sum, const void* fm, vml_cells_t cells,

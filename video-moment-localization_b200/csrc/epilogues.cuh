@@ -82,6 +82,50 @@ struct EpiContentOut {
   }
 };
 
+// a6 tail, fused variant for the tcgen05 GEMM (thread == row, C == 4 so one cell == 4 adjacent lanes):
+//   cu = (acc + bias) + fc + fbar,   fbar = sigmoid(fm*fs)*fm precomputed per CELL by the boundary unit
+//   (it needs the same quantity for f_bm, models.py:191-194 == :272-274), and the moment unit's
+//   operand half  mean_c cu  (models.py:297) is reduced with two warp shuffles and stored here.
+struct EpiContentOutFused {
+  static constexpr bool kWarpCollective = true;
+  const float* bias;   // [D]
+  const bf16* fc;      // [n*4, D]
+  const bf16* fbar;    // [n, D]
+  bf16* out;           // [n*4, D]
+  bf16* op;            // [n, 2D]: columns D.. receive mean_c cu
+  int ldo;             // D
+  template <int N>
+  __device__ __forceinline__ void apply_warp(int row, int col0, const float* acc, bool valid) const {
+    const int cell = row >> 2;
+    const bf16* x = fc + (size_t)row * ldo + col0;
+    const bf16* f = fbar + (size_t)cell * ldo + col0;
+    bf16* o = out + (size_t)row * ldo + col0;
+    const bool writer = valid && ((threadIdx.x & 3) == 0);
+    bf16* m = op + (size_t)cell * 2 * ldo + ldo + col0;
+#pragma unroll
+    for (int c = 0; c < N; c += 8) {
+      f8 v;
+      if (valid) {
+        const f8 xv = ld8(x + c), fv = ld8(f + c);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bias[col0 + c + e]) + xv.v[e] + fv.v[e];
+        st8(o + c, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = v.v[e];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        v.v[e] = t * 0.25f;
+      }
+      if (writer) st8(m + c, v);
+    }
+  }
+};
+
 // a8 tail  mu = (acc + (b_fb + b_fc)) + fm                (MomentUnit.forward, models.py:299-303)
 template <typename ActT>
 struct EpiMomentOut {

@@ -8,12 +8,20 @@
 // Pipelines: smem full/empty ring (STAGES), TMEM full/empty double buffer (2 accumulators),
 // so the epilogue of tile i overlaps the mainloop of tile i+1.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
 namespace vml {
 
 constexpr int UG_BM = 128, UG_BK = 64, UG_THREADS = 192;
+
+// epilogues that use warp shuffles across rows must be called by all 32 lanes
+template <typename E, typename = void>
+struct epi_is_collective : std::false_type {};
+template <typename E>
+struct epi_is_collective<E, std::enable_if_t<E::kWarpCollective>> : std::true_type {};
 
 template <int BN>
 struct UmmaCfg {
@@ -114,7 +122,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
         ptx::tmem_ld32(t_addr + (uint32_t)c, v);
         ptx::tmem_ld_wait();
-        if (row < M) epi.template apply<32>(row, n0 + c, v);
+        if constexpr (epi_is_collective<Epi>::value) epi.template apply_warp<32>(row, n0 + c, v, row < M);
+        else if (row < M) epi.template apply<32>(row, n0 + c, v);
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -475,13 +475,22 @@ template <typename ActT>
 __global__ void __launch_bounds__(256)
 boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, const float* __restrict__ fs,
                     const ActT* __restrict__ fm, const uint8_t* __restrict__ lmask, const int32_t* __restrict__ code,
-                    const int32_t* __restrict__ row_start, float* __restrict__ bu, int L, int D, int capacity) {
+                    const int32_t* __restrict__ row_start, float* __restrict__ bu, ActT* __restrict__ fbar, int L, int D,
+                    int capacity) {
   extern __shared__ float s_a[];  // [L]
   const int row = blockIdx.x, b = row / L;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, nw = blockDim.x / 32;
   const float* fbi = fb + (size_t)row * D;
   if (!lmask[row]) {  // A_b row is zeroed by the row mask: bu = 0 + fb + 0
     for (int e = tid; e < D; e += blockDim.x) bu[(size_t)row * D + e] = fbi[e];
+    if (fbar) {       // cells of a masked row (arbitrary masks only) still need their gated map value
+      const int lo = row_start[row], hi = min(row_start[row + 1], capacity);
+      for (int n = lo; n < hi; ++n)
+        for (int e = tid; e < D; e += blockDim.x) {
+          const float m = to_f(fm[(size_t)n * D + e]);
+          fbar[(size_t)n * D + e] = from_f<ActT>(sigmoidf_(m * fs[(size_t)b * D + e]) * m);
+        }
+    }
     return;
   }
   const float* gi = G + (size_t)row * D;
@@ -518,7 +527,9 @@ boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, c
     for (int n = n_lo; n < n_hi; ++n) {
       const int j = code[n] & 0xff;
       const float m = to_f(fm[(size_t)n * D + e]);
-      bm = fmaf(s_a[j], sigmoidf_(m * s) * m, bm);
+      const float gated = sigmoidf_(m * s) * m;      // sigmoid(f_m*f_s)*f_m, shared with the content unit
+      if (fbar) fbar[(size_t)n * D + e] = from_f<ActT>(gated);
+      bm = fmaf(s_a[j], gated, bm);
     }
     bu[(size_t)row * D + e] = (bb + fbi[e]) + bm;
   }
@@ -526,17 +537,17 @@ boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, c
 
 int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                   const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
-                  float* g_scratch, float* bu, int B, vml_dims_t d, int prec, cudaStream_t st) {
+                  float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.Nq <= 32);
   static bool reg = (register_kernel("boundary_gate_kernel"), register_kernel("boundary_row_kernel"), true); (void)reg;
   boundary_gate_kernel<<<B * d.L, 128, 0, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
   const size_t smem = sizeof(float) * d.L;
   if (prec == VML_BF16)
     boundary_row_kernel<bf16><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const bf16*)fm, lmask, cells.code,
-                                                          cells.row_start, bu, d.L, d.D, cells.capacity);
+                                                          cells.row_start, bu, (bf16*)fbar, d.L, d.D, cells.capacity);
   else
     boundary_row_kernel<float><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const float*)fm, lmask, cells.code,
-                                                           cells.row_start, bu, d.L, d.D, cells.capacity);
+                                                           cells.row_start, bu, (float*)fbar, d.L, d.D, cells.capacity);
   VML_LAUNCHED(2);
   return VML_OK;
 }
@@ -576,6 +587,35 @@ moment_operand_kernel(const ActT* __restrict__ cu, const float* __restrict__ bu,
       }
     }
   }
+}
+
+// first half only: operand[n, 0:D] = bu_i * bu_j (the mean_c cu half is written by the fused content-out epilogue)
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+moment_pair_kernel(const float* __restrict__ bu, const int32_t* __restrict__ code, const int32_t* __restrict__ n_cells,
+                   ActT* __restrict__ op, int L, int D) {
+  const int n_total = *n_cells;
+  const int per = D / 8, cells_per_blk = blockDim.x / per;
+  const int t = threadIdx.x % per, sub = threadIdx.x / per;
+  for (int n = blockIdx.x * cells_per_blk + sub; n < n_total; n += gridDim.x * cells_per_blk) {
+    int b, i, j; decode_cell(code[n], b, i, j);
+    const int dd = t * 8;
+    f8 x = ld8(bu + ((size_t)b * L + i) * D + dd), y = ld8(bu + ((size_t)b * L + j) * D + dd), o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = x.v[e] * y.v[e];
+    st8(op + (size_t)n * 2 * D + dd, o);
+  }
+}
+
+int moment_pair(const float* bu, vml_cells_t cells, void* op, vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.D % 8 == 0 && d.D / 8 <= 256 && 256 % (d.D / 8) == 0);
+  static bool reg = (register_kernel("moment_pair_kernel"), true); (void)reg;
+  const int cpb = 256 / (d.D / 8);
+  const int grid = min(ceil_div(cells.capacity, cpb), kNumSMs * 8);
+  if (prec == VML_BF16) moment_pair_kernel<bf16><<<grid, 256, 0, st>>>(bu, cells.code, cells.n_cells, (bf16*)op, d.L, d.D);
+  else moment_pair_kernel<float><<<grid, 256, 0, st>>>(bu, cells.code, cells.n_cells, (float*)op, d.L, d.D);
+  VML_LAUNCHED(1);
+  return VML_OK;
 }
 
 int moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* op, vml_dims_t d, int prec, cudaStream_t st) {

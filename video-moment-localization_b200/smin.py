@@ -301,6 +301,8 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
     cc_hat = ws.get("cc_hat", (cap * Cc, dl), act)
     g_scr = ws.get("bu_g", (B, Lm, D), f32)
     mu_op = ws.get("mu_op", (cap, 2 * D), act)
+    fused = bf and Cc == 4          # fused epilogues of the tcgen05 path (gate term from the boundary unit, mean_c in-epilogue)
+    fbar = ws.get("fbar", (cap, D), act) if fused else None
     n_dev = cells.n_cells
     cur = 0
     for k in range(layers):
@@ -308,20 +310,27 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
         # a7 boundary unit
         o = k * lay["blk"]
         call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
-             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(fb[nxt]), B, dims, prec, st)
+             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(fb[nxt]), ptr(fbar), B, dims, prec, st)
         mark("boundary_unit")
         # a5+a6 content unit
-        call("vml_linear", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl, n_dev, Cc,
-             prec, 0, st)
-        mark("content_in_gemm")
-        call("vml_content_attention", ptr(c_hat), ptr(qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
-             ptr(qmask), cells, ptr(cc_hat), B, dims, prec, st)
+        if fused and dl == 128 and Nq <= 24:
+            call("vml_content_in_attention", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o, o + dl,
+                 o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(cc_hat), B, dims, st)
+        else:
+            call("vml_linear", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl, n_dev, Cc,
+                 prec, 0, st)
+            mark("content_in_gemm")
+            call("vml_content_attention", ptr(c_hat), ptr(qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
+                 ptr(qmask), cells, ptr(cc_hat), B, dims, prec, st)
         mark("content_attention")
         call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]), ptr(fs),
-             cells, ptr(fc[nxt]), dims, prec, st)
+             ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, st)
         mark("content_out_gemm")
         # a8 moment unit
-        call("vml_moment_operand", ptr(fc[nxt]), ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
+        if fused:
+            call("vml_moment_pair", ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
+        else:
+            call("vml_moment_operand", ptr(fc[nxt]), ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
         mark("moment_operand")
         call("vml_moment_out", ptr(mu_op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(fm[cur]), cells, ptr(fm[nxt]), dims, prec, st)
         mark("moment_out_gemm")
