@@ -220,8 +220,8 @@ VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* b
                    void* mu, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
   if (prec == VML_BF16) {
-    EpiMomentOut<bf16> e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D};
-    return gemm_dispatch(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, prec, ST(stream));
+    EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D};
+    return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
   }
   EpiMomentOut<float> e{bias_sum, (const float*)fm, (float*)mu, d.D};
   return gemm_dispatch(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, prec, ST(stream));

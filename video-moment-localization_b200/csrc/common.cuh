@@ -81,6 +81,12 @@ __device__ __forceinline__ f8 ld8(const bf16* p) {
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
   return r;
 }
+__device__ __forceinline__ f8 unpack8(const uint4& u) {   // 8 bf16 held in registers -> fp32
+  f8 r; const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
+  return r;
+}
 __device__ __forceinline__ void st8(float* p, const f8& r) {
   st4(p, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
   st4(p + 4, make_float4(r.v[4], r.v[5], r.v[6], r.v[7]));

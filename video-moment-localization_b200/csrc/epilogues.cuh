@@ -94,11 +94,24 @@ struct EpiContentOutFused {
   bf16* out;           // [n*4, D]
   bf16* op;            // [n, 2D]: columns D.. receive mean_c cu
   int ldo;             // D
+  struct Pre { uint4 x[4], f[4]; };     // 32 columns of fc and fbar (bf16)
+  __device__ __forceinline__ Pre load(int row, int col0, bool valid) const {
+    Pre p;
+    if (valid) {
+      const uint4* x = reinterpret_cast<const uint4*>(fc + (size_t)row * ldo + col0);
+      const uint4* f = reinterpret_cast<const uint4*>(fbar + (size_t)(row >> 2) * ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { p.x[i] = __ldg(x + i); p.f[i] = __ldg(f + i); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { p.x[i] = make_uint4(0, 0, 0, 0); p.f[i] = p.x[i]; }
+    }
+    return p;
+  }
   template <int N>
-  __device__ __forceinline__ void apply_warp(int row, int col0, const float* acc, bool valid) const {
+  __device__ __forceinline__ void apply_pre(int row, int col0, const float* acc, const Pre& p, bool valid) const {
+    static_assert(N == 32, "prefetch bundle holds 32 columns");
     const int cell = row >> 2;
-    const bf16* x = fc + (size_t)row * ldo + col0;
-    const bf16* f = fbar + (size_t)cell * ldo + col0;
     bf16* o = out + (size_t)row * ldo + col0;
     const bool writer = valid && ((threadIdx.x & 3) == 0);
     bf16* m = op + (size_t)cell * 2 * ldo + ldo + col0;
@@ -106,7 +119,7 @@ struct EpiContentOutFused {
     for (int c = 0; c < N; c += 8) {
       f8 v;
       if (valid) {
-        const f8 xv = ld8(x + c), fv = ld8(f + c);
+        const f8 xv = unpack8(p.x[c / 8]), fv = unpack8(p.f[c / 8]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bias[col0 + c + e]) + xv.v[e] + fv.v[e];
         st8(o + c, v);
@@ -127,6 +140,36 @@ struct EpiContentOutFused {
 };
 
 // a8 tail  mu = (acc + (b_fb + b_fc)) + fm                (MomentUnit.forward, models.py:299-303)
+// bf16 variant with a prefetchable operand bundle (fm) for the tcgen05 GEMM
+struct EpiMomentOutPre {
+  const float* bias;  // [D] = b_fb + b_fc
+  const bf16* fm;     // [n, D]
+  bf16* out;          // [n, D]
+  int ldo;
+  struct Pre { uint4 m[4]; };
+  __device__ __forceinline__ Pre load(int row, int col0, bool valid) const {
+    Pre p;
+    const uint4* m = reinterpret_cast<const uint4*>(fm + (size_t)row * ldo + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.m[i] = valid ? __ldg(m + i) : make_uint4(0, 0, 0, 0);
+    return p;
+  }
+  template <int N>
+  __device__ __forceinline__ void apply_pre(int row, int col0, const float* acc, const Pre& p, bool valid) const {
+    static_assert(N == 32, "prefetch bundle holds 32 columns");
+    if (!valid) return;
+    bf16* o = out + (size_t)row * ldo + col0;
+#pragma unroll
+    for (int c = 0; c < N; c += 8) {
+      const f8 mv = unpack8(p.m[c / 8]);
+      f8 v;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bias[col0 + c + e]) + mv.v[e];
+      st8(o + c, v);
+    }
+  }
+};
+
 template <typename ActT>
 struct EpiMomentOut {
   const float* bias;  // [D] = b_fb + b_fc

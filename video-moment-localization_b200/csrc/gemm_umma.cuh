@@ -1,10 +1,12 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  out = A[M,K] . W[N,K]^T (+ epilogue), bf16 operands,
 // fp32 accumulation in tensor memory.
 //
-// Persistent, warp-specialised CTA (192 threads):
+// Persistent, warp-specialised CTA (320 threads):
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
-//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//   warps 2..9  epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global); two warps
+//               per TMEM lane quadrant, each taking half of the tile's columns, so every SM
+//               scheduler has two epilogue warps to interleave (one alone runs at IPC ~0.2)
 // Pipelines: smem full/empty ring (STAGES), TMEM full/empty double buffer (2 accumulators),
 // so the epilogue of tile i overlaps the mainloop of tile i+1.
 #pragma once
@@ -16,12 +18,23 @@
 namespace vml {
 
 constexpr int UG_BM = 128, UG_BK = 64, UG_THREADS = 192;
+constexpr int UG_EPI_WARPS = 8, UG_GEMM_THREADS = 64 + 32 * UG_EPI_WARPS;   // generic GEMM: 8 epilogue warps
 
 // epilogues that use warp shuffles across rows must be called by all 32 lanes
 template <typename E, typename = void>
 struct epi_is_collective : std::false_type {};
 template <typename E>
 struct epi_is_collective<E, std::enable_if_t<E::kWarpCollective>> : std::true_type {};
+
+// epilogues with global-memory operands can expose them as a prefetchable register bundle:
+//   Pre load(row, col0, valid)  /  apply_pre<32>(row, col0, acc, pre, valid)
+// The kernel then issues the loads of chunk c+1 (and of the next tile's first chunk, before it
+// waits for the MMA) while chunk c is being finished, hiding the L2/HBM latency that a single
+// epilogue warp per scheduler cannot hide by itself.
+template <typename E, typename = void>
+struct epi_has_pre : std::false_type {};
+template <typename E>
+struct epi_has_pre<E, std::void_t<typename E::Pre>> : std::true_type {};
 
 template <int BN>
 struct UmmaCfg {
@@ -34,7 +47,7 @@ struct UmmaCfg {
 };
 
 template <int BN, typename Epi>
-__global__ void __launch_bounds__(UG_THREADS, 1)
+__global__ void __launch_bounds__(UG_GEMM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
   using Cfg = UmmaCfg<BN>;
@@ -56,7 +69,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], UG_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -110,20 +123,39 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp % 4;                             // TMEM lane quadrant this warp may access
+    constexpr int HALF = BN >= 64 ? BN / 2 : BN;           // columns handled by this warp: [c_lo, c_hi)
+    const int c_lo = ((warp - 2) / 4) * HALF;              // (BN = 32: the second warp of a quadrant has no columns)
+    const int c_hi = c_lo + HALF < BN ? c_lo + HALF : BN;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * UG_BM, n0 = (tile % tiles_n) * BN;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (epi_has_pre<Epi>::value) {
+        typename Epi::Pre pre = epi.load(row, n0 + c_lo, row < M && c_lo < BN);   // in flight while the MMA finishes
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        ptx::tmem_ld32(t_addr + (uint32_t)c, v);
-        ptx::tmem_ld_wait();
-        if constexpr (epi_is_collective<Epi>::value) epi.template apply_warp<32>(row, n0 + c, v, row < M);
-        else if (row < M) epi.template apply<32>(row, n0 + c, v);
+        for (int c = c_lo; c < c_hi; c += 32) {
+          float v[32];
+          ptx::tmem_ld32(t_addr + (uint32_t)c, v);
+          typename Epi::Pre nxt = pre;
+          if (c + 32 < c_hi) nxt = epi.load(row, n0 + c + 32, row < M);
+          ptx::tmem_ld_wait();
+          epi.template apply_pre<32>(row, n0 + c, v, pre, row < M);
+          pre = nxt;
+        }
+      } else {
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) {
+          float v[32];
+          ptx::tmem_ld32(t_addr + (uint32_t)c, v);
+          ptx::tmem_ld_wait();
+          if constexpr (epi_is_collective<Epi>::value) epi.template apply_warp<32>(row, n0 + c, v, row < M);
+          else if (row < M) epi.template apply<32>(row, n0 + c, v);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -156,7 +188,7 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
   }
   const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_umma_kernel<BN, Epi><<<grid, UG_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+  gemm_umma_kernel<BN, Epi><<<grid, UG_GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
   VML_LAUNCHED(1);
   return VML_OK;
 }

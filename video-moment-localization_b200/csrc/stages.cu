@@ -430,85 +430,151 @@ int content_attention(const void* c_hat, const float* qproj, int ld, int off_wha
 // =====================================================================================
 // a7  BoundaryUnit  (Attention.forward models.py:137-154; BoundaryUnit.forward :164-196)
 // =====================================================================================
-// gate:  G[b,l,:] = fb * (softmax(q.k^T/sqrt(D))·fw * lmask + fs), with q.k^T = fb.kbt^T + beta_b
-// (W_q folded into the per-word keys kbt at pack time, so no per-layer projection of fb).
-__global__ void __launch_bounds__(128)
+// Both kernels: one CTA per (sample, tile of 8 map rows), one WARP per row; a lane owns the 16-byte
+// column groups {128*i + 4*lane}, so every global/shared access of a row is a coalesced 512 B.
+constexpr int BU_RT = 8;        // rows (= warps) per CTA
+constexpr int BU_MAXG = 8;      // D <= 128 * BU_MAXG (kernels are instantiated for NG = 1, 2, 4, 8 column groups)
+
+// gate:  G[b,l,:] = fb * (softmax(q.k^T/sqrt(D)) . fw * lmask + fs), with q.k^T = fb.kbt^T + beta_b
+// (W_q folded into the per-word keys kbt at pack time, so no per-layer projection of fb).  The
+// sample's keys and word states are staged once per CTA in shared memory.
+template <int NG>
+__global__ void __launch_bounds__(BU_RT * 32)
 boundary_gate_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab,
                      const float* __restrict__ fw, const float* __restrict__ fs, const float* __restrict__ fb,
                      const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ lmask, float* __restrict__ G,
                      int L, int Nq, int D) {
-  __shared__ float s_p[32];
-  const int row = blockIdx.x, b = row / L;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const float* q = fb + (size_t)row * D;
-  for (int k = warp; k < Nq; k += 4) {
-    const float* kr = qproj + ((size_t)b * Nq + k) * ld;
+  extern __shared__ __align__(16) float sg[];
+  float* s_k = sg;                 // [Nq][D]  kbt
+  float* s_w = s_k + Nq * D;       // [Nq][D]  fw
+  float* s_bm = s_w + Nq * D;      // [32] beta_b, [32] mask
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int dq = D / 4;
+  for (int e = tid; e < Nq * dq; e += blockDim.x) {
+    const int k = e / dq, c4 = (e % dq) * 4;
+    *reinterpret_cast<float4*>(s_k + k * D + c4) = __ldg(reinterpret_cast<const float4*>(qproj + ((size_t)b * Nq + k) * ld + off_kbt + c4));
+    *reinterpret_cast<float4*>(s_w + k * D + c4) = __ldg(reinterpret_cast<const float4*>(fw + ((size_t)b * Nq + k) * D + c4));
+  }
+  if (tid < 32) {
+    s_bm[tid] = tid < Nq ? qproj[((size_t)b * Nq + tid) * ld + off_betab] : 0.f;
+    s_bm[32 + tid] = (tid < Nq && qmask[(size_t)b * Nq + tid]) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  const int l = blockIdx.x * BU_RT + warp;
+  if (l >= L) return;
+  const int row = b * L + l;
+  float4 x[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NG; ++i)
+    if (i * 128 + lane * 4 < D) x[i] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)row * D + i * 128 + lane * 4));
+  // scores over the words (lane k keeps word k's score)
+  float my_s = -INFINITY;
+  for (int k = 0; k < Nq; ++k) {
     float acc = 0.f;
-    for (int e = lane; e < D; e += 32) acc = fmaf(q[e], kr[off_kbt + e], acc);
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      if (i * 128 + lane * 4 < D) {
+        const float4 w = *reinterpret_cast<const float4*>(s_k + k * D + i * 128 + lane * 4);
+        acc = fmaf(x[i].x, w.x, acc); acc = fmaf(x[i].y, w.y, acc); acc = fmaf(x[i].z, w.z, acc); acc = fmaf(x[i].w, w.w, acc);
+      }
     acc = warp_sum(acc);
-    if (lane == 0) s_p[k] = acc + kr[off_betab];
+    if (lane == k) my_s = acc;
   }
-  __syncthreads();
-  if (warp == 0) {
-    const float mk = lane < Nq ? (qmask[(size_t)b * Nq + lane] ? 1.f : 0.f) : 0.f;
-    float s = lane < Nq ? s_p[lane] / sqrtf((float)D) : 0.f;
-    s = s * mk;
-    if (mk == 0.f) s = -1e9f;
-    if (lane >= Nq) s = -INFINITY;
-    const float mx = warp_max(s);
-    const float ex = lane < Nq ? expf(s - mx) : 0.f;
-    const float den = warp_sum(ex);
-    __syncwarp();
-    s_p[lane] = ex / den;
+  const float mk = s_bm[32 + lane];
+  float sv = lane < Nq ? (my_s + s_bm[lane]) / sqrtf((float)D) : 0.f;
+  sv = sv * mk;
+  if (mk == 0.f) sv = -1e9f;                       // masked_fill(mask == 0, -1e9)
+  if (lane >= Nq) sv = -INFINITY;
+  const float mx = warp_max(sv);
+  const float ex = lane < Nq ? expf(sv - mx) : 0.f;
+  const float p_mine = ex / warp_sum(ex);
+  // attended words, row mask, gate
+  float4 a[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < Nq; ++k) {
+    const float p = __shfl_sync(0xffffffffu, p_mine, k);
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      if (i * 128 + lane * 4 < D) {
+        const float4 w = *reinterpret_cast<const float4*>(s_w + k * D + i * 128 + lane * 4);
+        a[i].x = fmaf(p, w.x, a[i].x); a[i].y = fmaf(p, w.y, a[i].y); a[i].z = fmaf(p, w.z, a[i].z); a[i].w = fmaf(p, w.w, a[i].w);
+      }
   }
-  __syncthreads();
   const float lm = lmask[row] ? 1.f : 0.f;
-  for (int e = tid; e < D; e += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < Nq; ++k) acc = fmaf(s_p[k], fw[((size_t)b * Nq + k) * D + e], acc);
-    G[(size_t)row * D + e] = fb[(size_t)row * D + e] * (acc * lm + fs[(size_t)b * D + e]);
-  }
+#pragma unroll
+  for (int i = 0; i < NG; ++i)
+    if (i * 128 + lane * 4 < D) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(fs + (size_t)b * D + i * 128 + lane * 4));
+      float4 g;
+      g.x = x[i].x * (a[i].x * lm + s4.x); g.y = x[i].y * (a[i].y * lm + s4.y);
+      g.z = x[i].z * (a[i].z * lm + s4.z); g.w = x[i].w * (a[i].w * lm + s4.w);
+      *reinterpret_cast<float4*>(G + (size_t)row * D + i * 128 + lane * 4) = g;
+    }
 }
 
-// row:  A_b[i,:] = softmax_j(G_i.G_j/sqrt(D)) (masked) ; bu[i] = A_b[i,:].fb + fb[i] + sum_j A_b[i,j] sigmoid(fm_ij*fs)*fm_ij
-template <typename ActT>
-__global__ void __launch_bounds__(256)
+// row:  A_b[i,:] = softmax_j(G_i.G_j/sqrt(D)) (masked) ;
+//       bu[i] = A_b[i,:].fb + fb[i] + sum_j A_b[i,j] sigmoid(fm_ij*fs)*fm_ij   (also written out as fbar)
+template <typename ActT, int NG>
+__global__ void __launch_bounds__(BU_RT * 32)
 boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, const float* __restrict__ fs,
                     const ActT* __restrict__ fm, const uint8_t* __restrict__ lmask, const int32_t* __restrict__ code,
                     const int32_t* __restrict__ row_start, float* __restrict__ bu, ActT* __restrict__ fbar, int L, int D,
                     int capacity) {
-  extern __shared__ float s_a[];  // [L]
-  const int row = blockIdx.x, b = row / L;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, nw = blockDim.x / 32;
-  const float* fbi = fb + (size_t)row * D;
-  if (!lmask[row]) {  // A_b row is zeroed by the row mask: bu = 0 + fb + 0
-    for (int e = tid; e < D; e += blockDim.x) bu[(size_t)row * D + e] = fbi[e];
-    if (fbar) {       // cells of a masked row (arbitrary masks only) still need their gated map value
-      const int lo = row_start[row], hi = min(row_start[row + 1], capacity);
-      for (int n = lo; n < hi; ++n)
-        for (int e = tid; e < D; e += blockDim.x) {
-          const float m = to_f(fm[(size_t)n * D + e]);
-          fbar[(size_t)n * D + e] = from_f<ActT>(sigmoidf_(m * fs[(size_t)b * D + e]) * m);
+  extern __shared__ float s_all[];  // [BU_RT][L] attention rows
+  const int b = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int i_row = blockIdx.x * BU_RT + warp;
+  if (i_row >= L) return;
+  float* s_a = s_all + warp * L;
+  const int row = b * L + i_row;
+  const bool row_on = lmask[row] != 0;
+  const int n_lo = row_start[row], n_hi = min(row_start[row + 1], capacity);
+  float4 s4[NG], acc[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) { s4[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = s4[i]; }
+#pragma unroll
+  for (int i = 0; i < NG; ++i)
+    if (i * 128 + lane * 4 < D) {
+      s4[i] = __ldg(reinterpret_cast<const float4*>(fs + (size_t)b * D + i * 128 + lane * 4));
+      acc[i] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)row * D + i * 128 + lane * 4));   // + f_b
+    }
+  if (row_on) {
+    float4 gi[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) gi[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      if (i * 128 + lane * 4 < D) gi[i] = __ldg(reinterpret_cast<const float4*>(G + (size_t)row * D + i * 128 + lane * 4));
+    for (int j0 = 0; j0 < L; j0 += 4) {            // 4 key rows per round trip: all loads first, then the math
+      float4 w[4][NG];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* gj = G + ((size_t)b * L + min(j0 + u, L - 1)) * D;
+#pragma unroll
+        for (int i = 0; i < NG; ++i)
+          w[u][i] = (i * 128 + lane * 4 < D) ? __ldg(reinterpret_cast<const float4*>(gj + i * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float mk4 = (lane < 4 && j0 + lane < L && lmask[b * L + j0 + lane]) ? 1.f : 0.f;
+      float d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          t = fmaf(gi[i].x, w[u][i].x, t); t = fmaf(gi[i].y, w[u][i].y, t); t = fmaf(gi[i].z, w[u][i].z, t); t = fmaf(gi[i].w, w[u][i].w, t);
         }
+        d[u] = warp_sum(t);
+      }
+      if (lane < 4 && j0 + lane < L) {
+        float sc = (lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]) / sqrtf((float)D);
+        sc = sc * mk4;
+        if (mk4 == 0.f) sc = -1e9f;
+        s_a[j0 + lane] = sc;
+      }
     }
-    return;
-  }
-  const float* gi = G + (size_t)row * D;
-  for (int j = warp; j < L; j += nw) {
-    const float* gj = G + ((size_t)b * L + j) * D;
-    float acc = 0.f;
-    for (int e = lane; e < D; e += 32) acc = fmaf(gi[e], gj[e], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float s = acc / sqrtf((float)D);
-      const float mk = lmask[b * L + j] ? 1.f : 0.f;
-      s = s * mk;
-      if (mk == 0.f) s = -1e9f;
-      s_a[j] = s;
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
+    __syncwarp();
     float mx = -INFINITY;
     for (int j = lane; j < L; j += 32) mx = fmaxf(mx, s_a[j]);
     mx = warp_max(mx);
@@ -516,40 +582,99 @@ boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, c
     for (int j = lane; j < L; j += 32) { const float ex = expf(s_a[j] - mx); s_a[j] = ex; den += ex; }
     den = warp_sum(den);
     for (int j = lane; j < L; j += 32) s_a[j] = s_a[j] / den;
-  }
-  __syncthreads();
-  const int n_lo = row_start[row], n_hi = min(row_start[row + 1], capacity);
-  for (int e = tid; e < D; e += blockDim.x) {
-    float bb = 0.f;
-    for (int j = 0; j < L; ++j) bb = fmaf(s_a[j], fb[((size_t)b * L + j) * D + e], bb);
-    const float s = fs[(size_t)b * D + e];
-    float bm = 0.f;
-    for (int n = n_lo; n < n_hi; ++n) {
-      const int j = code[n] & 0xff;
-      const float m = to_f(fm[(size_t)n * D + e]);
-      const float gated = sigmoidf_(m * s) * m;      // sigmoid(f_m*f_s)*f_m, shared with the content unit
-      if (fbar) fbar[(size_t)n * D + e] = from_f<ActT>(gated);
-      bm = fmaf(s_a[j], gated, bm);
+    __syncwarp();
+    // f_bb = A_b[i,:] . fb  (added to the f_b already in acc: (f_bb + f_b) as the reference orders it)
+    float4 bb[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) bb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int j = 0; j < L; ++j) {
+      const float a = s_a[j];
+      const float* fj = fb + ((size_t)b * L + j) * D;
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        if (i * 128 + lane * 4 < D) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(fj + i * 128 + lane * 4));
+          bb[i].x = fmaf(a, w.x, bb[i].x); bb[i].y = fmaf(a, w.y, bb[i].y); bb[i].z = fmaf(a, w.z, bb[i].z); bb[i].w = fmaf(a, w.w, bb[i].w);
+        }
     }
-    bu[(size_t)row * D + e] = (bb + fbi[e]) + bm;
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      if (i * 128 + lane * 4 < D) { acc[i].x += bb[i].x; acc[i].y += bb[i].y; acc[i].z += bb[i].z; acc[i].w += bb[i].w; }
   }
+  // f_bm over the valid cells of this map row; the gated map value is also what the content unit adds
+  float4 bm[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) bm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n0 = n_lo; n0 < n_hi; n0 += 4) {        // 4 cells per round trip
+    float4 m[4][NG];
+    float a4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = min(n0 + u, n_hi - 1);
+      a4[u] = (row_on && n0 + u < n_hi) ? s_a[code[n] & 0xff] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        m[u][i] = (i * 128 + lane * 4 < D) ? ld4(fm + (size_t)n * D + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (n0 + u < n_hi) {
+#pragma unroll
+        for (int i = 0; i < NG; ++i)
+          if (i * 128 + lane * 4 < D) {
+            const float4 mm = m[u][i];
+            float4 g;
+            g.x = sigmoidf_(mm.x * s4[i].x) * mm.x; g.y = sigmoidf_(mm.y * s4[i].y) * mm.y;
+            g.z = sigmoidf_(mm.z * s4[i].z) * mm.z; g.w = sigmoidf_(mm.w * s4[i].w) * mm.w;
+            if (fbar) st4(fbar + (size_t)(n0 + u) * D + i * 128 + lane * 4, g);
+            bm[i].x = fmaf(a4[u], g.x, bm[i].x); bm[i].y = fmaf(a4[u], g.y, bm[i].y);
+            bm[i].z = fmaf(a4[u], g.z, bm[i].z); bm[i].w = fmaf(a4[u], g.w, bm[i].w);
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NG; ++i)
+    if (i * 128 + lane * 4 < D) {
+      float4 o;
+      o.x = acc[i].x + bm[i].x; o.y = acc[i].y + bm[i].y; o.z = acc[i].z + bm[i].z; o.w = acc[i].w + bm[i].w;
+      *reinterpret_cast<float4*>(bu + (size_t)row * D + i * 128 + lane * 4) = o;
+    }
+}
+
+template <int NG>
+static int launch_boundary(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
+                           const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
+                           float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
+  dim3 grid(ceil_div(d.L, BU_RT), B);
+  const size_t smem_g = sizeof(float) * (2 * (size_t)d.Nq * d.D + 64);
+  VML_CUDA(cudaFuncSetAttribute(boundary_gate_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  boundary_gate_kernel<NG><<<grid, BU_RT * 32, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch,
+                                                             d.L, d.Nq, d.D);
+  const size_t smem = sizeof(float) * BU_RT * d.L;
+  if (prec == VML_BF16)
+    boundary_row_kernel<bf16, NG><<<grid, BU_RT * 32, smem, st>>>(g_scratch, fb, fs, (const bf16*)fm, lmask, cells.code,
+                                                                  cells.row_start, bu, (bf16*)fbar, d.L, d.D, cells.capacity);
+  else
+    boundary_row_kernel<float, NG><<<grid, BU_RT * 32, smem, st>>>(g_scratch, fb, fs, (const float*)fm, lmask, cells.code,
+                                                                   cells.row_start, bu, (float*)fbar, d.L, d.D, cells.capacity);
+  VML_LAUNCHED(2);
+  return VML_OK;
 }
 
 int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                   const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
                   float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
-  VML_CHECK_ARG(d.Nq <= 32);
+  VML_CHECK_ARG(d.Nq <= 32 && d.D % 4 == 0 && d.D <= 128 * BU_MAXG && ld % 4 == 0 && off_kbt % 4 == 0);
   static bool reg = (register_kernel("boundary_gate_kernel"), register_kernel("boundary_row_kernel"), true); (void)reg;
-  boundary_gate_kernel<<<B * d.L, 128, 0, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
-  const size_t smem = sizeof(float) * d.L;
-  if (prec == VML_BF16)
-    boundary_row_kernel<bf16><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const bf16*)fm, lmask, cells.code,
-                                                          cells.row_start, bu, (bf16*)fbar, d.L, d.D, cells.capacity);
-  else
-    boundary_row_kernel<float><<<B * d.L, 256, smem, st>>>(g_scratch, fb, fs, (const float*)fm, lmask, cells.code,
-                                                           cells.row_start, bu, (float*)fbar, d.L, d.D, cells.capacity);
-  VML_LAUNCHED(2);
-  return VML_OK;
+#define VML_BU(NG) return launch_boundary<NG>(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, qmask, lmask, cells, g_scratch, bu, fbar, B, d, prec, st)
+  const int ng = ceil_div(d.D, 128);
+  if (ng <= 1) VML_BU(1);
+  if (ng <= 2) VML_BU(2);
+  if (ng <= 4) VML_BU(4);
+  VML_BU(8);
+#undef VML_BU
 }
 
 // =====================================================================================
