@@ -84,6 +84,19 @@ VML_API int vml_pack_cells(const void* dense, void* packed, vml_cells_t cells, i
 /* fp32 [rows, k] -> bf16 [rows, k_pad] (zero padded), for TMA-legal operand rows. */
 VML_API int vml_cast_pad_bf16(const float* src, void* dst_bf16, int64_t rows, int k, int k_pad, void* stream);
 
+/* One launch that takes the caller's forward() arguments (models.py:367: video_features[B,T,d0],
+ * query_features[B,Nq,300] float; video/query/length/moment masks as bytes, dataset.py:165-176)
+ * into library-owned operand buffers: features -> bf16 rows zero-padded to v_kpad / q_kpad
+ * (VML_BF16) or float copies (VML_FP32, kpad == k); masks -> 0/1 byte copies; sm (optional,
+ * the IoU map compute_ious reads) -> copy; qlen[B] = sum(query_mask) (models.py:50, without
+ * the D2H copy of :52).  Any output pointer may be NULL (skipped).  Everything after this
+ * call reads only library-owned buffers, so the rest of a step can be a replayed CUDA graph. */
+VML_API int vml_ingest(const float* video_features, const float* query_features, const uint8_t* video_mask,
+                       const uint8_t* query_mask, const uint8_t* length_mask, const uint8_t* moment_mask, const float* sm,
+                       void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out, uint8_t* lmask_out,
+                       uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad, int q_kpad,
+                       int prec, void* stream);
+
 /* ---- dense contractions --------------------------------------------------------------- */
 
 /* out[M,N] = A[M,K] . W[N,K]^T + bias[N].  VML_FP32: A,W,out float.  VML_BF16: A,W bf16
@@ -192,10 +205,11 @@ VML_API int vml_scaled_iou_bce(const float* pm, const uint8_t* ym, const float* 
  * index ; top_iou = sm[idx] ; counts[n_idx*4 + m_idx] += any(top_iou[:n] > m) for
  * n in {1,5}, m in {.1,.3,.5,.7} (ACCUMULATES into counts, like the reference's running
  * sums, main.py:155-156).  nms_num/nms_den: temporal-NMS IoU threshold as a rational;
- * nms_num >= nms_den disables NMS (the reference has none, utils.py:14). */
+ * nms_num >= nms_den disables NMS (the reference has none, utils.py:14).  step_counts (optional)
+ * is a second accumulator of the same hits, for per-step read-back. */
 VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask,
                           const float* sm, int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx,
-                          float* top_score, float* top_iou, int64_t* counts, void* stream);
+                          float* top_score, float* top_iou, int64_t* counts, int64_t* step_counts, void* stream);
 
 #ifdef __cplusplus
 }

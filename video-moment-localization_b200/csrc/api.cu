@@ -68,6 +68,8 @@ int build_cells(const uint8_t*, int, int, vml_cells_t, cudaStream_t);
 int unpack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
 int pack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
 int cast_pad(const float*, void*, int64_t, int, int, cudaStream_t);
+int ingest(const float*, const float*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const float*, void*,
+           void*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, float*, int32_t*, int, vml_dims_t, int, int, int, cudaStream_t);
 int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*, int, vml_dims_t, int, cudaStream_t);
 int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
                       void*, int, vml_dims_t, int, cudaStream_t);
@@ -85,7 +87,7 @@ int scaled_iou_bce(const float*, const uint8_t*, const float*, const uint8_t*, c
                    const float*, const uint8_t*, const float*, const float*, const uint8_t*, const uint8_t*, int, int,
                    float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
 int score_topk_recall(const float*, const float*, const float*, const uint8_t*, const float*, int, int, int, int, int,
-                      int32_t*, float*, float*, int64_t*, cudaStream_t);
+                      int32_t*, float*, float*, int64_t*, int64_t*, cudaStream_t);
 
 // generic dispatch: fp32 -> CUDA-core GEMM, bf16 -> tcgen05 GEMM
 template <typename Epi>
@@ -127,6 +129,16 @@ VML_API int vml_pack_cells(const void* dense, void* packed, vml_cells_t cells, i
 }
 VML_API int vml_cast_pad_bf16(const float* src, void* dst, int64_t rows, int k, int k_pad, void* stream) {
   return cast_pad(src, dst, rows, k, k_pad, ST(stream));
+}
+
+VML_API int vml_ingest(const float* video_features, const float* query_features, const uint8_t* video_mask,
+                       const uint8_t* query_mask, const uint8_t* length_mask, const uint8_t* moment_mask, const float* sm,
+                       void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out, uint8_t* lmask_out,
+                       uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad, int q_kpad,
+                       int prec, void* stream) {
+  VML_PREC_OK(prec);
+  return ingest(video_features, query_features, video_mask, query_mask, length_mask, moment_mask, sm, v_out, q_out, vmask_out,
+                qmask_out, lmask_out, mmask_out, sm_out, qlen, B, d, v_kpad, q_kpad, prec, ST(stream));
 }
 
 VML_API int vml_linear(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
@@ -244,9 +256,9 @@ VML_API int vml_scaled_iou_bce(const float* pm, const uint8_t* ym, const float* 
 
 VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask, const float* sm,
                           int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score,
-                          float* top_iou, int64_t* counts, void* stream) {
+                          float* top_iou, int64_t* counts, int64_t* step_counts, void* stream) {
   return score_topk_recall(pm, ps, pe, moment_mask, sm, B, L, k, nms_num, nms_den, top_idx, top_score, top_iou, counts,
-                           ST(stream));
+                           step_counts, ST(stream));
 }
 
 }  // extern "C"

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256)
 score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ pe,
                   const uint8_t* __restrict__ mmask, const float* __restrict__ sm, int L, int k, int nms_num, int nms_den,
                   int32_t* __restrict__ top_idx, float* __restrict__ top_score, float* __restrict__ top_iou,
-                  unsigned long long* __restrict__ counts) {
+                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ counts2) {
   extern __shared__ __align__(8) unsigned char smem_raw[];
   float* sc = reinterpret_cast<float*>(smem_raw);                       // [L*L] scores; < 0 marks taken/suppressed
   __shared__ unsigned long long wbest[8];
@@ -382,20 +382,23 @@ score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, co
       for (int t = 0; t < 4; ++t) {
         bool hit = false;
         for (int r = 0; r < min(ns[a], k); ++r) hit = hit || (picked[r] >= 0 && picked_iou[r] > thr[t]);
-        if (hit) atomicAdd(&counts[a * 4 + t], 1ull);
+        if (hit) {
+          atomicAdd(&counts[a * 4 + t], 1ull);
+          if (counts2) atomicAdd(&counts2[a * 4 + t], 1ull);
+        }
       }
   }
 }
 
 int score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* mmask, const float* sm, int B,
                       int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score, float* top_iou,
-                      int64_t* counts, cudaStream_t st) {
+                      int64_t* counts, int64_t* counts2, cudaStream_t st) {
   VML_CHECK_ARG(B > 0 && L > 0 && k >= 1 && k <= 8 && nms_den > 0 && (size_t)L * L * 4 <= 200 * 1024);
   static bool reg = (register_kernel("score_topk_kernel"), true); (void)reg;
   const size_t smem = sizeof(float) * L * L;
   VML_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_topk_kernel<<<B, 256, smem, st>>>(pm, ps, pe, mmask, sm, L, k, nms_num, nms_den, top_idx, top_score, top_iou,
-                                          (unsigned long long*)counts);
+                                          (unsigned long long*)counts, (unsigned long long*)counts2);
   VML_LAUNCHED(1);
   return VML_OK;
 }

@@ -151,6 +151,90 @@ int cast_pad(const float* src, void* dst, int64_t rows, int k, int k_pad, cudaSt
 }
 
 // =====================================================================================
+// ingest: ONE launch that takes the caller's tensors into the library's operand buffers --
+// clip features / word vectors fp32 -> bf16 rows zero-padded to a TMA-legal stride (or fp32
+// copies), the four masks -> u8 copies, sm copy, qlen = sum(query_mask) (models.py:50).
+// Everything downstream reads only library-owned buffers, so the rest of the step can be a
+// replayed CUDA graph.
+// =====================================================================================
+struct IngestArgs {
+  const float* src[2];   // video_features [rows0, k0], query_features [rows1, k1]
+  void* dst[2];          // bf16 [rows, kpad] or float [rows, k]; nullptr = skip
+  int64_t rows[2];
+  int k[2], kpad[2];
+  const uint8_t* msrc[4];  // video, query, length, moment masks
+  uint8_t* mdst[4];
+  int64_t mbytes[4];
+  const float* sm_src; float* sm_dst; int64_t sm_n;
+  const uint8_t* qmask; int32_t* qlen; int B, Nq;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+ingest_kernel(IngestArgs a) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!a.dst[s]) continue;
+    const int k = a.k[s], kp4 = a.kpad[s] / 4;
+    const int64_t total = a.rows[s] * kp4;
+    const float* src = a.src[s];
+    for (int64_t e = tid; e < total; e += nth) {
+      const int64_t r = e / kp4;
+      const int c = (int)(e - r * kp4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 3 < k) v = __ldg(reinterpret_cast<const float4*>(src + r * k + c));
+      else {
+        if (c < k) v.x = src[r * k + c];
+        if (c + 1 < k) v.y = src[r * k + c + 1];
+        if (c + 2 < k) v.z = src[r * k + c + 2];
+      }
+      if (BF16) st4(reinterpret_cast<bf16*>(a.dst[s]) + r * a.kpad[s] + c, v);
+      else st4(reinterpret_cast<float*>(a.dst[s]) + r * a.kpad[s] + c, v);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if (!a.mdst[s]) continue;
+    for (int64_t e = tid; e < a.mbytes[s]; e += nth) a.mdst[s][e] = a.msrc[s][e] ? 1 : 0;
+  }
+  if (a.sm_dst)
+    for (int64_t e = tid; e < a.sm_n; e += nth) a.sm_dst[e] = a.sm_src[e];
+  if (a.qlen)
+    for (int64_t b = tid; b < a.B; b += nth) {
+      int n = 0;
+      for (int w = 0; w < a.Nq; ++w) n += a.qmask[b * a.Nq + w] ? 1 : 0;
+      a.qlen[b] = n;
+    }
+}
+
+int ingest(const float* vf, const float* qf, const uint8_t* vmask, const uint8_t* qmask, const uint8_t* lmask,
+           const uint8_t* mmask, const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
+           uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad,
+           int q_kpad, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(B > 0 && d.d0 % 4 == 0 && v_kpad % 4 == 0 && q_kpad % 4 == 0 && v_kpad >= d.d0 && q_kpad >= 300);
+  VML_CHECK_ARG(prec == VML_BF16 || (v_kpad == d.d0 && q_kpad == 300));
+  static bool reg = (register_kernel("ingest_kernel"), true); (void)reg;
+  IngestArgs a;
+  a.src[0] = vf; a.src[1] = qf; a.dst[0] = v_out; a.dst[1] = q_out;
+  a.rows[0] = (int64_t)B * d.T; a.rows[1] = (int64_t)B * d.Nq;
+  a.k[0] = d.d0; a.k[1] = 300; a.kpad[0] = v_kpad; a.kpad[1] = q_kpad;
+  a.msrc[0] = vmask; a.msrc[1] = qmask; a.msrc[2] = lmask; a.msrc[3] = mmask;
+  a.mdst[0] = vmask_out; a.mdst[1] = qmask_out; a.mdst[2] = lmask_out; a.mdst[3] = mmask_out;
+  a.mbytes[0] = (int64_t)B * d.T; a.mbytes[1] = (int64_t)B * d.Nq; a.mbytes[2] = (int64_t)B * d.L;
+  a.mbytes[3] = (int64_t)B * d.L * d.L;
+  a.sm_src = sm; a.sm_dst = sm ? sm_out : nullptr; a.sm_n = (int64_t)B * d.L * d.L;
+  a.qmask = qmask; a.qlen = qlen; a.B = B; a.Nq = d.Nq;
+  const int64_t total = (v_out ? a.rows[0] * (v_kpad / 4) : 0) + (q_out ? a.rows[1] * (q_kpad / 4) : 0) + a.mbytes[3];
+  const int64_t want = ceil_div64(total, 256 * 4), cap = (int64_t)kNumSMs * 8;
+  const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  if (prec == VML_BF16) ingest_kernel<true><<<grid, 256, 0, st>>>(a);
+  else ingest_kernel<false><<<grid, 256, 0, st>>>(a);
+  VML_LAUNCHED(1);
+  return VML_OK;
+}
+
+// =====================================================================================
 // a3+a4  fused  f = fv*fs  +  span pooling over clips   (models.py:81,88-98,115-126)
 //
 // One CTA per (sample, D-slice).  The slice of the fused clip sequence is turned into an

@@ -43,6 +43,7 @@ _SIGS = {
     "vml_unpack_cells": [_P, _P, Cells, _I, _I, _I, _I, _P],
     "vml_pack_cells": [_P, _P, Cells, _I, _I, _I, _I, _P],
     "vml_cast_pad_bf16": [_P, _P, _I64, _I, _I, _P],
+    "vml_ingest": [_P] * 15 + [_I, Dims, _I, _I, _I, _P],
     "vml_linear": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "vml_clip_projection": [_P, _P, _P, _P, _P, _P, _I, Dims, _I, _I, _P],
     "vml_lstm_layer": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
@@ -57,7 +58,7 @@ _SIGS = {
     "vml_moment_out": [_P, _P, _P, _P, Cells, _P, Dims, _I, _P],
     "vml_localize": [_P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_scaled_iou_bce": [_P] * 13 + [_I, _I] + [_P] * 7 + [_P],
-    "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
 }
 _RET = {"vml_last_error": C.c_char_p, "vml_kernel_names": C.c_char_p, "vml_launch_count": C.c_int64}
 

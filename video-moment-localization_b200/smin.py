@@ -200,6 +200,13 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.buf: Dict[str, torch.Tensor] = {}
+        self._side = None
+
+    def side_stream(self):
+        """Second stream for the independent branches of a step (created on first use)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def get(self, name, shape, dtype):
         t = self.buf.get(name)
@@ -220,75 +227,127 @@ def make_cells(ws: Workspace, B: int, L: int, capacity: Optional[int] = None) ->
     return Cells(code.data_ptr(), row_start.data_ptr(), meta.data_ptr(), meta.data_ptr() + 4, cap)
 
 
-def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace, video_features, video_mask,
-                 query_features, query_mask, length_mask, moment_mask, keep: Optional[dict] = None, mark=None):
-    """The whole hot path, stage by stage.  ``keep`` (tests only)
-    receives references to intermediates; ``mark(name)`` (bench only) is called after each
-    stage has been enqueued so the caller can record CUDA events on the launching stream."""
-    mark = mark or (lambda name: None)
-    dev = video_features.device
+def _mask_u8(t, shape):
+    """Byte view of a mask without a conversion kernel when it already is 1 byte per element."""
+    t = t.reshape(shape)
+    if t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8)
+    if t.dtype == torch.uint8:
+        return t.contiguous()
+    return (t != 0).contiguous().view(torch.uint8)
+
+
+def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask, query_features, query_mask, length_mask,
+                moment_mask, sm=None, static: bool = False, pk=None):
+    """Take the caller's ``forward`` arguments into library-owned operand buffers with ONE launch
+    (``vml_ingest``): bf16 zero-padded feature rows (fast mode), query lengths, and -- when
+    ``static`` (CUDA-graph replay of the rest of the step) -- copies of the masks / fp32 features /
+    ``sm`` so that nothing downstream reads caller memory."""
     B = video_features.shape[0]
+    T, Lm, d0, Nq = dims.T, dims.L, dims.d0, dims.Nq
+    bf = prec == L_.BF16
+    vf = video_features.float().contiguous()
+    qf = query_features.float().contiguous()
+    vmask, qmask = _mask_u8(video_mask, (B, T)), _mask_u8(query_mask, (B, Nq))
+    lmask, mmask = _mask_u8(length_mask, (B, Lm)), _mask_u8(moment_mask, (B, Lm, Lm))
+    vk = _round_up(d0, 8) if bf else d0
+    qk = _round_up(300, 8) if bf else 300
+    inp = {"B": B, "vk": vk, "qk": qk}
+    qlen = ws.get("qlen", (B,), torch.int32)
+    if bf:
+        v_out, q_out = ws.get("v16", (B * T, vk), torch.bfloat16), ws.get("q16", (B * Nq, qk), torch.bfloat16)
+    elif static:
+        v_out, q_out = ws.get("v32", (B * T, d0), torch.float32), ws.get("q32", (B * Nq, 300), torch.float32)
+    else:
+        v_out = q_out = None
+    if static:
+        m_out = [ws.get("in_vmask", (B, T), torch.uint8), ws.get("in_qmask", (B, Nq), torch.uint8),
+                 ws.get("in_lmask", (B, Lm), torch.uint8), ws.get("in_mmask", (B, Lm, Lm), torch.uint8)]
+        sm_in = sm.float().contiguous() if sm is not None else None
+        sm_out = ws.get("in_sm", (B, Lm, Lm), torch.float32) if sm is not None else None
+    else:
+        m_out, sm_in, sm_out = [None] * 4, None, None
+    call("vml_ingest", ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), ptr(v_out), ptr(q_out),
+         *[ptr(m) for m in m_out], ptr(sm_out), ptr(qlen), B, dims, vk, qk, prec, stream_ptr())
+    inp.update(v=v_out if v_out is not None else vf, q=q_out if q_out is not None else qf, qlen=qlen,
+               vmask=m_out[0] if static else vmask, qmask=m_out[1] if static else qmask,
+               lmask=m_out[2] if static else lmask, mmask=m_out[3] if static else mmask,
+               sm=sm_out if static else sm)
+    return inp
+
+
+def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace, inp: dict, keep: Optional[dict] = None,
+              mark=None, overlap: bool = True):
+    """Everything after ``smin_ingest``; reads only library-owned buffers.
+    ``overlap``: independent branches run on a second stream (query encoder || clip projection +
+    cell compaction; content chain || boundary/moment chain of every SMI layer), joined with
+    events -- also valid under CUDA-graph capture.  ``keep`` (tests only) receives intermediates;
+    ``mark(name)`` (bench only) is called after each stage has been enqueued (serial mode)."""
+    serial = (mark is not None) or (keep is not None) or not overlap
+    mark = mark or (lambda name: None)
+    B = inp["B"]
     T, Lm, Cc, D, dl, layers, d0, Nq, H = (dims.T, dims.L, dims.C, dims.D, dims.dl, dims.layers, dims.d0, dims.Nq, dims.H)
-    st = stream_ptr()
+    dev = inp["qlen"].device
     act = torch.bfloat16 if prec == L_.BF16 else torch.float32
     f32 = torch.float32
-    vf = video_features.contiguous()
-    qf = query_features.contiguous()
-    vmask = video_mask.reshape(B, T).to(torch.uint8).contiguous()
-    qmask = query_mask.reshape(B, Nq).to(torch.uint8).contiguous()
-    lmask = length_mask.to(torch.uint8).contiguous()
-    mmask = moment_mask.to(torch.uint8).contiguous()
-
-    # ---- a1 clip projection --------------------------------------------------------------
-    fv = ws.get("fv", (B * T, D), act)
-    if prec == L_.BF16:
-        kp = pk["ve_kpad"]
-        v16 = ws.get("v16", (B * T, kp), torch.bfloat16)
-        call("vml_cast_pad_bf16", ptr(vf), ptr(v16), B * T, d0, kp, st)
-        mark("clip_cast")
-        call("vml_clip_projection", ptr(v16), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(fv), B, dims, kp, prec, st)
-    else:
-        call("vml_clip_projection", ptr(vf), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(fv), B, dims, d0, prec, st)
-    mark("clip_projection")
-
-    # ---- a2 query encoder ------------------------------------------------------------------
     bf = prec == L_.BF16
-    qlen = ws.get("qlen", (B,), torch.int32)
-    call("vml_query_lengths", ptr(qmask), ptr(qlen), B, Nq, st)
+    vmask, qmask, lmask, mmask, qlen = inp["vmask"], inp["qmask"], inp["lmask"], inp["mmask"], inp["qlen"]
+    main = torch.cuda.current_stream()
+    side = main if serial else ws.side_stream()
+
+    def fork():
+        if side is not main:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+
+    def join(src, dst):
+        if src is not dst:
+            ev = torch.cuda.Event()
+            ev.record(src)
+            dst.wait_event(ev)
+
+    lay = query_layout(dims)
+    ld = lay["ld"]
     gin = ws.get("gin", (B * Nq, 8 * H), f32)
     y0 = ws.get("lstm_y0", (B, Nq, 2 * H), f32)
     fwfs = ws.get("fwfs", (B * Nq + B, 2 * H), f32)            # word states, then sentence states
     fw, fs = fwfs[: B * Nq].view(B, Nq, 2 * H), fwfs[B * Nq:]
     y0h = ws.get("lstm_y0_bf16", (B, Nq, 2 * H), torch.bfloat16) if bf else None
     fwfs_h = ws.get("fwfs_bf16", (B * Nq + B, 2 * H), torch.bfloat16) if bf else None
-    if bf:
-        qk = pk["q_kpad"]
-        q16 = ws.get("q16", (B * Nq, qk), torch.bfloat16)
-        call("vml_cast_pad_bf16", ptr(qf), ptr(q16), B * Nq, 300, qk, st)
-        call("vml_linear", ptr(q16), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, qk, 8 * H, None, 1, prec, 1, st)
-    else:
-        call("vml_linear", ptr(qf), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, 300, 8 * H, None, 1, prec, 1, st)
-    call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), ptr(y0h), None, None, B, Nq, H, st)
-    call("vml_linear", ptr(y0h if bf else y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin), B * Nq, 8 * H, 2 * H, 8 * H,
-         None, 1, prec, 1, st)
-    call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), ptr(fwfs_h), ptr(fs),
-         None if not bf else fwfs_h.data_ptr() + B * Nq * 2 * H * 2, B, Nq, H, st)
-    mark("query_lstm")
-
-    # every query-side projection of every SMI layer in one GEMM (fw / fs do not change across layers)
-    lay = query_layout(dims)
-    ld = lay["ld"]
     qproj = ws.get("qproj", (B * Nq + B, ld), f32)
-    call("vml_linear", ptr(fwfs_h if bf else fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(qproj), B * Nq + B, ld, D, ld,
-         None, 1, prec, 1, st)
-    s_hat_base = qproj.data_ptr() + (B * Nq * ld + lay["s0"]) * 4
-    mark("query_proj")
-
-    # ---- cells + a3/a4 span pooling ---------------------------------------------------------
+    fv = ws.get("fv", (B * T, D), act)
     cells = make_cells(ws, B, Lm)
     cap = cells.capacity
+
+    # ---- a2 query encoder (side stream) ------------------------------------------------------
+    fork()
+    with torch.cuda.stream(side):
+        st = stream_ptr()
+        call("vml_linear", ptr(inp["q"]), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, inp["qk"], 8 * H,
+             None, 1, prec, 1, st)
+        call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), ptr(y0h), None, None, B, Nq, H, st)
+        call("vml_linear", ptr(y0h if bf else y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin), B * Nq, 8 * H, 2 * H, 8 * H,
+             None, 1, prec, 1, st)
+        call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), ptr(fwfs_h), ptr(fs),
+             None if not bf else fwfs_h.data_ptr() + B * Nq * 2 * H * 2, B, Nq, H, st)
+        mark("query_lstm")
+        # every query-side projection of every SMI layer in one GEMM (fw / fs do not change across layers)
+        call("vml_linear", ptr(fwfs_h if bf else fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(qproj), B * Nq + B, ld, D, ld,
+             None, 1, prec, 1, st)
+        mark("query_proj")
+    s_hat_base = qproj.data_ptr() + (B * Nq * ld + lay["s0"]) * 4
+
+    # ---- a1 clip projection, cell compaction (main stream) -----------------------------------------
+    st = stream_ptr()
+    call("vml_clip_projection", ptr(inp["v"]), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(fv), B, dims,
+         inp["vk"], prec, st)
+    mark("clip_projection")
     call("vml_build_cells", ptr(mmask), B, Lm, cells, st)
     mark("build_cells")
+    join(side, main)
+
+    # ---- a3/a4 span pooling ----------------------------------------------------------------------------
     fc = [ws.get("fc_a", (cap, Cc, D), act), ws.get("fc_b", (cap, Cc, D), act)]
     fm = [ws.get("fm_a", (cap, D), act), ws.get("fm_b", (cap, D), act)]
     fb = [ws.get("fb_a", (B, Lm, D), f32), ws.get("fb_b", (B, Lm, D), f32)]
@@ -304,34 +363,48 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
     fused = bf and Cc == 4          # fused epilogues of the tcgen05 path (gate term from the boundary unit, mean_c in-epilogue)
     fbar = ws.get("fbar", (cap, D), act) if fused else None
     n_dev = cells.n_cells
+    two_chains = fused and side is not main
+    cside = side if two_chains else main
+    if two_chains:
+        fork()                      # content chain lives on `side`; it first needs span_pool's fc
     cur = 0
     for k in range(layers):
         nxt = cur ^ 1
-        # a7 boundary unit
         o = k * lay["blk"]
+        # a7 boundary unit (main)
         call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
              ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(fb[nxt]), ptr(fbar), B, dims, prec, st)
         mark("boundary_unit")
-        # a5+a6 content unit
-        if fused and dl == 128 and Nq <= 24:
-            call("vml_content_in_attention", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o, o + dl,
-                 o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(cc_hat), B, dims, st)
-        else:
-            call("vml_linear", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl, n_dev, Cc,
-                 prec, 0, st)
-            mark("content_in_gemm")
-            call("vml_content_attention", ptr(c_hat), ptr(qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
-                 ptr(qmask), cells, ptr(cc_hat), B, dims, prec, st)
-        mark("content_attention")
-        call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]), ptr(fs),
-             ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, st)
-        mark("content_out_gemm")
-        # a8 moment unit
+        ev_bu = None
+        if two_chains:
+            ev_bu = torch.cuda.Event()
+            ev_bu.record(main)
+        # a5+a6 content unit (side when overlapping: the next layer's front half only needs this layer's cu)
+        with torch.cuda.stream(cside):
+            sst = stream_ptr()
+            if fused and dl == 128 and Nq <= 24:
+                call("vml_content_in_attention", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o,
+                     o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(cc_hat), B, dims, sst)
+            else:
+                call("vml_linear", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl,
+                     n_dev, Cc, prec, 0, sst)
+                mark("content_in_gemm")
+                call("vml_content_attention", ptr(c_hat), ptr(qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
+                     ptr(qmask), cells, ptr(cc_hat), B, dims, prec, sst)
+            mark("content_attention")
+            if ev_bu is not None:
+                cside.wait_event(ev_bu)         # fbar of this layer
+            call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]), ptr(fs),
+                 ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
+            mark("content_out_gemm")
+        # a8 moment unit (main)
         if fused:
             call("vml_moment_pair", ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
         else:
             call("vml_moment_operand", ptr(fc[nxt]), ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
         mark("moment_operand")
+        if two_chains:
+            join(side, main)                    # cu half of the operand
         call("vml_moment_out", ptr(mu_op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(fm[cur]), cells, ptr(fm[nxt]), dims, prec, st)
         mark("moment_out_gemm")
         cur = nxt
@@ -347,6 +420,16 @@ def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspa
          ptr(pe), ptr(pa), B, dims, prec, st)
     mark("localize")
     return pm, ps, pe, pa
+
+
+def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace, video_features, video_mask,
+                 query_features, query_mask, length_mask, moment_mask, keep: Optional[dict] = None, mark=None,
+                 overlap: bool = True):
+    """The whole hot path: ``smin_ingest`` + ``smin_core``."""
+    inp = smin_ingest(dims, prec, ws, video_features, video_mask, query_features, query_mask, length_mask, moment_mask)
+    if mark:
+        mark("ingest")
+    return smin_core(pk, dims, prec, ws, inp, keep=keep, mark=mark, overlap=overlap)
 
 
 class SMIN(nn.Module):
@@ -381,7 +464,8 @@ class SMIN(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def forward(self, video_features, video_mask, query_features, query_mask, length_mask, moment_mask, mark=None):
+    def forward(self, video_features, video_mask, query_features, query_mask, length_mask, moment_mask, mark=None,
+                overlap: bool = True):
         if not video_features.is_cuda:
             raise L_.VmlError("vml_b200.SMIN runs on CUDA (sm_100a) only; there is no CPU path. "
                               "Move the module and its inputs to a B200 device.")
@@ -393,5 +477,5 @@ class SMIN(nn.Module):
         with torch.no_grad():
             pk = self._weights(dev, prec)
             ws = self._ws.setdefault(str(dev), Workspace(dev))
-            return smin_forward(pk, self._dims, prec, ws, video_features.float(), video_mask, query_features.float(),
-                                query_mask, length_mask, moment_mask, mark=mark)
+            return smin_forward(pk, self._dims, prec, ws, video_features, video_mask, query_features,
+                                query_mask, length_mask, moment_mask, mark=mark, overlap=overlap)
