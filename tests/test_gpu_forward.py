@@ -88,6 +88,22 @@ def test_every_stage_matches_oracle(name, prec):
             assert torch.equal(fm.cpu() == 0, inter[f"fm{k}"] == 0)
 
 
+@pytest.mark.parametrize("name,B,lo,hi", [("charadessta", 24, 1, 12), ("activitynet", 12, 2, 9), ("tacos", 16, 4, 20)])
+def test_forward_bf16_short_videos(name, B, lo, hi):
+    """Very short videos (1..few map rows): many samples share one 128-row tile of the fused
+    content kernel (multi-group path), and samples with < 5 valid cells exist."""
+    cfg = CONFIGS[name]
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, B, 900 + B, nfeats_range=(lo, hi))
+    ref = _oracle(cfg, batch, params)
+    for prec, tol in (("bf16", BF16_TOL), ("fp32", FP32_TOL)):
+        model = model_for(cfg, prec, params)
+        out = model(*[batch[k].cuda() for k in synth.MODEL_INPUT_KEYS])
+        for key, o, r in zip(("pm", "ps", "pe", "pa"), out, ref):
+            assert rel_err(o, r) < tol, (prec, key, rel_err(o, r))
+            assert torch.equal(o.cpu() == 0, r == 0), key
+
+
 def test_batch_slice_invariance_fp32():
     """Samples are independent (invariant 4): the data-parallel split is exact."""
     cfg = CONFIGS["charadessta"]

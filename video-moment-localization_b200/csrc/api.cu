@@ -1,5 +1,6 @@
 // extern "C" boundary of libvml_b200.so (see include/vml_b200.h) and the GEMM-backed stages.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -76,8 +77,8 @@ int content_attention(const void*, const float*, int, int, int, int, const float
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
                   const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, void*, int, vml_dims_t, int, cudaStream_t);
 int moment_pair(const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
-int content_fused(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
-                  vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
+int content_tc(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
+               vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
              float*, int, vml_dims_t, int, cudaStream_t);
@@ -189,8 +190,8 @@ VML_API int vml_content_attention(const void* c_hat, const float* qproj, int ld,
 VML_API int vml_content_in_attention(const void* fc, const void* W, const float* bias, const float* qproj, int ld, int off_what,
                              int off_ktil, int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask,
                              vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, void* stream) {
-  return content_fused(fc, W, bias, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, cc_hat, B, d,
-                       ST(stream));
+  return content_tc(fc, W, bias, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, cc_hat, B, d,
+                    ST(stream));
 }
 
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm, const float* fs,

@@ -382,7 +382,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         # a5+a6 content unit (side when overlapping: the next layer's front half only needs this layer's cu)
         with torch.cuda.stream(cside):
             sst = stream_ptr()
-            if fused and dl == 128 and Nq <= 24:
+            if fused and dl == 128 and Nq <= 31:
                 call("vml_content_in_attention", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o,
                      o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(cc_hat), B, dims, sst)
             else:

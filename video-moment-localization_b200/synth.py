@@ -75,7 +75,7 @@ def masks_from_nfeats(nfeats: int, T: int, L: int):
 
 
 def make_batch(cfg, B: int, seed: int = 0, full_length: bool = False,
-               features: bool = True) -> Dict[str, torch.Tensor]:
+               features: bool = True, nfeats_range=None) -> Dict[str, torch.Tensor]:
     """One synthetic batch (CPU tensors) keyed like the reference's ``collate_fn`` output
     (dataset.py:76-90,165-186).  ``cfg`` needs attributes T, L, d0, Nq.  With
     ``full_length`` every video has T clips (worst-case map occupancy)."""
@@ -83,7 +83,9 @@ def make_batch(cfg, B: int, seed: int = 0, full_length: bool = False,
     rng = np.random.Generator(np.random.PCG64(seed))
     r = T // L
     nfeats = rng.integers(T // 2, T + 1, size=B)
-    if full_length:
+    if nfeats_range is not None:                          # edge-case batches: very short (or fixed-range) videos
+        nfeats = rng.integers(nfeats_range[0], nfeats_range[1] + 1, size=B)
+    elif full_length:
         nfeats[:] = T
     else:
         nfeats[0] = T                                     # >= 1 full-length sample
