@@ -123,6 +123,14 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
 VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16,
                            float* fs, void* fs_bf16, int B, int Nq, int H, void* stream);
 
+/* Fast-mode variant of the recurrence (H = 256): h.W_hh^T as bf16 mma.sync with the weights resident in
+ * registers, fp32 cell state; one 4-CTA cluster per (direction, 16 samples).  whh_frag: the bf16
+ * fragment-ordered copy of W_hh, uint32 [2 dirs][4 CTAs][8 warps][32 chunks][32 lanes][4]
+ * (register 4*chunk+w of a lane holds the pair W_hh[q*H + 64*cta + 8*warp + lane/4][16*ks + 2*(lane%4) + 8*j + {0,1}],
+ * (ks, q, j) = (reg/8, (reg/2)%4, reg%2); see smin.pack_lstm_fragments).  Other arguments as vml_lstm_layer. */
+VML_API int vml_lstm_layer_tc(const float* gin, const void* whh_frag, const int32_t* qlen, float* y, void* y_bf16,
+                              float* fs, void* fs_bf16, int B, int Nq, int H, void* stream);
+
 /* query_mask[B,Nq] u8 -> qlen[B] int32  (models.py:50, without the D2H copy of :52). */
 VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, int Nq, void* stream);
 

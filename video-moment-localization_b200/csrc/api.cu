@@ -84,6 +84,7 @@ int localize(const void*, const float*, const float*, const float*, vml_cells_t,
              float*, int, vml_dims_t, int, cudaStream_t);
 int query_lengths(const uint8_t*, int32_t*, int, int, cudaStream_t);
 int lstm_layer(const float*, const float*, const int32_t*, float*, void*, float*, void*, int, int, int, cudaStream_t);
+int lstm_layer_tc(const float*, const void*, const int32_t*, float*, void*, float*, void*, int, int, int, cudaStream_t);
 int scaled_iou_bce(const float*, const uint8_t*, const float*, const uint8_t*, const float*, const uint8_t*, const float*,
                    const float*, const uint8_t*, const float*, const float*, const uint8_t*, const uint8_t*, int, int,
                    float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
@@ -169,6 +170,10 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
 VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16, float* fs,
                    void* fs_bf16, int B, int Nq, int H, void* stream) {
   return lstm_layer(gin, whh_t, qlen, y, y_bf16, fs, fs_bf16, B, Nq, H, ST(stream));
+}
+VML_API int vml_lstm_layer_tc(const float* gin, const void* whh_frag, const int32_t* qlen, float* y, void* y_bf16, float* fs,
+                              void* fs_bf16, int B, int Nq, int H, void* stream) {
+  return lstm_layer_tc(gin, whh_frag, qlen, y, y_bf16, fs, fs_bf16, B, Nq, H, ST(stream));
 }
 VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, int Nq, void* stream) {
   return query_lengths(query_mask, qlen, B, Nq, ST(stream));

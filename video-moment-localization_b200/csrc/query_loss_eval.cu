@@ -164,6 +164,169 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
   cluster.sync();                           // no CTA may exit while peers can still address its smem
 }
 
+// -------------------------------------------------------------------------------------
+// Fast-mode recurrence (bf16 operands, fp32 state), H = 256: h_{t-1}.W_hh^T on the tensor cores.
+// One 4-CTA cluster per (direction, tile of 16 samples).  CTA r owns hidden units [64r, 64r+64);
+// warp w of it owns 8 units and keeps the 4 x 8 x 256 slice of W_hh (all four gates) as
+// mma.sync B-fragments IN REGISTERS for the whole sequence (128 registers per thread, loaded once
+// from a fragment-ordered bf16 copy packed on the host side).  A time step of a warp is
+// 64 x mma.m16n8k16 (A = h_{t-1} of the 16 samples from shared memory) whose accumulator layout
+// gives every thread the i,f,g,o pre-activations of 2 units x 2 samples, so the cell update is
+// thread-local.  The new h (bf16 pairs) goes to the h buffer of all 4 CTAs with st.async counted on
+// the destination's mbarrier; warps never meet at a CTA barrier inside the loop.
+// -------------------------------------------------------------------------------------
+constexpr int LT_CL = 4, LT_BT = 16, LT_H = 256, LT_HP = 264;   // h row pitch (bf16): conflict-free fragment loads
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "r"(v), "r"(cluster_mbar) : "memory");
+}
+
+__global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(256, 1)
+lstm_tc_kernel(const float* __restrict__ gin, const uint4* __restrict__ wfrag, const int32_t* __restrict__ qlen,
+               float* __restrict__ y, bf16* __restrict__ y16, float* __restrict__ fs, bf16* __restrict__ fs16, int B, int Nq) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int H = LT_H;
+  __shared__ __align__(16) bf16 hbuf[2][LT_BT][LT_HP];
+  __shared__ __align__(8) uint64_t hbar[2];
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / LT_CL;
+  const int dir = cid & 1, b0 = (cid >> 1) * LT_BT;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int t4 = lane & 3, r = lane >> 2;
+  const int U = rank * 64 + warp * 8 + 2 * t4;          // this thread's two adjacent hidden units: U, U+1
+
+  // recurrent weights -> registers (fragment order: chunk-major, coalesced 16-byte loads)
+  uint32_t wreg[128];
+  {
+    const uint4* src = wfrag + ((size_t)((dir * LT_CL + rank) * 8 + warp) * 32) * 32;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const uint4 v = __ldg(src + c * 32 + lane);
+      wreg[4 * c] = v.x; wreg[4 * c + 1] = v.y; wreg[4 * c + 2] = v.z; wreg[4 * c + 3] = v.w;
+    }
+  }
+  for (int e = tid; e < 2 * LT_BT * LT_HP / 2; e += blockDim.x) reinterpret_cast<uint32_t*>(&hbuf[0][0][0])[e] = 0u;
+  if (tid == 0) { ptx::mbar_init(&hbar[0], 1); ptx::mbar_init(&hbar[1], 1); ptx::fence_barrier_init(); }
+
+  const int smp[2] = {b0 + r, b0 + r + 8};
+  int len[2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) len[a] = smp[a] < B ? min(qlen[smp[a]], Nq) : 0;
+  int maxlen = 0;
+  for (int tt = 0; tt < LT_BT; ++tt) maxlen = max(maxlen, (b0 + tt < B) ? min(qlen[b0 + tt], Nq) : 0);
+
+  // DSMEM destinations of this thread's h pairs in every CTA of the cluster
+  uint32_t remote_h[LT_CL][2], remote_bar[LT_CL];
+#pragma unroll
+  for (int d = 0; d < LT_CL; ++d) {
+    remote_h[d][0] = ptx::mapa(ptx::smem_u32(&hbuf[0][r][U]), d);
+    remote_h[d][1] = ptx::mapa(ptx::smem_u32(&hbuf[0][r + 8][U]), d);
+    remote_bar[d] = ptx::mapa(ptx::smem_u32(&hbar[0]), d);
+  }
+  constexpr uint32_t BUF_BYTES = LT_BT * LT_HP * 2, STEP_BYTES = LT_BT * H * 2;
+
+  float gpre[2][4][2];                       // input-projection values of the coming step: [sample][gate][unit]
+  auto load_gin = [&](int step) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (step < len[a]) {
+        const int t = dir == 0 ? step : len[a] - 1 - step;
+        const float* p = gin + ((size_t)smp[a] * Nq + t) * 8 * H + (size_t)dir * 4 * H + U;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(p + q * H));
+          gpre[a][q][0] = v.x; gpre[a][q][1] = v.y;
+        }
+      }
+    }
+  };
+  float c_state[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, h_state[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  load_gin(0);
+  cluster.sync();
+
+  for (int step = 0; step < maxlen; ++step) {
+    const int cur = step & 1, nxt = cur ^ 1;
+    if (tid == 0) ptx::mbar_arrive_expect_tx(&hbar[nxt], STEP_BYTES);       // arm this step's receive barrier
+    if (step > 0) ptx::mbar_wait(&hbar[cur], (uint32_t)(((step - 1) >> 1) & 1));   // h_{t-1} has landed here
+    float acc[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+    const bf16* hr0 = &hbuf[cur][r][2 * t4];
+    const bf16* hr1 = &hbuf[cur][r + 8][2 * t4];
+#pragma unroll
+    for (int ks = 0; ks < H / 16; ++ks) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(hr0 + ks * 16);
+      a[1] = *reinterpret_cast<const uint32_t*>(hr1 + ks * 16);
+      a[2] = *reinterpret_cast<const uint32_t*>(hr0 + ks * 16 + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(hr1 + ks * 16 + 8);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mma_bf16_16816(acc[q], a, wreg[(ks * 4 + q) * 2], wreg[(ks * 4 + q) * 2 + 1]);
+    }
+    // accumulator (q, e): gate q of (sample e/2, unit e%2)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (step < len[a]) {
+        const int t = dir == 0 ? step : len[a] - 1 - step;
+#pragma unroll
+        for (int un = 0; un < 2; ++un) {
+          const float ig = sigmoidf_(acc[0][2 * a + un] + gpre[a][0][un]), fg = sigmoidf_(acc[1][2 * a + un] + gpre[a][1][un]);
+          const float gg = tanhf(acc[2][2 * a + un] + gpre[a][2][un]), og = sigmoidf_(acc[3][2 * a + un] + gpre[a][3][un]);
+          c_state[a][un] = fg * c_state[a][un] + ig * gg;
+          h_state[a][un] = og * tanhf(c_state[a][un]);
+        }
+        const size_t o = ((size_t)smp[a] * Nq + t) * 2 * H + (size_t)dir * H + U;
+        *reinterpret_cast<float2*>(y + o) = make_float2(h_state[a][0], h_state[a][1]);
+        if (y16) *reinterpret_cast<__nv_bfloat162*>(y16 + o) = __floats2bfloat162_rn(h_state[a][0], h_state[a][1]);
+      }
+    }
+    load_gin(step + 1);                       // consumed one step later: its latency hides behind the exchange
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const __nv_bfloat162 hp = __floats2bfloat162_rn(h_state[a][0], h_state[a][1]);
+      const uint32_t bits = *reinterpret_cast<const uint32_t*>(&hp);
+#pragma unroll
+      for (int d = 0; d < LT_CL; ++d)
+        st_async_u32(remote_h[d][a] + (uint32_t)nxt * BUF_BYTES, bits, remote_bar[d] + (uint32_t)(nxt * 8));
+    }
+  }
+  // zeros past each sample's length (pad_packed_sequence), final states
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    if (smp[a] < B) {
+      for (int t = len[a]; t < Nq; ++t) {
+        const size_t o = ((size_t)smp[a] * Nq + t) * 2 * H + (size_t)dir * H + U;
+        *reinterpret_cast<float2*>(y + o) = make_float2(0.f, 0.f);
+        if (y16) *reinterpret_cast<__nv_bfloat162*>(y16 + o) = __floats2bfloat162_rn(0.f, 0.f);
+      }
+      const size_t o = (size_t)smp[a] * 2 * H + (size_t)dir * H + U;   // fwd: h(len-1); bwd: h(0)
+      if (fs) *reinterpret_cast<float2*>(fs + o) = make_float2(h_state[a][0], h_state[a][1]);
+      if (fs16) *reinterpret_cast<__nv_bfloat162*>(fs16 + o) = __floats2bfloat162_rn(h_state[a][0], h_state[a][1]);
+    }
+  }
+  if (maxlen > 0) ptx::mbar_wait(&hbar[maxlen & 1], (uint32_t)(((maxlen - 1) >> 1) & 1));   // the last step's h has landed here too
+  cluster.sync();                             // no CTA exits while peers may still address its shared memory
+}
+
+int lstm_layer_tc(const float* gin, const void* wfrag, const int32_t* qlen, float* y, void* y16, float* fs, void* fs16, int B,
+                  int Nq, int H, cudaStream_t st) {
+  VML_CHECK_ARG(H == LT_H && B > 0 && Nq > 0);
+  static bool reg = (register_kernel("lstm_tc_kernel"), true); (void)reg;
+  const int clusters = 2 * ceil_div(B, LT_BT);
+  lstm_tc_kernel<<<clusters * LT_CL, 256, 0, st>>>(gin, (const uint4*)wfrag, qlen, y, (bf16*)y16, fs, (bf16*)fs16, B, Nq);
+  VML_LAUNCHED(1);
+  return VML_OK;
+}
+
 int query_lengths(const uint8_t* qmask, int32_t* qlen, int B, int Nq, cudaStream_t st) {
   static bool reg = (register_kernel("query_lengths_kernel"), true); (void)reg;
   query_lengths_kernel<<<ceil_div(B, 128), 128, 0, st>>>(qmask, qlen, B, Nq);

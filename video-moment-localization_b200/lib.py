@@ -47,6 +47,7 @@ _SIGS = {
     "vml_linear": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "vml_clip_projection": [_P, _P, _P, _P, _P, _P, _I, Dims, _I, _I, _P],
     "vml_lstm_layer": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vml_lstm_layer_tc": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "vml_query_lengths": [_P, _P, _I, _I, _P],
     "vml_span_pool_fuse": [_P, _P, Cells, _P, _P, _P, _I, Dims, _I, _P],
     "vml_content_attention": [_P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _I, _P],

@@ -117,6 +117,26 @@ def query_layout(dims: Dims):
     return lay
 
 
+def pack_lstm_fragments(w_fwd: torch.Tensor, w_rev: torch.Tensor) -> torch.Tensor:
+    """W_hh of both directions ([4H, H], H = 256) -> the bf16 mma.sync B-fragment order consumed by
+    ``vml_lstm_layer_tc`` (layout documented in include/vml_b200.h): int32 [2, 4, 8, 32, 32, 4]."""
+    H = w_fwd.shape[1]
+    assert H == 256 and w_fwd.shape[0] == 4 * H
+    dev = w_fwd.device
+    W = torch.stack([w_fwd, w_rev]).to(torch.bfloat16)                       # [2, 4H, H]
+    ridx = torch.arange(128, device=dev)
+    ks, q, j = ridx // 8, (ridx // 2) % 4, ridx % 2
+    lane = torch.arange(32, device=dev)
+    g, t4 = lane // 4, lane % 4
+    rank, warp = torch.arange(4, device=dev), torch.arange(8, device=dev)
+    row = (q[None, None, :, None] * H + rank[:, None, None, None] * 64 + warp[None, :, None, None] * 8
+           + g[None, None, None, :]).expand(4, 8, 128, 32)
+    col = (ks[:, None] * 16 + 2 * t4[None, :] + 8 * j[:, None])[None, None].expand(4, 8, 128, 32)
+    pair = torch.stack([W[:, row, col], W[:, row, col + 1]], -1).contiguous()   # [2,4,8,128,32,2] (lo, hi)
+    regs = pair.view(torch.int32).reshape(2, 4, 8, 32, 4, 32)                   # reg = 4*chunk + within
+    return regs.permute(0, 1, 2, 3, 5, 4).contiguous()                          # [.., chunk, lane, within]
+
+
 def pack_weights(sd: Dict[str, torch.Tensor], dims: Dims, prec: int, device) -> Dict[str, torch.Tensor]:
     """Re-lay the reference-named parameters for the kernels.
 
@@ -161,6 +181,8 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: Dims, prec: int, device) -> 
                              f32(sd[f"{ls}weight_hh_l{layer}_reverse"]).t().contiguous()], 0)
         pk[f"lstm_wih{layer}"] = gemm_weight(wih, pk["q_kpad"] if layer == 0 else None)
         pk[f"lstm_b{layer}"], pk[f"lstm_whht{layer}"] = bias.contiguous(), whh_t.contiguous()
+        if prec == L_.BF16 and H == 256:
+            pk[f"lstm_frag{layer}"] = pack_lstm_fragments(f32(sd[f"{ls}weight_hh_l{layer}"]), f32(sd[f"{ls}weight_hh_l{layer}_reverse"]))
 
     lay = query_layout(dims)
     qw = torch.zeros(lay["ld"], D, device=device, dtype=torch.float64)
@@ -326,11 +348,15 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         st = stream_ptr()
         call("vml_linear", ptr(inp["q"]), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, inp["qk"], 8 * H,
              None, 1, prec, 1, st)
-        call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), ptr(y0h), None, None, B, Nq, H, st)
+        tc = "lstm_frag0" in pk           # fast mode, H = 256: recurrence on the tensor cores
+        if tc:
+            call("vml_lstm_layer_tc", ptr(gin), ptr(pk["lstm_frag0"]), ptr(qlen), ptr(y0), ptr(y0h), None, None, B, Nq, H, st)
+        else:
+            call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(y0), ptr(y0h), None, None, B, Nq, H, st)
         call("vml_linear", ptr(y0h if bf else y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin), B * Nq, 8 * H, 2 * H, 8 * H,
              None, 1, prec, 1, st)
-        call("vml_lstm_layer", ptr(gin), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), ptr(fwfs_h), ptr(fs),
-             None if not bf else fwfs_h.data_ptr() + B * Nq * 2 * H * 2, B, Nq, H, st)
+        call("vml_lstm_layer_tc" if tc else "vml_lstm_layer", ptr(gin), ptr(pk["lstm_frag1" if tc else "lstm_whht1"]), ptr(qlen),
+             ptr(fw), ptr(fwfs_h), ptr(fs), None if not bf else fwfs_h.data_ptr() + B * Nq * 2 * H * 2, B, Nq, H, st)
         mark("query_lstm")
         # every query-side projection of every SMI layer in one GEMM (fw / fs do not change across layers)
         call("vml_linear", ptr(fwfs_h if bf else fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(qproj), B * Nq + B, ld, D, ld,
