@@ -101,7 +101,8 @@ def stage_work(cfg, B, n_cells, prec_bytes):
     w["content_in_gemm"] = ("tensor", 2.0 * n_cells * C * D * dl)
     w["content_attention"] = ("hbm", 2 * a * n_cells * C * dl)
     w["content_out_gemm"] = ("tensor", 2.0 * n_cells * C * dl * D)
-    w["moment_operand"] = ("hbm", a * (n_cells * C * D + n_cells * 2 * D))
+    # fast mode: only the bu_i*bu_j half is built here (the mean_c cu half comes from the content-out epilogue)
+    w["moment_operand"] = ("hbm", a * n_cells * D + 4 * B * L * D) if a == 2 and C == 4 else ("hbm", a * (n_cells * C * D + n_cells * 2 * D))
     w["moment_out_gemm"] = ("tensor", 4.0 * n_cells * D * D)
     w["boundary_unit"] = ("hbm", a * n_cells * D + 4 * 3 * B * L * D)
     w["localize"] = ("hbm", a * n_cells * D + 4 * B * L * D)
@@ -154,7 +155,8 @@ def main():
     ap.add_argument("--config", default="charadessta", choices=["charadessta", "tacos", "activitynet"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slots", type=int, default=3, help="batches in flight (ScoringPipeline)")
+    ap.add_argument("--slots", type=int, default=2, help="batches in flight (ScoringPipeline)")
+    ap.add_argument("--coalesce", type=int, default=3, help="submitted batches scored per pass (ScoringPipeline)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
 
@@ -204,7 +206,7 @@ def main():
     n_cells = [int(b["moment_mask"].sum().item()) for b in host]
 
     acc = RecallAccumulator(dev)
-    pipe = ScoringPipeline(model, slots=args.slots, use_graph=not args.no_graph)
+    pipe = ScoringPipeline(model, slots=args.slots, coalesce=args.coalesce, use_graph=not args.no_graph)
 
     def step(b, mark=None):
         """Serial eager step through the drop-in module API (instrumented pass only)."""
@@ -227,8 +229,9 @@ def main():
 
     # ---------------- device-resident throughput ------------------------------------------------
     # ScoringPipeline: per step one eager ingest launch + one CUDA-graph replay, `slots` steps in flight
-    for i in range(max(args.warmup, 2 * args.slots + 1)):
+    for i in range(max(args.warmup, (2 * args.slots + 1) * args.coalesce)):
         pipe.submit(resident[i % n_rot])
+    pipe.synchronize()
     barrier()
     launches_per_step = None
     if not args.no_graph:
@@ -247,15 +250,16 @@ def main():
         e1.record()
         barrier()
     launches = lib.launch_count() - launches0
-    if launches_per_step is not None:
-        launches = launches_per_step * args.steps
+    if launches_per_step is not None:     # per step: its own ingest launch + its share of the pass's kernels
+        launches = int(args.steps * (1 + (launches_per_step - 1) / args.coalesce))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * BATCH * args.steps / (ms_total / 1e3)
 
     # ---------------- end to end: pinned host -> device -> counters back ------------------------
     h2d = batch_bytes
     d2h = 8 * 8
-    n_rb = 2 * args.slots + 2
+    lag = 2 * args.slots * args.coalesce
+    n_rb = lag + 2
     result_host = [torch.zeros(2, 4, dtype=torch.int64).pin_memory() for _ in range(n_rb)]
 
     def e2e_run(n):
@@ -266,12 +270,13 @@ def main():
         pending = deque()
         seen = 0
         for i in range(n):
-            ev, _ = pipe.submit(pinned[i % n_rot], from_host=True, readback=result_host[i % n_rb])
+            ev = pipe.submit(pinned[i % n_rot], from_host=True, readback=result_host[i % n_rb])
             pending.append((ev, i % n_rb))
-            if len(pending) > 2 * args.slots:
+            if len(pending) > lag:
                 pev, idx = pending.popleft()
                 pev.synchronize()
                 seen += int(result_host[idx].sum())
+        pipe.flush()
         while pending:
             pev, idx = pending.popleft()
             pev.synchronize()
@@ -289,35 +294,56 @@ def main():
     e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
 
     # ---------------- instrumented pass: per-stage CUDA-event times ------------------------------
-    inst_steps = min(args.steps, 50)
-    events = []
-
-    def make_mark(lst):
-        def mark(name):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            lst.append((name, ev))
-        return mark
-
+    # One serial eager step is recorded (launcher name + arguments per stage); each stage's launches are
+    # then captured into their own CUDA graph and replayed between two CUDA events on the launching
+    # stream, with L2 flushed (256 MiB memset) before every replay -- so a stage time is pure device
+    # time of its kernels on cold caches, free of host launch gaps.
     barrier()
-    for i in range(inst_steps):
-        lst = []
-        start = torch.cuda.Event(enable_timing=True)
-        start.record()
-        step(resident[i % n_rot], mark=make_mark(lst))
-        events.append((start, lst))
+    b0 = resident[0]
+    rec, marks = [], []
+    ev_out = [torch.empty(BATCH, 5, device=dev, dtype=torch.int32), torch.empty(BATCH, 5, device=dev),
+              torch.empty(BATCH, 5, device=dev), torch.zeros(2, 4, device=dev, dtype=torch.int64)]
+    lib.set_recorder(rec)
+    keep_out = model(*[b0[k] for k in synth.MODEL_INPUT_KEYS], mark=lambda name: marks.append((name, len(rec))))
+    lib.call("vml_score_topk_recall", keep_out[0].data_ptr(), keep_out[1].data_ptr(), keep_out[2].data_ptr(),
+             b0["moment_mask"].view(torch.uint8).data_ptr(), b0["sm"].data_ptr(), BATCH, cfg.L, 5, 1, 1, ev_out[0].data_ptr(),
+             ev_out[1].data_ptr(), ev_out[2].data_ptr(), ev_out[3].data_ptr(), None, 0, lib.stream_ptr())
+    marks.append(("eval_topk_recall", len(rec)))
+    lib.set_recorder(None)
     torch.cuda.synchronize()
+    flush = torch.empty(256 * 2**20, device=dev, dtype=torch.uint8)
+    inst_reps = 10
     stage_ms, stage_calls = {}, {}
-    for start, lst in events:
-        prev = start
-        for name, ev in lst:
-            stage_ms[name] = stage_ms.get(name, 0.0) + prev.elapsed_time(ev)
-            stage_calls[name] = stage_calls.get(name, 0) + 1
-            prev = ev
-    per_step = {k: v / inst_steps for k, v in stage_ms.items()}
-    calls_per_step = {k: stage_calls[k] / inst_steps for k in stage_calls}
+    lo = 0
+    for name, hi in marks:
+        calls = rec[lo:hi]
+        lo = hi
+        if not calls:
+            continue
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for fn, a in calls:
+                    lib.call(fn, *a[:-1], lib.stream_ptr())
+            tot = 0.0
+            for _ in range(inst_reps + 1):
+                flush.zero_()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                g.replay()
+                s1.record()
+                s1.synchronize()
+                tot += s0.elapsed_time(s1) if _ else 0.0          # first replay = warm-up
+        torch.cuda.current_stream().wait_stream(side)
+        stage_ms[name] = stage_ms.get(name, 0.0) + tot / inst_reps
+        stage_calls[name] = stage_calls.get(name, 0) + 1
+    per_step = dict(stage_ms)
+    calls_per_step = {k: float(v) for k, v in stage_calls.items()}
     total_inst = sum(per_step.values())
-    mean_cells = sum(n_cells[i % n_rot] for i in range(inst_steps)) / inst_steps
+    inst_steps = 1
+    mean_cells = float(n_cells[0])
     work = stage_work(cfg, BATCH, mean_cells, 2 if args.precision == "bf16" else 4)
     stages = {}
     for name, ms in sorted(per_step.items(), key=lambda kv: -kv[1]):
@@ -338,7 +364,8 @@ def main():
         t = stages[top]
         roofline = {"kernel": top, "bound": t["bound"], "achieved": t["achieved"],
                     "peak": peaks["hbm_gbs"] if t["bound"] == "hbm" else peaks["bf16_tflops"], "unit": t["unit"],
-                    "frac": t["frac"], "traffic": None, "share_of_step": t["share"], "peak_source": peaks["source"]}
+                    "frac": t["frac"], "traffic": None, "share_of_step": t["share"], "peak_source": peaks["source"],
+                    "how": "stage launches replayed as a CUDA graph between CUDA events, L2 flushed before each replay"}
 
     # ---------------- counters across ranks (the only collective) -----------------------------------
     pipe.synchronize()
@@ -380,13 +407,14 @@ def main():
             "config": {"workload": f"{cfg.name}: SMIN forward + R@n,IoU=m eval, batch {BATCH} per GPU, random-init weights "
                                    f"(T={cfg.T} L={cfg.L} C={cfg.C} D={cfg.D} dl={cfg.dl} d0={cfg.d0} Nq={cfg.Nq}, {cfg.layers} SMI layers)",
                        "global_batch": BATCH * world, "parallelism": f"dp{world} (batch sharded by rank, no data-path collective)",
-                       "pipeline": f"{args.slots} batches in flight, " + ("eager launches" if args.no_graph else "ingest launch + CUDA-graph replay per step"),
+                       "pipeline": f"{args.slots} passes in flight, {args.coalesce} submitted batch(es) of {BATCH} scored per pass; per step one ingest launch, per pass "
+                                   + ("eager launches" if args.no_graph else "one CUDA-graph replay"),
                        "l2": f"inputs rotate over {n_rot} resident batches ({n_rot * batch_bytes / 2**20:.0f} MiB > 126 MiB L2)",
-                       "mean_valid_cells_per_batch": mean_cells},
+                       "valid_cells_in_profiled_batch": mean_cells},
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
-                    "pipeline": f"{args.slots} slots: pinned H2D + ingest + graph replay per slot stream; counters read back every step, "
-                                f"consumed {2 * args.slots} steps later"},
+                    "pipeline": f"pinned H2D ring on a copy stream + ingest per step, {args.slots} passes in flight x {args.coalesce} batch(es) per pass; each step's counters read back, "
+                                f"consumed {lag} steps later"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roofline,

@@ -214,10 +214,13 @@ VML_API int vml_scaled_iou_bce(const float* pm, const uint8_t* ym, const float* 
  * n in {1,5}, m in {.1,.3,.5,.7} (ACCUMULATES into counts, like the reference's running
  * sums, main.py:155-156).  nms_num/nms_den: temporal-NMS IoU threshold as a rational;
  * nms_num >= nms_den disables NMS (the reference has none, utils.py:14).  step_counts (optional)
- * is a second accumulator of the same hits, for per-step read-back. */
+ * is a second accumulator of the same hits for per-step read-back: sample b adds into
+ * step_counts[(b / step_group) * 8 + ...] (step_group <= 0: one group), so a pass over several
+ * coalesced batches still reports each batch's own hits. */
 VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask,
                           const float* sm, int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx,
-                          float* top_score, float* top_iou, int64_t* counts, int64_t* step_counts, void* stream);
+                          float* top_score, float* top_iou, int64_t* counts, int64_t* step_counts, int step_group,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 from gpu_util import model_for  # noqa: E402
 
 
-@pytest.mark.parametrize("prec,slots,graph", [("bf16", 2, True), ("fp32", 2, True), ("bf16", 3, False), ("bf16", 1, True)])
-def test_pipeline_matches_eager(prec, slots, graph):
+@pytest.mark.parametrize("prec,slots,graph,coalesce", [("bf16", 2, True, 1), ("fp32", 2, True, 1), ("bf16", 3, False, 1),
+                                                        ("bf16", 1, True, 1), ("bf16", 2, True, 3), ("fp32", 1, True, 2)])
+def test_pipeline_matches_eager(prec, slots, graph, coalesce):
     cfg = CONFIGS["charadessta"]
     model = model_for(cfg, prec)
     batches = [synth.make_batch(cfg, 8, 300 + i) for i in range(7)]
@@ -25,12 +26,18 @@ def test_pipeline_matches_eager(prec, slots, graph):
         out = model(*[b[k] for k in synth.MODEL_INPUT_KEYS], overlap=False)
         acc.update(out[0], out[1], out[2], b["moment_mask"], b["sm"])
         eager.append([o.clone() for o in out])
-    pipe = ScoringPipeline(model, slots=slots, use_graph=graph)
+    pipe = ScoringPipeline(model, slots=slots, use_graph=graph, coalesce=coalesce)
+    group = []
     for i, b in enumerate(dev):
-        ev, slot = pipe.submit({k: b[k] for k in INPUT_KEYS})
-        ev.synchronize()
-        for a, e in zip(slot.outputs[0], eager[i]):
-            assert torch.equal(a, e), (i, "pipeline output differs from the eager module")
+        group.append((i, pipe.submit({k: b[k] for k in INPUT_KEYS})))
+        if len(group) == coalesce or i == len(dev) - 1:
+            pipe.flush()                                  # (only the ragged last group actually needs it)
+            for j, t in group:
+                t.synchronize()
+                for a, e in zip(t.slot.outputs[0], eager[j]):
+                    rows = slice(t.index * 8, t.index * 8 + 8)
+                    assert torch.equal(a[rows], e), (j, "pipeline output differs from the eager module")
+            group = []
     assert torch.equal(pipe.counts.cpu(), acc.counts.cpu())
     assert pipe.result() == acc.result()
 
@@ -45,11 +52,12 @@ def test_pipeline_from_pinned_host_and_readback():
         d = {k: v.cuda() for k, v in b.items()}
         out = model(*[d[k] for k in synth.MODEL_INPUT_KEYS])
         acc.update(out[0], out[1], out[2], d["moment_mask"], d["sm"])
-    pipe = ScoringPipeline(model, slots=2)
+    pipe = ScoringPipeline(model, slots=2, coalesce=2)
     rb = [torch.zeros(2, 4, dtype=torch.int64).pin_memory() for _ in range(len(batches))]
-    evs = [pipe.submit(p, from_host=True, readback=rb[i])[0] for i, p in enumerate(pinned)]
-    for ev in evs:
-        ev.synchronize()
+    tickets = [pipe.submit(p, from_host=True, readback=rb[i]) for i, p in enumerate(pinned)]
+    pipe.flush()
+    for t in tickets:
+        t.synchronize()
     assert torch.equal(sum(rb), acc.counts.cpu())          # per-step hits add up to the total
     assert torch.equal(pipe.counts.cpu(), acc.counts.cpu())
 

@@ -37,6 +37,20 @@ def lstm(B=64, Nq=13, H=256):
         print(f"lstm_layer B={B} Nq={Nq} H={H} full={full}: {us:.1f} us  ({us / Nq:.2f} us/step)")
 
 
+def lstm_tc(B=64, Nq=13, H=256):
+    from vml_b200.smin import pack_lstm_fragments
+    gin = torch.randn(B * Nq, 8 * H, device="cuda") * 0.1
+    frag = pack_lstm_fragments(torch.randn(4 * H, H, device="cuda") * 0.05, torch.randn(4 * H, H, device="cuda") * 0.05)
+    qlen = torch.full((B,), Nq, device="cuda", dtype=torch.int32)
+    y = torch.empty(B, Nq, 2 * H, device="cuda")
+    y16 = torch.empty(B, Nq, 2 * H, device="cuda", dtype=torch.bfloat16)
+    fs = torch.empty(B, 2 * H, device="cuda")
+    st = stream_ptr()
+    us = timeit(lambda: call("vml_lstm_layer_tc", ptr(gin), ptr(frag), ptr(qlen), ptr(y), ptr(y16), ptr(fs), None, B, Nq, H, st))
+    print(f"lstm_layer_tc B={B} Nq={Nq}: {us:.1f} us  ({us / Nq:.2f} us/step)")
+    return us
+
+
 def gemm(M, N, K, prec="bf16", out32=0):
     p = L_.PREC[prec]
     dt = torch.bfloat16 if p == L_.BF16 else torch.float32
@@ -55,6 +69,12 @@ if __name__ == "__main__":
         lstm()
         lstm(B=8)
         lstm(B=64, Nq=20)
+    elif what == "lstm_tc":
+        a = lstm_tc(Nq=13)
+        b = lstm_tc(Nq=26)
+        print(f"per-step slope {(b - a) / 13:.2f} us, fixed {a - 13 * (b - a) / 13:.1f} us")
+        lstm_tc(B=16, Nq=13)
+        lstm_tc(B=256, Nq=13)
     elif what == "gemm":
         for shp in [(21504, 128, 512), (21504, 512, 128), (5376, 512, 1024), (4096, 512, 1024), (832, 2048, 512), (896, 2816, 512),
                     (65536, 512, 1024), (262144, 128, 512)]:

@@ -187,6 +187,10 @@ __device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, 
                ::"r"(cluster_addr), "r"(v), "r"(cluster_mbar) : "memory");
 }
 
+// single-MUFU activations for the fast mode (tanh.approx.f32: ~2^-11 relative error, far inside bf16's)
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
 __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(256, 1)
 lstm_tc_kernel(const float* __restrict__ gin, const uint4* __restrict__ wfrag, const int32_t* __restrict__ qlen,
                float* __restrict__ y, bf16* __restrict__ y16, float* __restrict__ fs, bf16* __restrict__ fs16, int B, int Nq) {
@@ -279,10 +283,10 @@ lstm_tc_kernel(const float* __restrict__ gin, const uint4* __restrict__ wfrag, c
         const int t = dir == 0 ? step : len[a] - 1 - step;
 #pragma unroll
         for (int un = 0; un < 2; ++un) {
-          const float ig = sigmoidf_(acc[0][2 * a + un] + gpre[a][0][un]), fg = sigmoidf_(acc[1][2 * a + un] + gpre[a][1][un]);
-          const float gg = tanhf(acc[2][2 * a + un] + gpre[a][2][un]), og = sigmoidf_(acc[3][2 * a + un] + gpre[a][3][un]);
+          const float ig = sigmoid_fast(acc[0][2 * a + un] + gpre[a][0][un]), fg = sigmoid_fast(acc[1][2 * a + un] + gpre[a][1][un]);
+          const float gg = tanh_fast(acc[2][2 * a + un] + gpre[a][2][un]), og = sigmoid_fast(acc[3][2 * a + un] + gpre[a][3][un]);
           c_state[a][un] = fg * c_state[a][un] + ig * gg;
-          h_state[a][un] = og * tanhf(c_state[a][un]);
+          h_state[a][un] = og * tanh_fast(c_state[a][un]);
         }
         const size_t o = ((size_t)smp[a] * Nq + t) * 2 * H + (size_t)dir * H + U;
         *reinterpret_cast<float2*>(y + o) = make_float2(h_state[a][0], h_state[a][1]);
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(256)
 score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ pe,
                   const uint8_t* __restrict__ mmask, const float* __restrict__ sm, int L, int k, int nms_num, int nms_den,
                   int32_t* __restrict__ top_idx, float* __restrict__ top_score, float* __restrict__ top_iou,
-                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ counts2) {
+                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ counts2, int group) {
   extern __shared__ __align__(8) unsigned char smem_raw[];
   float* sc = reinterpret_cast<float*>(smem_raw);                       // [L*L] scores; < 0 marks taken/suppressed
   __shared__ unsigned long long wbest[8];
@@ -547,7 +551,7 @@ score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, co
         for (int r = 0; r < min(ns[a], k); ++r) hit = hit || (picked[r] >= 0 && picked_iou[r] > thr[t]);
         if (hit) {
           atomicAdd(&counts[a * 4 + t], 1ull);
-          if (counts2) atomicAdd(&counts2[a * 4 + t], 1ull);
+          if (counts2) atomicAdd(&counts2[(b / group) * 8 + a * 4 + t], 1ull);
         }
       }
   }
@@ -555,13 +559,13 @@ score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, co
 
 int score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* mmask, const float* sm, int B,
                       int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score, float* top_iou,
-                      int64_t* counts, int64_t* counts2, cudaStream_t st) {
+                      int64_t* counts, int64_t* counts2, int group, cudaStream_t st) {
   VML_CHECK_ARG(B > 0 && L > 0 && k >= 1 && k <= 8 && nms_den > 0 && (size_t)L * L * 4 <= 200 * 1024);
   static bool reg = (register_kernel("score_topk_kernel"), true); (void)reg;
   const size_t smem = sizeof(float) * L * L;
   VML_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_topk_kernel<<<B, 256, smem, st>>>(pm, ps, pe, mmask, sm, L, k, nms_num, nms_den, top_idx, top_score, top_iou,
-                                          (unsigned long long*)counts, (unsigned long long*)counts2);
+                                          (unsigned long long*)counts, (unsigned long long*)counts2, group > 0 ? group : B);
   VML_LAUNCHED(1);
   return VML_OK;
 }

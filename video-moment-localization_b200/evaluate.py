@@ -23,7 +23,8 @@ def _as_u8(t):
     return t.to(torch.uint8).contiguous()
 
 
-def score_topk_recall(pm, ps, pe, moment_mask, sm, k: int = 5, nms_threshold: float = 1.0, counts=None, step_counts=None):
+def score_topk_recall(pm, ps, pe, moment_mask, sm, k: int = 5, nms_threshold: float = 1.0, counts=None, step_counts=None,
+                      step_group: int = 0):
     """One launch: scores, top-k indices/scores/IoUs per sample, and the 8 hit counters
     (int64 [2,4], accumulated in place when ``counts`` is given; ``step_counts``, optional, is a
     second accumulator for per-step read-back).  Everything stays on the device."""
@@ -41,7 +42,7 @@ def score_topk_recall(pm, ps, pe, moment_mask, sm, k: int = 5, nms_threshold: fl
     pm_, ps_, pe_, sm_ = (t.float().contiguous() for t in (pm, ps, pe, sm))
     mask_ = _as_u8(moment_mask)
     call("vml_score_topk_recall", ptr(pm_), ptr(ps_), ptr(pe_), ptr(mask_), ptr(sm_), B, L, k, fr.numerator, fr.denominator,
-         ptr(top_idx), ptr(top_score), ptr(top_iou), ptr(counts), ptr(step_counts), stream_ptr())
+         ptr(top_idx), ptr(top_score), ptr(top_iou), ptr(counts), ptr(step_counts), step_group, stream_ptr())
     return top_idx, top_score, top_iou, counts
 
 

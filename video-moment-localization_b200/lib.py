@@ -59,7 +59,7 @@ _SIGS = {
     "vml_moment_out": [_P, _P, _P, _P, Cells, _P, Dims, _I, _P],
     "vml_localize": [_P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_scaled_iou_bce": [_P] * 13 + [_I, _I] + [_P] * 7 + [_P],
-    "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
 }
 _RET = {"vml_last_error": C.c_char_p, "vml_kernel_names": C.c_char_p, "vml_launch_count": C.c_int64}
 
@@ -112,5 +112,17 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+# bench instrumentation: when a list is installed here, every launcher call is also appended to it
+# as (name, args) so that a stage's launches can be re-issued (e.g. captured into a CUDA graph).
+_recorder = None
+
+
+def set_recorder(rec):
+    global _recorder
+    _recorder = rec
+
+
 def call(name: str, *args):
+    if _recorder is not None:
+        _recorder.append((name, args))
     check(getattr(load(), name)(*args), name)

@@ -1,12 +1,17 @@
 """Throughput-oriented scoring of a stream of batches: ``SMIN.forward`` + ``compute_ious`` for a
 whole split (the loop of main.py:168-189), with the host taken out of the steady state.
 
-Each of ``slots`` in-flight batches owns a CUDA stream, a workspace and -- after its first use --
-a captured CUDA graph of everything behind ``vml_ingest`` (forward + R@n,IoU=m evaluation).  A
-step is then two host calls: the eager ingest launch (the only kernel that reads caller memory)
-and one graph replay.  Slots run concurrently, so the small kernels of one batch fill the SMs
-another batch leaves idle.  Hit counters are accumulated on the device with atomics and read
-back once (or per step, asynchronously, if the caller wants them).
+* ``slots`` passes are in flight at once; each owns a CUDA stream, a workspace and -- after its first
+  use -- a captured CUDA graph of everything behind ``vml_ingest`` (forward + R@n,IoU=m evaluation).
+  Slots run concurrently, so the small kernels of one pass fill the SMs another pass leaves idle.
+* ``coalesce`` submitted batches are scored by ONE pass: every ``submit`` is an eager ingest launch
+  (the only kernel that reads caller memory) that fills its share of the slot's operand buffers; the
+  last one of a group replays the graph.  Samples are independent (batch-slice invariance is a GPU
+  test), so results are identical to scoring each batch alone -- the passes are just better filled.
+* Pinned host batches are copied H2D on a dedicated copy stream into a ring of staging areas, so the
+  copy engine runs ahead of the compute slots.
+* Hit counters are accumulated on the device with atomics; each submitted batch can have its own
+  hits read back asynchronously (``readback``).
 """
 from __future__ import annotations
 
@@ -21,15 +26,30 @@ from .smin import SMIN, Workspace, smin_core, smin_ingest
 INPUT_KEYS = ("video_features", "video_mask", "query_features", "query_mask", "length_mask", "moment_mask", "sm")
 
 
+class Ticket:
+    """Handle of one submitted batch; ``event`` is recorded once its pass has been enqueued."""
+
+    def __init__(self, slot, index):
+        self.slot, self.index, self.event = slot, index, None
+
+    def synchronize(self):
+        if self.event is None:
+            raise RuntimeError("the batch's group has not been launched yet: call ScoringPipeline.flush()")
+        self.event.synchronize()
+
+
 class _Slot:
-    def __init__(self, device):
+    def __init__(self, device, coalesce):
         self.stream = torch.cuda.Stream(device=device)
         self.ws = Workspace(device)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.done = torch.cuda.Event()
         self.outputs = None
         self.warm = 0
-        self.step_counts = torch.zeros(2, 4, device=device, dtype=torch.int64)   # hits of the slot's current step
+        self.fill = 0                      # batches ingested into the current group
+        self.inp = None
+        self.tickets: List[Ticket] = []
+        self.readbacks: List[Optional[torch.Tensor]] = []
+        self.step_counts = torch.zeros(coalesce, 2, 4, device=device, dtype=torch.int64)   # hits per batch of the group
 
 
 class _Staging:
@@ -42,7 +62,7 @@ class _Staging:
 
 
 class ScoringPipeline:
-    def __init__(self, model: SMIN, slots: int = 2, use_graph: bool = True, nms_threshold: float = 1.0):
+    def __init__(self, model: SMIN, slots: int = 3, coalesce: int = 1, use_graph: bool = True, nms_threshold: float = 1.0):
         L_.load()
         self.model = model
         self.device = next(model.parameters()).device
@@ -50,50 +70,80 @@ class ScoringPipeline:
             raise L_.VmlError("ScoringPipeline runs on CUDA (sm_100a) only; there is no CPU path")
         self.prec = L_.PREC[model.precision]
         self.dims = model._dims
-        self.slots: List[_Slot] = [_Slot(self.device) for _ in range(max(1, slots))]
+        self.coalesce = max(1, coalesce)
+        self.slots: List[_Slot] = [_Slot(self.device, self.coalesce) for _ in range(max(1, slots))]
         self.use_graph = use_graph
         self.nms_threshold = nms_threshold
         self.counts = torch.zeros(2, 4, device=self.device, dtype=torch.int64)
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.staging = [_Staging() for _ in range(len(self.slots) + 1)]
+        self.staging = [_Staging() for _ in range((len(self.slots) + 1) * self.coalesce)]
         self._next_staging = 0
         self.num_samples = 0
-        self._next = 0
+        self._cur = 0
         self._batch = None
         self._pk = None
 
-    # -- one step on a slot ---------------------------------------------------------------------------
-    def _core_and_eval(self, slot: _Slot, pk, inp):
+    # -- one pass on a slot ------------------------------------------------------------------------------
+    def _core_and_eval(self, slot: _Slot, pk, inp, group):
         out = smin_core(pk, self.dims, self.prec, slot.ws, inp)
         slot.step_counts.zero_()
         top = score_topk_recall(out[0], out[1], out[2], inp["mmask"], inp["sm"], 5, self.nms_threshold, self.counts,
-                                step_counts=slot.step_counts)
+                                step_counts=slot.step_counts, step_group=group)
         return out, top
 
-    def submit(self, batch: Dict[str, torch.Tensor], from_host: bool = False, readback: Optional[torch.Tensor] = None):
-        """Enqueue one batch (dict with INPUT_KEYS).  ``from_host``: the tensors are pinned host
-        memory; they are copied H2D on the pipeline's copy stream into a ring of staging areas, so the
-        copy engine runs ahead of the compute slots.  ``readback``: pinned int64 [2,4] host tensor that
-        receives THIS step's hit counters (async D2H on the slot's stream).  Returns
-        (event, slot): the event is recorded after the step; ``slot.outputs`` holds (pm, ps, pe, pa),
-        (top_idx, top_score, top_iou, counts), valid until the slot is reused."""
+    def _launch(self, slot: _Slot):
+        B = self._batch
+        with torch.no_grad(), torch.cuda.stream(slot.stream):
+            pk = self._pk
+            full = slot.fill == self.coalesce
+            inp = dict(slot.inp)
+            inp["B"] = slot.fill * B
+            if self.use_graph and full and slot.graph is not None:
+                slot.graph.replay()
+            elif self.use_graph and full and slot.warm >= 1:
+                # second full pass of the slot: every lazily-initialised piece has run once -> capture
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=slot.stream):
+                    slot.outputs = self._core_and_eval(slot, pk, inp, B)
+                slot.graph = g
+                g.replay()
+            else:
+                slot.outputs = self._core_and_eval(slot, pk, inp, B)
+                slot.warm += 1 if full else 0
+            for i, rb in enumerate(slot.readbacks):
+                if rb is not None:
+                    rb.copy_(slot.step_counts[i], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(slot.stream)
+        for t in slot.tickets:
+            t.event = done
+        slot.fill, slot.tickets, slot.readbacks = 0, [], []
+
+    def submit(self, batch: Dict[str, torch.Tensor], from_host: bool = False, readback: Optional[torch.Tensor] = None) -> Ticket:
+        """Enqueue one batch (dict with INPUT_KEYS).  ``from_host``: the tensors are pinned host memory
+        (H2D on the copy stream).  ``readback``: pinned int64 [2,4] host tensor that receives THIS
+        batch's hit counters (async D2H after its pass).  Returns a Ticket; after
+        ``ticket.synchronize()``, ``ticket.slot.outputs`` holds the pass's (pm, ps, pe, pa) and top-k
+        records (rows ``ticket.index * B ...`` belong to this batch) until the slot is reused."""
         B = batch["video_features"].shape[0]
         if self._batch is None:
             self._batch = B
-        slot = self.slots[self._next]
-        self._next = (self._next + 1) % len(self.slots)
-        caller = torch.cuda.current_stream(self.device)
+        if B != self._batch:
+            raise ValueError(f"ScoringPipeline is set up for batches of {self._batch} (got {B}); score a ragged tail batch "
+                             "with the module API or a second pipeline")
         with torch.no_grad():
             pk = self.model._weights(self.device, self.prec)
             if pk is not self._pk:                   # (re)packed on the caller's stream: publish to every slot stream
                 torch.cuda.synchronize(self.device)
                 self._pk = pk
                 self.invalidate()
+        slot = self.slots[self._cur]
+        caller = torch.cuda.current_stream(self.device)
         with torch.no_grad(), torch.cuda.stream(slot.stream):
             if from_host:
                 stg = self.staging[self._next_staging]
                 self._next_staging = (self._next_staging + 1) % len(self.staging)
-                if stg.buf is None or stg.buf["video_features"].shape[0] != B:
+                if stg.buf is None:
                     stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in INPUT_KEYS}
                 with torch.cuda.stream(self.copy_stream):
                     if stg.free is not None:
@@ -108,45 +158,44 @@ class ScoringPipeline:
                 ev.record(caller)
                 slot.stream.wait_event(ev)           # the caller's tensors are ready
                 src = batch
-            inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True)
+            slot.inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True,
+                                   b_off=slot.fill * B, b_total=self.coalesce * B)
             if from_host:
                 stg.free = torch.cuda.Event()
                 stg.free.record(slot.stream)
-            graphable = self.use_graph and B == self._batch
-            if graphable and slot.graph is not None:
-                slot.graph.replay()
-            elif graphable and slot.warm >= 1:
-                # second use of the slot: every lazily-initialised piece has run once -> capture
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=slot.stream):
-                    slot.outputs = self._core_and_eval(slot, pk, inp)
-                slot.graph = g
-                g.replay()
-            else:
-                slot.outputs = self._core_and_eval(slot, pk, inp)
-                slot.warm += 1
-            if readback is not None:
-                readback.copy_(slot.step_counts, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(slot.stream)
-            slot.done = done
+        ticket = Ticket(slot, slot.fill)
+        slot.tickets.append(ticket)
+        slot.readbacks.append(readback)
+        slot.fill += 1
         self.num_samples += B
-        return done, slot
+        if slot.fill == self.coalesce:
+            self._launch(slot)
+            self._cur = (self._cur + 1) % len(self.slots)
+        return ticket
 
-    def wait_all(self, stream=None):
-        """Make ``stream`` (default: the caller's current stream) wait for every enqueued step."""
-        stream = stream or torch.cuda.current_stream(self.device)
-        for s in self.slots:
-            ev = torch.cuda.Event()
-            ev.record(s.stream)
-            stream.wait_event(ev)
+    def flush(self):
+        """Launch a partially filled group (end of the split)."""
+        slot = self.slots[self._cur]
+        if slot.fill:
+            self._launch(slot)
+            self._cur = (self._cur + 1) % len(self.slots)
 
     def invalidate(self):
         """Drop the captured graphs (call after the model's parameters changed)."""
         for s in self.slots:
             s.graph, s.warm = None, 0
 
+    def wait_all(self, stream=None):
+        """Make ``stream`` (default: the caller's current stream) wait for every enqueued pass."""
+        self.flush()
+        stream = stream or torch.cuda.current_stream(self.device)
+        for s in self.slots:
+            ev = torch.cuda.Event()
+            ev.record(s.stream)
+            stream.wait_event(ev)
+
     def synchronize(self):
+        self.flush()
         for s in self.slots:
             s.stream.synchronize()
 

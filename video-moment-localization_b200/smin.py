@@ -260,12 +260,16 @@ def _mask_u8(t, shape):
 
 
 def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask, query_features, query_mask, length_mask,
-                moment_mask, sm=None, static: bool = False, pk=None):
+                moment_mask, sm=None, static: bool = False, b_off: int = 0, b_total: Optional[int] = None):
     """Take the caller's ``forward`` arguments into library-owned operand buffers with ONE launch
     (``vml_ingest``): bf16 zero-padded feature rows (fast mode), query lengths, and -- when
     ``static`` (CUDA-graph replay of the rest of the step) -- copies of the masks / fp32 features /
-    ``sm`` so that nothing downstream reads caller memory."""
+    ``sm`` so that nothing downstream reads caller memory.  ``b_off`` / ``b_total`` (static mode):
+    this call fills samples [b_off, b_off + B) of operand buffers sized for ``b_total`` samples, so
+    several submitted batches can be scored by one pass (samples are independent)."""
     B = video_features.shape[0]
+    Bt = B if b_total is None else b_total
+    assert static or (b_off == 0 and Bt == B)
     T, Lm, d0, Nq = dims.T, dims.L, dims.d0, dims.Nq
     bf = prec == L_.BF16
     vf = video_features.float().contiguous()
@@ -274,23 +278,27 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
     lmask, mmask = _mask_u8(length_mask, (B, Lm)), _mask_u8(moment_mask, (B, Lm, Lm))
     vk = _round_up(d0, 8) if bf else d0
     qk = _round_up(300, 8) if bf else 300
-    inp = {"B": B, "vk": vk, "qk": qk}
-    qlen = ws.get("qlen", (B,), torch.int32)
+    inp = {"B": Bt, "vk": vk, "qk": qk}
+    qlen = ws.get("qlen", (Bt,), torch.int32)
     if bf:
-        v_out, q_out = ws.get("v16", (B * T, vk), torch.bfloat16), ws.get("q16", (B * Nq, qk), torch.bfloat16)
+        v_out, q_out = ws.get("v16", (Bt * T, vk), torch.bfloat16), ws.get("q16", (Bt * Nq, qk), torch.bfloat16)
     elif static:
-        v_out, q_out = ws.get("v32", (B * T, d0), torch.float32), ws.get("q32", (B * Nq, 300), torch.float32)
+        v_out, q_out = ws.get("v32", (Bt * T, d0), torch.float32), ws.get("q32", (Bt * Nq, 300), torch.float32)
     else:
         v_out = q_out = None
     if static:
-        m_out = [ws.get("in_vmask", (B, T), torch.uint8), ws.get("in_qmask", (B, Nq), torch.uint8),
-                 ws.get("in_lmask", (B, Lm), torch.uint8), ws.get("in_mmask", (B, Lm, Lm), torch.uint8)]
+        m_out = [ws.get("in_vmask", (Bt, T), torch.uint8), ws.get("in_qmask", (Bt, Nq), torch.uint8),
+                 ws.get("in_lmask", (Bt, Lm), torch.uint8), ws.get("in_mmask", (Bt, Lm, Lm), torch.uint8)]
         sm_in = sm.float().contiguous() if sm is not None else None
-        sm_out = ws.get("in_sm", (B, Lm, Lm), torch.float32) if sm is not None else None
+        sm_out = ws.get("in_sm", (Bt, Lm, Lm), torch.float32) if sm is not None else None
     else:
         m_out, sm_in, sm_out = [None] * 4, None, None
-    call("vml_ingest", ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), ptr(v_out), ptr(q_out),
-         *[ptr(m) for m in m_out], ptr(sm_out), ptr(qlen), B, dims, vk, qk, prec, stream_ptr())
+
+    def at(t):                      # device pointer of sample b_off inside a [Bt, ...] operand buffer
+        return None if t is None else t.data_ptr() + b_off * (t.numel() // Bt) * t.element_size()
+
+    call("vml_ingest", ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
+         *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, stream_ptr())
     inp.update(v=v_out if v_out is not None else vf, q=q_out if q_out is not None else qf, qlen=qlen,
                vmask=m_out[0] if static else vmask, qmask=m_out[1] if static else qmask,
                lmask=m_out[2] if static else lmask, mmask=m_out[3] if static else mmask,
