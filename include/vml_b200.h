@@ -171,13 +171,16 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 
 /* Boundary-word scores use the W_q-folded keys kbt (column off_kbt of qproj) and their bias
  * term beta_b (column off_betab): (fb.Wq^T+bq).(fw.Wk^T+bk)^T = fb.kbt^T + beta_b.
- * g_scratch float [B,L,D].  bu float [B,L,D] = f_bb + f_b + f_bm.
+ * Scratch: g_scratch float [B,L,D] (the gated rows G), ab_scratch float [B,L,L] (the attention rows A_b).
+ * bu float [B,L,D] = f_bb + f_b + f_bm.
  * fbar (optional, act [n, D]) receives sigmoid(fm*fs)*fm per cell (models.py:191 == :272-274),
- * which the fused content-out epilogue reuses instead of recomputing it per clip. */
+ * which the fused content-out epilogue reuses instead of recomputing it per clip.
+ * Three launches: gate and rows (warp-level TF32 mma; 3xTF32 split in VML_FP32), then a streaming pass over
+ * the map cells (one CTA per map row). */
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask,
-                      const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* bu, void* fbar,
-                      int B, vml_dims_t d, int prec, void* stream);
+                      const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu,
+                      void* fbar, int B, vml_dims_t d, int prec, void* stream);
 
 /* ---- a8: MomentUnit (models.py:288-303) ------------------------------------------------------ */
 

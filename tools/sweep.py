@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: span-map scaling sweep, kernel-level roofline report (GPU box only).
+
+    python tools/sweep.py [--out gpurun_out/sweep.json] [--quick]
+
+For map side N in {16,32,64,128}, batch B in {32..1024}, window ratio r = T/N in {4 (regular), 2
+(ActivityNet-style irregular)}: times, with CUDA events on the launching stream and L2 flushed
+before every launch, the fused span-pool/fusion kernel (HBM roofline, SURVEY.md 8d bytes) and the
+moment-unit GEMM = the "map-conv stack" (tensor roofline, 4*V*D^2 flops), full-length videos
+(V = N(N+1)/2 valid cells per query).  Peaks: MEASURED_PEAKS.json.
+"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vml_b200  # noqa
+from vml_b200 import lib as L_
+from vml_b200.lib import Dims, call, ptr, stream_ptr
+from vml_b200.smin import Workspace, make_cells
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def cold_time(fn, flush, reps=8):
+    fn(); torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps * 1e3   # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    L_.load()
+    dev = torch.device("cuda")
+    hbm, tf, src = peaks()
+    flush = torch.empty(256 * 2**20, device=dev, dtype=torch.uint8)
+    D, C = 512, 4
+    rows = []
+    Ns = (16, 64) if args.quick else (16, 32, 64, 128)
+    Bs = (64, 1024) if args.quick else (32, 64, 128, 256, 512, 1024)
+    for N in Ns:
+        for r in (4, 2):
+            T = r * N
+            for B in Bs:
+                V = N * (N + 1) // 2
+                n = B * V
+                if n * C * D * 2 > 40e9:          # keep fc under 40 GB
+                    continue
+                dims = Dims(T, N, C, D, 128, 3, 1024, 13, 256)
+                ws = Workspace(dev)
+                cells = make_cells(ws, B, N)
+                mmask = torch.ones(N, N, dtype=torch.bool, device=dev).triu().unsqueeze(0).expand(B, N, N).contiguous().view(torch.uint8)
+                st = stream_ptr()
+                call("vml_build_cells", ptr(mmask), B, N, cells, st)
+                fv = (torch.randn(B * T, D, device=dev) * 0.5).to(torch.bfloat16)
+                fs = torch.randn(B, D, device=dev)
+                fc = torch.empty(n, C, D, device=dev, dtype=torch.bfloat16)
+                fm = torch.empty(n, D, device=dev, dtype=torch.bfloat16)
+                fb = torch.empty(B, N, D, device=dev)
+                us = cold_time(lambda: call("vml_span_pool_fuse", ptr(fv), ptr(fs), cells, ptr(fc), ptr(fm), ptr(fb), B, dims, L_.BF16, st), flush)
+                bytes_ = 2 * (B * T * D + n * C * D + n * D) + 4 * (B * D + B * N * D)
+                gbs = bytes_ / us / 1e3
+                row = {"N": N, "r": r, "T": T, "B": B, "cells": n, "span_pool_us": round(us, 1), "span_pool_GBs": round(gbs, 1),
+                       "span_pool_frac": round(gbs / hbm, 4)}
+                del fc
+                # moment-unit GEMM: mu = [bu_i*bu_j | mean_c cu] . [Wfb|Wfc]^T + b + fm
+                op = (torch.randn(n, 2 * D, device=dev) * 0.1).to(torch.bfloat16)
+                W = (torch.randn(D, 2 * D, device=dev) * 0.03).to(torch.bfloat16)
+                bias = torch.randn(D, device=dev)
+                mu = torch.empty(n, D, device=dev, dtype=torch.bfloat16)
+                us2 = cold_time(lambda: call("vml_moment_out", ptr(op), ptr(W), ptr(bias), ptr(fm), cells, ptr(mu), dims, L_.BF16, st), flush)
+                tfl = 4.0 * n * D * D / us2 / 1e6
+                row.update(moment_gemm_us=round(us2, 1), moment_gemm_TFs=round(tfl, 1), moment_gemm_frac=round(tfl / tf, 4))
+                rows.append(row)
+                print(json.dumps(row), flush=True)
+                del op, mu, fm, fv
+                torch.cuda.empty_cache()
+    out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "timing": "CUDA events, L2 flushed (256 MiB memset) before every launch, mean of 8",
+           "rows": rows}
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(out, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

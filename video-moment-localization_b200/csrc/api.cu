@@ -75,7 +75,7 @@ int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*,
 int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
                       void*, int, vml_dims_t, int, cudaStream_t);
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
-                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, void*, int, vml_dims_t, int, cudaStream_t);
+                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, int, vml_dims_t, int, cudaStream_t);
 int moment_pair(const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int content_tc(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
                vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
@@ -218,10 +218,11 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
-                      vml_cells_t cells, float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, void* stream) {
+                      vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec,
+                      void* stream) {
   VML_PREC_OK(prec);
-  return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, bu, fbar, B, d,
-                       prec, ST(stream));
+  return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, ab_scratch, bu,
+                       fbar, B, d, prec, ST(stream));
 }
 
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {

@@ -1,0 +1,460 @@
+// a7  BoundaryUnit  (Attention.forward models.py:137-154; BoundaryUnit.forward :164-196)
+//
+// Per sample the unit is four small contractions around two softmaxes,
+//     scores = fb.kbt^T (+beta_b)      [L x Nq x D]     Aq   = softmax(scores).fw      [L x D x Nq]
+//     S      = G.G^T / sqrt(D)         [L x L  x D]     f_bb = softmax(S).fb           [L x D x L ]
+// with G = fb * (Aq*lmask + fs), plus one streaming pass over the sample's map cells (boundary_stream_kernel,
+// one CTA per map row, HBM-bound)
+//     f_bm[i] = sum_j A_b[i,j] * sigmoid(fm_ij*fs)*fm_ij     (also written out per cell as `fbar`).
+// The contractions run as warp-level mma.sync m16n8k8 TF32 with fp32 accumulation: one pass in the
+// fast mode, the 3xTF32 split (a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, ~2^-21 relative) in the fp32
+// validation mode, so both modes share this code.  One CTA (8 warps) per (sample, 16 map rows):
+// contractions over D are split across the warps along K and reduced through shared memory,
+// contractions producing D columns are split across the warps along N.
+#include "common.cuh"
+
+namespace vml {
+
+constexpr int BMM_ROWS = 16, BMM_WARPS = 8, BMM_THREADS = BMM_WARPS * 32;
+constexpr int BMM_MAXQ = 32;      // word slots (Nq <= 32)
+constexpr int BMM_MAXD64 = 8;     // D <= 512: D/64 column tiles per warp
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// d[16x8] += a[16x8] . b[8x8]; fragment layout of mma.m16n8k8 (g = lane/4, t = lane%4):
+//   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k=t, n=g)  b1 (k=t+4, n=g);  d0,d1 (g, 2t..2t+1)  d2,d3 (g+8, ..)
+template <bool PRECISE>
+__device__ __forceinline__ void mma_16x8x8(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], bh[2];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ah[e] = f2tf32(a[e]);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) bh[e] = f2tf32(b[e]);
+  if (PRECISE) {
+    uint32_t al[4], bl[2];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) al[e] = f2tf32(a[e] - __uint_as_float(ah[e]));
+#pragma unroll
+    for (int e = 0; e < 2; ++e) bl[e] = f2tf32(b[e] - __uint_as_float(bh[e]));
+    mma_tf32(d, al, bh);
+    mma_tf32(d, ah, bl);
+  }
+  mma_tf32(d, ah, bh);
+}
+
+// ---- gate:  G[b,l,:] = fb * (softmax(fb.kbt^T + beta_b).fw * lmask + fs) ------------------------------
+// The sample's W_q-folded keys and word states are staged once per CTA in shared memory (rows padded
+// by 4 floats: the mma fragment loads are then bank-conflict free).
+template <bool PRECISE>
+__global__ void __launch_bounds__(BMM_THREADS)
+boundary_gate_mma_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
+                         const float* __restrict__ fs, const float* __restrict__ fb, const uint8_t* __restrict__ qmask,
+                         const uint8_t* __restrict__ lmask, float* __restrict__ G, int L, int Nq, int D) {
+  extern __shared__ __align__(16) float sg[];
+  const int DS = D + 4;
+  float* Ks = sg;                                     // [Nq][DS]  kbt
+  float* Ws = Ks + (size_t)Nq * DS;                   // [Nq][DS]  fw
+  float* Xs = Ws + (size_t)Nq * DS;                   // [16][DS]  this tile's fb rows
+  __shared__ float part[BMM_WARPS][BMM_ROWS][BMM_MAXQ + 1];
+  __shared__ float prob[BMM_ROWS][BMM_MAXQ + 4];
+  const int b = blockIdx.y, i0 = blockIdx.x * BMM_ROWS;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
+  const int dq = D / 4;
+  for (int e = tid; e < Nq * dq; e += BMM_THREADS) {
+    const int k = e / dq, c4 = (e - k * dq) * 4;
+    *reinterpret_cast<float4*>(Ks + (size_t)k * DS + c4) = __ldg(reinterpret_cast<const float4*>(qproj + ((size_t)b * Nq + k) * ld + off_kbt + c4));
+    *reinterpret_cast<float4*>(Ws + (size_t)k * DS + c4) = __ldg(reinterpret_cast<const float4*>(fw + ((size_t)b * Nq + k) * D + c4));
+  }
+  for (int e = tid; e < BMM_ROWS * dq; e += BMM_THREADS) {
+    const int rr = e / dq, c4 = (e - rr * dq) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + rr < L) v = __ldg(reinterpret_cast<const float4*>(fb + ((size_t)b * L + i0 + rr) * D + c4));
+    *reinterpret_cast<float4*>(Xs + (size_t)rr * DS + c4) = v;
+  }
+  __syncthreads();
+  const int rA = i0 + g, rB = i0 + g + 8;
+  const bool vA = rA < L, vB = rB < L;
+  const int nq_tiles = (Nq + 7) / 8;
+  const int dpw = D / BMM_WARPS;                       // D columns (or K range) owned by this warp
+  // ---- scores, split over K --------------------------------------------------------------------------
+  {
+    float acc[BMM_MAXQ / 8][4];
+#pragma unroll
+    for (int n = 0; n < BMM_MAXQ / 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    for (int k0 = warp * dpw; k0 < (warp + 1) * dpw; k0 += 8) {
+      const float a[4] = {Xs[g * DS + k0 + t], Xs[(g + 8) * DS + k0 + t], Xs[g * DS + k0 + t + 4], Xs[(g + 8) * DS + k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < BMM_MAXQ / 8; ++n) {
+        if (n < nq_tiles) {
+          const int w = n * 8 + g;
+          float bf[2] = {0.f, 0.f};
+          if (w < Nq) { bf[0] = Ks[(size_t)w * DS + k0 + t]; bf[1] = Ks[(size_t)w * DS + k0 + t + 4]; }
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < BMM_MAXQ / 8; ++n) {
+      part[warp][g][n * 8 + 2 * t] = acc[n][0]; part[warp][g][n * 8 + 2 * t + 1] = acc[n][1];
+      part[warp][g + 8][n * 8 + 2 * t] = acc[n][2]; part[warp][g + 8][n * 8 + 2 * t + 1] = acc[n][3];
+    }
+  }
+  __syncthreads();
+  // ---- masked softmax over the words (models.py:143-150); warp w owns rows 2w, 2w+1, lane = word ---------
+  {
+    const float mk = (lane < Nq && qmask[(size_t)b * Nq + lane]) ? 1.f : 0.f;
+    const float beta = lane < Nq ? qproj[((size_t)b * Nq + lane) * ld + off_betab] : 0.f;
+    const float sqrt_d = sqrtf((float)D);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = 2 * warp + rr;
+      float s = 0.f;
+#pragma unroll
+      for (int p = 0; p < BMM_WARPS; ++p) s += part[p][row][lane];
+      float sv = (s + beta) / sqrt_d;
+      sv = sv * mk;
+      if (mk == 0.f) sv = -1e9f;                       // masked_fill(mask == 0, -1e9)
+      if (lane >= Nq) sv = -INFINITY;                  // not a word at all
+      const float mx = warp_max(sv);
+      const float ex = lane < Nq ? expf(sv - mx) : 0.f;
+      prob[row][lane] = ex / warp_sum(ex);
+    }
+  }
+  __syncthreads();
+  // ---- attended words for this warp's D/8 columns, gate, store G ------------------------------------------
+  {
+    float acc[BMM_MAXD64][4];
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    const int ntd = dpw / 8;
+    for (int k0 = 0; k0 < nq_tiles * 8; k0 += 8) {
+      const float a[4] = {prob[g][k0 + t], prob[g + 8][k0 + t], prob[g][k0 + t + 4], prob[g + 8][k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < BMM_MAXD64; ++n) {
+        if (n < ntd) {
+          const int col = warp * dpw + n * 8 + g;
+          float bf[2];
+          bf[0] = (k0 + t < Nq) ? Ws[(size_t)(k0 + t) * DS + col] : 0.f;
+          bf[1] = (k0 + t + 4 < Nq) ? Ws[(size_t)(k0 + t + 4) * DS + col] : 0.f;
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+    const float lmA = (vA && lmask[(size_t)b * L + rA]) ? 1.f : 0.f, lmB = (vB && lmask[(size_t)b * L + rB]) ? 1.f : 0.f;
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n) {
+      if (n < ntd) {
+        const int col = warp * dpw + n * 8 + 2 * t;
+        const float2 s2 = __ldg(reinterpret_cast<const float2*>(fs + (size_t)b * D + col));
+        if (vA) {
+          const float2 x = *reinterpret_cast<const float2*>(Xs + g * DS + col);
+          *reinterpret_cast<float2*>(G + ((size_t)b * L + rA) * D + col) =
+              make_float2(x.x * (acc[n][0] * lmA + s2.x), x.y * (acc[n][1] * lmA + s2.y));
+        }
+        if (vB) {
+          const float2 x = *reinterpret_cast<const float2*>(Xs + (g + 8) * DS + col);
+          *reinterpret_cast<float2*>(G + ((size_t)b * L + rB) * D + col) =
+              make_float2(x.x * (acc[n][2] * lmB + s2.x), x.y * (acc[n][3] * lmB + s2.y));
+        }
+      }
+    }
+  }
+}
+
+// ---- rows:  A_b = softmax_j(G_i.G_j / sqrt(D)) (masked);  bu[i] = A_b[i,:].fb + fb[i] + sum_j A_b[i,j] fbar_ij ----
+// Keys / values (G, then fb) of the sample are staged in shared memory in blocks of JR rows.  Writes the
+// attention rows A_b and bu = f_bb + f_b; boundary_stream_kernel then adds f_bm.
+constexpr int BMM_JB = 64;
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(BMM_THREADS)
+boundary_rows_mma_kernel(const float* __restrict__ G, const float* __restrict__ fb, const uint8_t* __restrict__ lmask,
+                         float* __restrict__ bu, float* __restrict__ ab_out, int L, int D,
+                         int JR /* rows per staged block: multiple of 8, <= BMM_JB */) {
+  extern __shared__ __align__(16) float sm_all[];
+  const int LP = (L + 7) & ~7;                         // keys padded to a multiple of 8
+  const int LS = LP + 1, DS = D + 4;
+  float* Js = sm_all;                                  // [JR][DS]      staged G / fb rows
+  float* part = Js + (size_t)JR * DS;                  // [8][16][LS]   split-K partial scores
+  float* Ab = part + BMM_WARPS * BMM_ROWS * LS;        // [16][LS]      attention rows
+  float* outT = Ab + BMM_ROWS * LS;                    // [16][DS]      tile rows: G_i, then f_bb + f_b
+  const int b = blockIdx.y, i0 = blockIdx.x * BMM_ROWS;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
+  const int rA = i0 + g, rB = i0 + g + 8;
+  const bool vA = rA < L, vB = rB < L;
+  const int dpw = D / BMM_WARPS, dq = D / 4;
+  const float* Gb = G + (size_t)b * L * D;
+  const float* fbb = fb + (size_t)b * L * D;
+  auto stage = [&](const float* src, int j0) {         // rows [j0, j0 + JR) of src -> Js (zero past L)
+    for (int e = tid; e < JR * dq; e += BMM_THREADS) {
+      const int rr = e / dq, c4 = (e - rr * dq) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + rr < L) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(j0 + rr) * D + c4));
+      *reinterpret_cast<float4*>(Js + (size_t)rr * DS + c4) = v;
+    }
+  };
+  for (int e = tid; e < BMM_ROWS * dq; e += BMM_THREADS) {   // the tile's own G rows
+    const int rr = e / dq, c4 = (e - rr * dq) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + rr < L) v = __ldg(reinterpret_cast<const float4*>(Gb + (size_t)(i0 + rr) * D + c4));
+    *reinterpret_cast<float4*>(outT + (size_t)rr * DS + c4) = v;
+  }
+  // ---- S = G_tile . G^T, split over K, one block of keys at a time --------------------------------------------
+  for (int j0 = 0; j0 < LP; j0 += JR) {
+    __syncthreads();
+    stage(Gb, j0);
+    __syncthreads();
+    const int ntl = min(JR, LP - j0) / 8;
+    float acc[BMM_JB / 8][4];
+#pragma unroll
+    for (int n = 0; n < BMM_JB / 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    for (int k0 = warp * dpw; k0 < (warp + 1) * dpw; k0 += 8) {
+      const float a[4] = {outT[g * DS + k0 + t], outT[(g + 8) * DS + k0 + t], outT[g * DS + k0 + t + 4], outT[(g + 8) * DS + k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < BMM_JB / 8; ++n) {
+        if (n < ntl) {
+          const float bf[2] = {Js[(size_t)(n * 8 + g) * DS + k0 + t], Js[(size_t)(n * 8 + g) * DS + k0 + t + 4]};
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < BMM_JB / 8; ++n) {
+      if (n < ntl) {
+        float* p0 = part + ((size_t)warp * BMM_ROWS + g) * LS + j0 + n * 8 + 2 * t;
+        float* p1 = part + ((size_t)warp * BMM_ROWS + g + 8) * LS + j0 + n * 8 + 2 * t;
+        p0[0] = acc[n][0]; p0[1] = acc[n][1]; p1[0] = acc[n][2]; p1[1] = acc[n][3];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- masked softmax over the keys (models.py:176-184); warp w owns rows 2w, 2w+1 ------------------------------
+  {
+    const float sqrt_d = sqrtf((float)D);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = 2 * warp + rr, i = i0 + row;
+      const bool row_on = i < L && lmask[(size_t)b * L + i] != 0;
+      float* arow = Ab + row * LS;
+      float mx = -INFINITY;
+      for (int j = lane; j < LP; j += 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int p = 0; p < BMM_WARPS; ++p) s += part[((size_t)p * BMM_ROWS + row) * LS + j];
+        float sc = -INFINITY;
+        if (j < L) {
+          const float mk = lmask[(size_t)b * L + j] ? 1.f : 0.f;
+          sc = (s / sqrt_d) * mk;
+          if (mk == 0.f) sc = -1e9f;
+        }
+        arow[j] = sc;
+        mx = fmaxf(mx, sc);
+      }
+      mx = warp_max(mx);
+      float den = 0.f;
+      for (int j = lane; j < LP; j += 32) { const float ex = j < L ? expf(arow[j] - mx) : 0.f; arow[j] = ex; den += ex; }
+      den = warp_sum(den);
+      for (int j = lane; j < LP; j += 32) arow[j] = row_on ? arow[j] / den : 0.f;
+    }
+  }
+  // ---- f_bb for this warp's D/8 columns, one block of values at a time ---------------------------------------------
+  {
+    float acc[BMM_MAXD64][4];
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    const int ntd = dpw / 8;
+    for (int j0 = 0; j0 < LP; j0 += JR) {
+      __syncthreads();
+      stage(fbb, j0);
+      __syncthreads();
+      const int kn = min(JR, LP - j0);
+      for (int k0 = 0; k0 < kn; k0 += 8) {
+        const float a[4] = {Ab[g * LS + j0 + k0 + t], Ab[(g + 8) * LS + j0 + k0 + t], Ab[g * LS + j0 + k0 + t + 4],
+                            Ab[(g + 8) * LS + j0 + k0 + t + 4]};
+#pragma unroll
+        for (int n = 0; n < BMM_MAXD64; ++n) {
+          if (n < ntd) {
+            const int col = warp * dpw + n * 8 + g;
+            const float bf[2] = {Js[(size_t)(k0 + t) * DS + col], Js[(size_t)(k0 + t + 4) * DS + col]};
+            mma_16x8x8<PRECISE>(acc[n], a, bf);
+          }
+        }
+      }
+    }
+    __syncthreads();                                   // every warp is done reading the tile's G rows in outT
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n) {
+      if (n < ntd) {
+        const int col = warp * dpw + n * 8 + 2 * t;
+        float2 xa = make_float2(0.f, 0.f), xb = xa;
+        if (vA) xa = __ldg(reinterpret_cast<const float2*>(fbb + (size_t)rA * D + col));
+        if (vB) xb = __ldg(reinterpret_cast<const float2*>(fbb + (size_t)rB * D + col));
+        outT[g * DS + col] = acc[n][0] + xa.x; outT[g * DS + col + 1] = acc[n][1] + xa.y;           // (f_bb + f_b)
+        outT[(g + 8) * DS + col] = acc[n][2] + xb.x; outT[(g + 8) * DS + col + 1] = acc[n][3] + xb.y;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- hand over: attention rows and (f_bb + f_b); the streaming kernel adds f_bm ------------------------------------
+  for (int e = tid; e < BMM_ROWS * LP; e += BMM_THREADS) {
+    const int rr = e / LP, j = e - rr * LP;
+    if (i0 + rr < L && j < L) ab_out[((size_t)b * L + i0 + rr) * L + j] = Ab[rr * LS + j];
+  }
+  for (int e = tid; e < BMM_ROWS * dq; e += BMM_THREADS) {
+    const int rr = e / dq, c4 = (e - rr * dq) * 4;
+    if (i0 + rr < L)
+      *reinterpret_cast<float4*>(bu + ((size_t)b * L + i0 + rr) * D + c4) = *reinterpret_cast<const float4*>(outT + (size_t)rr * DS + c4);
+  }
+}
+
+// ---- stream:  fbar_ij = sigmoid(fm_ij*fs)*fm_ij for every valid cell;  bu[i] += sum_j A_b[i,j] fbar_ij ----------------
+// One CTA (4 warps) per map row (b, i): warp w takes the row's cells w, w+4, ..., four at a time; a lane owns
+// the 8 consecutive columns {256*q + 8*lane} (one 16-byte load per cell and column group in fast mode).
+// The four partial sums are combined in warp order, so the result does not depend on scheduling.
+template <typename ActT, int NG, bool PRECISE>
+__global__ void __launch_bounds__(128)
+boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const ActT* __restrict__ fm,
+                       const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
+                       ActT* __restrict__ fbar, int L, int D, int capacity) {
+  extern __shared__ __align__(16) float sred[];        // [3][D] partial sums of warps 1..3
+  const int grow = blockIdx.x;                         // b * L + i
+  const int b = grow / L;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_lo = row_start[grow], n_hi = min(row_start[grow + 1], capacity);
+  if (n_lo >= n_hi) return;                            // empty row: bu stays f_bb + f_b (A_b row is all zero there)
+  const float* arow = ab + (size_t)grow * L;
+  f8 s8[NG], bm[NG];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s8[q].v[e] = 0.f; bm[q].v[e] = 0.f; }
+    if (q * 256 + lane * 8 < D) s8[q] = ld8(fs + (size_t)b * D + q * 256 + lane * 8);
+  }
+  constexpr int CB = 4;
+  for (int n0 = n_lo + warp * CB; n0 < n_hi; n0 += 4 * CB) {
+    f8 m[CB][NG];
+    float a4[CB];
+#pragma unroll
+    for (int u = 0; u < CB; ++u) {
+      const int n = min(n0 + u, n_hi - 1);
+      a4[u] = (n0 + u < n_hi) ? __ldg(arow + (code[n] & 0xff)) : 0.f;
+#pragma unroll
+      for (int q = 0; q < NG; ++q) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[u][q].v[e] = 0.f;
+        if (q * 256 + lane * 8 < D) m[u][q] = ld8(fm + (size_t)n * D + q * 256 + lane * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CB; ++u) {
+      if (n0 + u < n_hi) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q)
+          if (q * 256 + lane * 8 < D) {
+            f8 gv;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float x = m[u][q].v[e], z = x * s8[q].v[e];
+              gv.v[e] = PRECISE ? sigmoidf_(z) * x : __fdividef(x, 1.0f + __expf(-z));
+              bm[q].v[e] = fmaf(a4[u], gv.v[e], bm[q].v[e]);
+            }
+            if (fbar) st8(fbar + (size_t)(n0 + u) * D + q * 256 + lane * 8, gv);
+          }
+      }
+    }
+  }
+  if (warp > 0) {
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+      if (q * 256 + lane * 8 < D) st8(sred + (size_t)(warp - 1) * D + q * 256 + lane * 8, bm[q]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NG; ++q)
+      if (q * 256 + lane * 8 < D) {
+        f8 tot = bm[q];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const f8 p = ld8(sred + (size_t)w * D + q * 256 + lane * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot.v[e] += p.v[e];
+        }
+        float* o = bu + (size_t)grow * D + q * 256 + lane * 8;
+        const f8 base = ld8(o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tot.v[e] = base.v[e] + tot.v[e];
+        st8(o, tot);
+      }
+  }
+}
+
+template <bool PRECISE>
+static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, float* bu, float* ab, int B, vml_dims_t d,
+                       cudaStream_t st) {
+  const int LP = (d.L + 7) & ~7;
+  int JR = LP < BMM_JB ? LP : BMM_JB;
+  auto need = [&](int jr) { return sizeof(float) * ((size_t)jr * (d.D + 4) + (size_t)(BMM_WARPS + 1) * BMM_ROWS * (LP + 1) + (size_t)BMM_ROWS * (d.D + 4)); };
+  while (JR > 8 && need(JR) > 100 * 1024) JR -= 8;      // <= 100 KB: two CTAs per SM
+  const size_t smem = need(JR);
+  VML_CHECK_ARG(smem <= 227 * 1024);
+  VML_CUDA(cudaFuncSetAttribute(boundary_rows_mma_kernel<PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(d.L, BMM_ROWS), B);
+  boundary_rows_mma_kernel<PRECISE><<<grid, BMM_THREADS, smem, st>>>(G, fb, lmask, bu, ab, d.L, d.D, JR);
+  return VML_OK;
+}
+
+template <typename ActT, int NG, bool PRECISE>
+static int launch_stream(const float* ab, const float* fs, const void* fm, vml_cells_t cells, float* bu, void* fbar, int B,
+                         vml_dims_t d, cudaStream_t st) {
+  boundary_stream_kernel<ActT, NG, PRECISE><<<B * d.L, 128, sizeof(float) * 3 * d.D, st>>>(
+      ab, fs, (const ActT*)fm, cells.code, cells.row_start, bu, (ActT*)fbar, d.L, d.D, cells.capacity);
+  return VML_OK;
+}
+
+int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
+                  const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
+                  float* g_scratch, float* ab_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
+  VML_CHECK_ARG(d.Nq <= BMM_MAXQ && d.D % 64 == 0 && d.D <= 64 * BMM_MAXD64 && d.L <= 248 && ld % 4 == 0 && off_kbt % 4 == 0);
+  VML_CHECK_ARG(g_scratch != nullptr && ab_scratch != nullptr);
+  static bool reg = (register_kernel("boundary_gate_mma_kernel"), register_kernel("boundary_rows_mma_kernel"),
+                     register_kernel("boundary_stream_kernel"), true); (void)reg;
+  dim3 grid(ceil_div(d.L, BMM_ROWS), B);
+  const size_t smem_g = sizeof(float) * (size_t)(2 * d.Nq + BMM_ROWS) * (d.D + 4);
+  if (prec == VML_FP32) {
+    VML_CUDA(cudaFuncSetAttribute(boundary_gate_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    boundary_gate_mma_kernel<true><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
+  } else {
+    VML_CUDA(cudaFuncSetAttribute(boundary_gate_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    boundary_gate_mma_kernel<false><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
+  }
+  int rc = prec == VML_FP32 ? launch_rows<true>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st)
+                            : launch_rows<false>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st);
+  if (rc) return rc;
+  const int ng = ceil_div(d.D, 256);
+  if (prec == VML_FP32) rc = ng <= 1 ? launch_stream<float, 1, true>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st)
+                                     : launch_stream<float, 2, true>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st);
+  else rc = ng <= 1 ? launch_stream<bf16, 1, false>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st)
+                    : launch_stream<bf16, 2, false>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st);
+  if (rc) return rc;
+  VML_LAUNCHED(3);
+  return VML_OK;
+}
+
+}  // namespace vml

@@ -38,7 +38,7 @@ struct epi_has_pre<E, std::void_t<typename E::Pre>> : std::true_type {};
 
 template <int BN>
 struct UmmaCfg {
-  static constexpr int STAGES = BN >= 128 ? 5 : 6;
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
   static constexpr int A_BYTES = UG_BM * UG_BK * 2;
   static constexpr int B_BYTES = BN * UG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -202,6 +202,10 @@ int launch_gemm_umma(const void* A, const void* W, int M, int N, int K, int lda,
   if (M <= 0) return VML_OK;
   static bool reg = (register_kernel("gemm_umma_kernel"), true);
   (void)reg;
+  // 128 x 256 tiles halve the shared-memory operand traffic per flop (the 128 x 128 shape sits exactly on the
+  // 128 B/clk smem roof); used once there are enough tiles to fill the machine twice over
+  if (N % 256 == 0 && (int64_t)ceil_div(M, UG_BM) * (N / 256) >= 2 * kNumSMs)
+    return launch_gemm_umma_bn<256, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 128 == 0) return launch_gemm_umma_bn<128, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 64 == 0) return launch_gemm_umma_bn<64, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   return launch_gemm_umma_bn<32, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);

@@ -238,13 +238,17 @@ int ingest(const float* vf, const float* qf, const uint8_t* vmask, const uint8_t
 // a3+a4  fused  f = fv*fs  +  span pooling over clips   (models.py:81,88-98,115-126)
 //
 // One CTA per (sample, D-slice).  The slice of the fused clip sequence is turned into an
-// inclusive prefix sum over t in shared memory (fp32); every pooled clip of every valid cell
-// is then a difference of two prefix rows times fp32(1/clip_size) -- exactly the non-zero
-// pattern of the reference's dense Wc -- and only valid (b,i,j) cells are stored, with
-// 128-bit stores.  fm = mean_c fc (always / C), fb = average pool over T/L clips.
+// inclusive prefix sum over t in shared memory (fp32: all threads load the tile with 128/64-bit
+// coalesced loads, then a segmented scan); every pooled clip of every valid cell is a difference
+// of two prefix rows times fp32(1/clip_size) -- exactly the non-zero pattern of the reference's
+// dense Wc, including ActivityNet's irregular windows -- and consecutive clips of a cell share
+// their boundary row, so a cell costs C+1 shared-memory row reads for C+1 stored rows.  Only
+// valid (b,i,j) cells are stored, with 128-bit stores.  fm = mean_c fc (always / C), fb = average
+// pool over T/L clips.  The D-slice is sized for >= 3-4 resident CTAs per SM: the kernel is a
+// write stream (5 V D bytes out per T D bytes in) and needs the occupancy to keep HBM busy.
 // =====================================================================================
 template <typename ActT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, const int32_t* __restrict__ code,
                  const int32_t* __restrict__ row_start, ActT* __restrict__ fc, ActT* __restrict__ fm,
                  float* __restrict__ fb, int T, int L, int C, int D, int dslice, int capacity) {
@@ -253,21 +257,47 @@ span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, cons
   const int tid = threadIdx.x;
   const int r = T / L;
 
-  // prefix sums of fv*fs along t, one column per thread (coalesced across the slice)
-  for (int d = tid; d < dslice; d += blockDim.x) {
-    const float s = fs[(size_t)b * D + d0 + d];
-    const ActT* col = fv + (size_t)b * T * D + d0 + d;
-    float run = 0.f;
-    P[d] = 0.f;
-    int t = 0;
-    for (; t + 8 <= T; t += 8) {
-      float x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = to_f(col[(size_t)(t + u) * D]);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { run += x[u] * s; P[(size_t)(t + u + 1) * dslice + d] = run; }
+  // ---- load the tile, fuse with fs (a3) ----------------------------------------------------
+  const int q4 = dslice / 4;
+  for (int e = tid; e < T * q4; e += blockDim.x) {
+    const int t = e / q4, c4 = (e - t * q4) * 4;
+    const float4 x = ld4(fv + ((size_t)b * T + t) * D + d0 + c4);
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(fs + (size_t)b * D + d0 + c4));
+    *reinterpret_cast<float4*>(P + (size_t)(t + 1) * dslice + c4) = make_float4(x.x * s4.x, x.y * s4.y, x.z * s4.z, x.w * s4.w);
+  }
+  for (int e = tid; e < dslice; e += blockDim.x) P[e] = 0.f;
+  __syncthreads();
+  // ---- inclusive scan over t: fixed 16-row segments per column, then the running total of the earlier
+  // segments is added -- the summation order depends on T only (never on the slice width or the batch
+  // size, which only decide how the work is spread over CTAs), so results are bitwise batch-invariant.
+  {
+    constexpr int SEG = 16, MAXI = 8;
+    const int nseg = (T + SEG - 1) / SEG;
+    const int items = dslice * nseg;                      // (column, segment) pairs; <= MAXI per thread (checked on the host)
+    for (int e = tid; e < items; e += blockDim.x) {
+      const int col = e % dslice, seg = e / dslice;
+      const int lo = seg * SEG, hi = min(lo + SEG, T);
+      float run = 0.f;
+      for (int t = lo; t < hi; ++t) { run += P[(size_t)(t + 1) * dslice + col]; P[(size_t)(t + 1) * dslice + col] = run; }
     }
-    for (; t < T; ++t) { run += to_f(col[(size_t)t * D]) * s; P[(size_t)(t + 1) * dslice + d] = run; }
+    __syncthreads();
+    float off[MAXI];
+    int it = 0;
+    for (int e = tid; e < items; e += blockDim.x, ++it) {
+      const int col = e % dslice, seg = e / dslice;
+      float o = 0.f;
+      for (int s2 = 0; s2 < seg; ++s2) o += P[(size_t)min((s2 + 1) * SEG, T) * dslice + col];
+      if (it < MAXI) off[it] = o;
+    }
+    __syncthreads();
+    it = 0;
+    for (int e = tid; e < items; e += blockDim.x, ++it) {
+      const int col = e % dslice, seg = e / dslice;
+      if (seg == 0) continue;
+      const int lo = seg * SEG, hi = min(lo + SEG, T);
+      const float o = off[it < MAXI ? it : 0];
+      for (int t = lo; t < hi; ++t) P[(size_t)(t + 1) * dslice + col] += o;
+    }
   }
   __syncthreads();
 
@@ -300,13 +330,14 @@ span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, cons
     for (int e = 0; e < 8; ++e) mean.v[e] = 0.f;
     const int s0 = i * r;
     ActT* fc_row = fc + ((size_t)n * C) * D + d0 + dd;
+    f8 prev = ld8(P + (size_t)s0 * dslice + dd);
     for (int c = 0; c < C; ++c) {
       f8 o;
       if (c < nclips) {
-        f8 a = ld8(P + (size_t)(s0 + (c + 1) * cs) * dslice + dd);
-        f8 z = ld8(P + (size_t)(s0 + c * cs) * dslice + dd);
+        const f8 cur = ld8(P + (size_t)(s0 + (c + 1) * cs) * dslice + dd);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { o.v[e] = (a.v[e] - z.v[e]) * w; mean.v[e] += o.v[e]; }
+        for (int e = 0; e < 8; ++e) { o.v[e] = (cur.v[e] - prev.v[e]) * w; mean.v[e] += o.v[e]; }
+        prev = cur;
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o.v[e] = 0.f;
@@ -323,21 +354,28 @@ int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc,
                    vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.T % d.L == 0 && d.D % 8 == 0 && d.C >= 1);
   static bool reg = (register_kernel("span_pool_kernel"), true); (void)reg;
-  // largest D-slice (multiple of 8 dividing D) whose prefix table fits in 200 KB and that
-  // still yields >= 2 CTAs per SM
+  // D-slice: a multiple of 8 that divides D, at most 256 columns.  Prefer a prefix table within ~48 KB
+  // (>= 4 resident CTAs per SM) but never go below 64 columns for it: 128-byte row segments keep every
+  // store a full line (64-byte segments measured at 2.4 TB/s vs 4+ TB/s).  When the table then exceeds
+  // ~75 KB (1-2 CTAs per SM) the CTA runs 512 threads instead of 256.  Small batches shrink the slice
+  // further to put >= 2 CTAs on every SM.
+  auto bytes = [&](int s) { return (size_t)(d.T + 1) * s * 4; };
   int dslice = d.D;
-  auto fits = [&](int s) { return (size_t)(d.T + 1) * s * 4 <= 200 * 1024; };
-  while (dslice > 8 && (dslice % 16 == 0) && (!fits(dslice) || (int64_t)B * (d.D / dslice) < 2 * kNumSMs)) dslice /= 2;
-  VML_CHECK_ARG(fits(dslice) && d.D % dslice == 0 && dslice % 8 == 0 && dslice / 8 <= 256);
-  const size_t smem = (size_t)(d.T + 1) * dslice * 4;
+  while (dslice % 16 == 0 && (dslice > 256 || (bytes(dslice) > 48 * 1024 && dslice > 64))) dslice /= 2;
+  while (dslice % 16 == 0 && bytes(dslice) > 200 * 1024) dslice /= 2;
+  while (dslice % 16 == 0 && dslice > 8 && (int64_t)B * (d.D / dslice) < 2 * kNumSMs) dslice /= 2;
+  VML_CHECK_ARG(bytes(dslice) <= 200 * 1024 && d.D % dslice == 0 && dslice % 8 == 0 && dslice <= 256);
+  const size_t smem = bytes(dslice);
+  const int threads = smem > 75 * 1024 ? 512 : 256;
+  VML_CHECK_ARG((int64_t)dslice * ceil_div(d.T, 16) <= 8 * threads);     // scan work items per thread
   dim3 grid(B, d.D / dslice);
   if (prec == VML_BF16) {
     VML_CUDA(cudaFuncSetAttribute(span_pool_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    span_pool_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)fv, fs, cells.code, cells.row_start, (bf16*)fc,
+    span_pool_kernel<bf16><<<grid, threads, smem, st>>>((const bf16*)fv, fs, cells.code, cells.row_start, (bf16*)fc,
                                                     (bf16*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
   } else {
     VML_CUDA(cudaFuncSetAttribute(span_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    span_pool_kernel<float><<<grid, 256, smem, st>>>((const float*)fv, fs, cells.code, cells.row_start, (float*)fc,
+    span_pool_kernel<float><<<grid, threads, smem, st>>>((const float*)fv, fs, cells.code, cells.row_start, (float*)fc,
                                                      (float*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
   }
   VML_LAUNCHED(1);
@@ -511,255 +549,7 @@ int content_attention(const void* c_hat, const float* qproj, int ld, int off_wha
 #undef VML_CA
 }
 
-// =====================================================================================
-// a7  BoundaryUnit  (Attention.forward models.py:137-154; BoundaryUnit.forward :164-196)
-// =====================================================================================
-// Both kernels: one CTA per (sample, tile of 8 map rows), one WARP per row; a lane owns the 16-byte
-// column groups {128*i + 4*lane}, so every global/shared access of a row is a coalesced 512 B.
-constexpr int BU_RT = 8;        // rows (= warps) per CTA
-constexpr int BU_MAXG = 8;      // D <= 128 * BU_MAXG (kernels are instantiated for NG = 1, 2, 4, 8 column groups)
-
-// gate:  G[b,l,:] = fb * (softmax(q.k^T/sqrt(D)) . fw * lmask + fs), with q.k^T = fb.kbt^T + beta_b
-// (W_q folded into the per-word keys kbt at pack time, so no per-layer projection of fb).  The
-// sample's keys and word states are staged once per CTA in shared memory.
-template <int NG>
-__global__ void __launch_bounds__(BU_RT * 32)
-boundary_gate_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab,
-                     const float* __restrict__ fw, const float* __restrict__ fs, const float* __restrict__ fb,
-                     const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ lmask, float* __restrict__ G,
-                     int L, int Nq, int D) {
-  extern __shared__ __align__(16) float sg[];
-  float* s_k = sg;                 // [Nq][D]  kbt
-  float* s_w = s_k + Nq * D;       // [Nq][D]  fw
-  float* s_bm = s_w + Nq * D;      // [32] beta_b, [32] mask
-  const int b = blockIdx.y, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const int dq = D / 4;
-  for (int e = tid; e < Nq * dq; e += blockDim.x) {
-    const int k = e / dq, c4 = (e % dq) * 4;
-    *reinterpret_cast<float4*>(s_k + k * D + c4) = __ldg(reinterpret_cast<const float4*>(qproj + ((size_t)b * Nq + k) * ld + off_kbt + c4));
-    *reinterpret_cast<float4*>(s_w + k * D + c4) = __ldg(reinterpret_cast<const float4*>(fw + ((size_t)b * Nq + k) * D + c4));
-  }
-  if (tid < 32) {
-    s_bm[tid] = tid < Nq ? qproj[((size_t)b * Nq + tid) * ld + off_betab] : 0.f;
-    s_bm[32 + tid] = (tid < Nq && qmask[(size_t)b * Nq + tid]) ? 1.f : 0.f;
-  }
-  __syncthreads();
-  const int l = blockIdx.x * BU_RT + warp;
-  if (l >= L) return;
-  const int row = b * L + l;
-  float4 x[NG];
-#pragma unroll
-  for (int i = 0; i < NG; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < NG; ++i)
-    if (i * 128 + lane * 4 < D) x[i] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)row * D + i * 128 + lane * 4));
-  // scores over the words (lane k keeps word k's score)
-  float my_s = -INFINITY;
-  for (int k = 0; k < Nq; ++k) {
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < NG; ++i)
-      if (i * 128 + lane * 4 < D) {
-        const float4 w = *reinterpret_cast<const float4*>(s_k + k * D + i * 128 + lane * 4);
-        acc = fmaf(x[i].x, w.x, acc); acc = fmaf(x[i].y, w.y, acc); acc = fmaf(x[i].z, w.z, acc); acc = fmaf(x[i].w, w.w, acc);
-      }
-    acc = warp_sum(acc);
-    if (lane == k) my_s = acc;
-  }
-  const float mk = s_bm[32 + lane];
-  float sv = lane < Nq ? (my_s + s_bm[lane]) / sqrtf((float)D) : 0.f;
-  sv = sv * mk;
-  if (mk == 0.f) sv = -1e9f;                       // masked_fill(mask == 0, -1e9)
-  if (lane >= Nq) sv = -INFINITY;
-  const float mx = warp_max(sv);
-  const float ex = lane < Nq ? expf(sv - mx) : 0.f;
-  const float p_mine = ex / warp_sum(ex);
-  // attended words, row mask, gate
-  float4 a[NG];
-#pragma unroll
-  for (int i = 0; i < NG; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < Nq; ++k) {
-    const float p = __shfl_sync(0xffffffffu, p_mine, k);
-#pragma unroll
-    for (int i = 0; i < NG; ++i)
-      if (i * 128 + lane * 4 < D) {
-        const float4 w = *reinterpret_cast<const float4*>(s_w + k * D + i * 128 + lane * 4);
-        a[i].x = fmaf(p, w.x, a[i].x); a[i].y = fmaf(p, w.y, a[i].y); a[i].z = fmaf(p, w.z, a[i].z); a[i].w = fmaf(p, w.w, a[i].w);
-      }
-  }
-  const float lm = lmask[row] ? 1.f : 0.f;
-#pragma unroll
-  for (int i = 0; i < NG; ++i)
-    if (i * 128 + lane * 4 < D) {
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(fs + (size_t)b * D + i * 128 + lane * 4));
-      float4 g;
-      g.x = x[i].x * (a[i].x * lm + s4.x); g.y = x[i].y * (a[i].y * lm + s4.y);
-      g.z = x[i].z * (a[i].z * lm + s4.z); g.w = x[i].w * (a[i].w * lm + s4.w);
-      *reinterpret_cast<float4*>(G + (size_t)row * D + i * 128 + lane * 4) = g;
-    }
-}
-
-// row:  A_b[i,:] = softmax_j(G_i.G_j/sqrt(D)) (masked) ;
-//       bu[i] = A_b[i,:].fb + fb[i] + sum_j A_b[i,j] sigmoid(fm_ij*fs)*fm_ij   (also written out as fbar)
-template <typename ActT, int NG>
-__global__ void __launch_bounds__(BU_RT * 32)
-boundary_row_kernel(const float* __restrict__ G, const float* __restrict__ fb, const float* __restrict__ fs,
-                    const ActT* __restrict__ fm, const uint8_t* __restrict__ lmask, const int32_t* __restrict__ code,
-                    const int32_t* __restrict__ row_start, float* __restrict__ bu, ActT* __restrict__ fbar, int L, int D,
-                    int capacity) {
-  extern __shared__ float s_all[];  // [BU_RT][L] attention rows
-  const int b = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int i_row = blockIdx.x * BU_RT + warp;
-  if (i_row >= L) return;
-  float* s_a = s_all + warp * L;
-  const int row = b * L + i_row;
-  const bool row_on = lmask[row] != 0;
-  const int n_lo = row_start[row], n_hi = min(row_start[row + 1], capacity);
-  float4 s4[NG], acc[NG];
-#pragma unroll
-  for (int i = 0; i < NG; ++i) { s4[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc[i] = s4[i]; }
-#pragma unroll
-  for (int i = 0; i < NG; ++i)
-    if (i * 128 + lane * 4 < D) {
-      s4[i] = __ldg(reinterpret_cast<const float4*>(fs + (size_t)b * D + i * 128 + lane * 4));
-      acc[i] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)row * D + i * 128 + lane * 4));   // + f_b
-    }
-  if (row_on) {
-    float4 gi[NG];
-#pragma unroll
-    for (int i = 0; i < NG; ++i) gi[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < NG; ++i)
-      if (i * 128 + lane * 4 < D) gi[i] = __ldg(reinterpret_cast<const float4*>(G + (size_t)row * D + i * 128 + lane * 4));
-    for (int j0 = 0; j0 < L; j0 += 4) {            // 4 key rows per round trip: all loads first, then the math
-      float4 w[4][NG];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* gj = G + ((size_t)b * L + min(j0 + u, L - 1)) * D;
-#pragma unroll
-        for (int i = 0; i < NG; ++i)
-          w[u][i] = (i * 128 + lane * 4 < D) ? __ldg(reinterpret_cast<const float4*>(gj + i * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const float mk4 = (lane < 4 && j0 + lane < L && lmask[b * L + j0 + lane]) ? 1.f : 0.f;
-      float d[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < NG; ++i) {
-          t = fmaf(gi[i].x, w[u][i].x, t); t = fmaf(gi[i].y, w[u][i].y, t); t = fmaf(gi[i].z, w[u][i].z, t); t = fmaf(gi[i].w, w[u][i].w, t);
-        }
-        d[u] = warp_sum(t);
-      }
-      if (lane < 4 && j0 + lane < L) {
-        float sc = (lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]) / sqrtf((float)D);
-        sc = sc * mk4;
-        if (mk4 == 0.f) sc = -1e9f;
-        s_a[j0 + lane] = sc;
-      }
-    }
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int j = lane; j < L; j += 32) mx = fmaxf(mx, s_a[j]);
-    mx = warp_max(mx);
-    float den = 0.f;
-    for (int j = lane; j < L; j += 32) { const float ex = expf(s_a[j] - mx); s_a[j] = ex; den += ex; }
-    den = warp_sum(den);
-    for (int j = lane; j < L; j += 32) s_a[j] = s_a[j] / den;
-    __syncwarp();
-    // f_bb = A_b[i,:] . fb  (added to the f_b already in acc: (f_bb + f_b) as the reference orders it)
-    float4 bb[NG];
-#pragma unroll
-    for (int i = 0; i < NG; ++i) bb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int j = 0; j < L; ++j) {
-      const float a = s_a[j];
-      const float* fj = fb + ((size_t)b * L + j) * D;
-#pragma unroll
-      for (int i = 0; i < NG; ++i)
-        if (i * 128 + lane * 4 < D) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(fj + i * 128 + lane * 4));
-          bb[i].x = fmaf(a, w.x, bb[i].x); bb[i].y = fmaf(a, w.y, bb[i].y); bb[i].z = fmaf(a, w.z, bb[i].z); bb[i].w = fmaf(a, w.w, bb[i].w);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NG; ++i)
-      if (i * 128 + lane * 4 < D) { acc[i].x += bb[i].x; acc[i].y += bb[i].y; acc[i].z += bb[i].z; acc[i].w += bb[i].w; }
-  }
-  // f_bm over the valid cells of this map row; the gated map value is also what the content unit adds
-  float4 bm[NG];
-#pragma unroll
-  for (int i = 0; i < NG; ++i) bm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int n0 = n_lo; n0 < n_hi; n0 += 4) {        // 4 cells per round trip
-    float4 m[4][NG];
-    float a4[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int n = min(n0 + u, n_hi - 1);
-      a4[u] = (row_on && n0 + u < n_hi) ? s_a[code[n] & 0xff] : 0.f;
-#pragma unroll
-      for (int i = 0; i < NG; ++i)
-        m[u][i] = (i * 128 + lane * 4 < D) ? ld4(fm + (size_t)n * D + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (n0 + u < n_hi) {
-#pragma unroll
-        for (int i = 0; i < NG; ++i)
-          if (i * 128 + lane * 4 < D) {
-            const float4 mm = m[u][i];
-            float4 g;
-            g.x = sigmoidf_(mm.x * s4[i].x) * mm.x; g.y = sigmoidf_(mm.y * s4[i].y) * mm.y;
-            g.z = sigmoidf_(mm.z * s4[i].z) * mm.z; g.w = sigmoidf_(mm.w * s4[i].w) * mm.w;
-            if (fbar) st4(fbar + (size_t)(n0 + u) * D + i * 128 + lane * 4, g);
-            bm[i].x = fmaf(a4[u], g.x, bm[i].x); bm[i].y = fmaf(a4[u], g.y, bm[i].y);
-            bm[i].z = fmaf(a4[u], g.z, bm[i].z); bm[i].w = fmaf(a4[u], g.w, bm[i].w);
-          }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NG; ++i)
-    if (i * 128 + lane * 4 < D) {
-      float4 o;
-      o.x = acc[i].x + bm[i].x; o.y = acc[i].y + bm[i].y; o.z = acc[i].z + bm[i].z; o.w = acc[i].w + bm[i].w;
-      *reinterpret_cast<float4*>(bu + (size_t)row * D + i * 128 + lane * 4) = o;
-    }
-}
-
-template <int NG>
-static int launch_boundary(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
-                           const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
-                           float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
-  dim3 grid(ceil_div(d.L, BU_RT), B);
-  const size_t smem_g = sizeof(float) * (2 * (size_t)d.Nq * d.D + 64);
-  VML_CUDA(cudaFuncSetAttribute(boundary_gate_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  boundary_gate_kernel<NG><<<grid, BU_RT * 32, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch,
-                                                             d.L, d.Nq, d.D);
-  const size_t smem = sizeof(float) * BU_RT * d.L;
-  if (prec == VML_BF16)
-    boundary_row_kernel<bf16, NG><<<grid, BU_RT * 32, smem, st>>>(g_scratch, fb, fs, (const bf16*)fm, lmask, cells.code,
-                                                                  cells.row_start, bu, (bf16*)fbar, d.L, d.D, cells.capacity);
-  else
-    boundary_row_kernel<float, NG><<<grid, BU_RT * 32, smem, st>>>(g_scratch, fb, fs, (const float*)fm, lmask, cells.code,
-                                                                   cells.row_start, bu, (float*)fbar, d.L, d.D, cells.capacity);
-  VML_LAUNCHED(2);
-  return VML_OK;
-}
-
-int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
-                  const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
-                  float* g_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
-  VML_CHECK_ARG(d.Nq <= 32 && d.D % 4 == 0 && d.D <= 128 * BU_MAXG && ld % 4 == 0 && off_kbt % 4 == 0);
-  static bool reg = (register_kernel("boundary_gate_kernel"), register_kernel("boundary_row_kernel"), true); (void)reg;
-#define VML_BU(NG) return launch_boundary<NG>(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, qmask, lmask, cells, g_scratch, bu, fbar, B, d, prec, st)
-  const int ng = ceil_div(d.D, 128);
-  if (ng <= 1) VML_BU(1);
-  if (ng <= 2) VML_BU(2);
-  if (ng <= 4) VML_BU(4);
-  VML_BU(8);
-#undef VML_BU
-}
+// a7 BoundaryUnit: see boundary_mma.cu
 
 // =====================================================================================
 // a8 operand:  [ bu_i * bu_j | mean_c cu ]   (MomentUnit.forward models.py:292-301)

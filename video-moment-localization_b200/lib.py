@@ -53,7 +53,7 @@ _SIGS = {
     "vml_content_attention": [_P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _I, _P],
     "vml_content_in_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _P],
     "vml_content_out": [_P, _P, _P, _P, _P, _P, _P, _P, Cells, _P, Dims, _I, _P],
-    "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_moment_pair": [_P, Cells, _P, Dims, _I, _P],
     "vml_moment_operand": [_P, _P, Cells, _P, Dims, _I, _P],
     "vml_moment_out": [_P, _P, _P, _P, Cells, _P, Dims, _I, _P],

@@ -393,6 +393,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     c_hat = ws.get("c_hat", (cap * Cc, dl), act)
     cc_hat = ws.get("cc_hat", (cap * Cc, dl), act)
     g_scr = ws.get("bu_g", (B, Lm, D), f32)
+    ab_scr = ws.get("bu_ab", (B, Lm, Lm), f32)
     mu_op = ws.get("mu_op", (cap, 2 * D), act)
     fused = bf and Cc == 4          # fused epilogues of the tcgen05 path (gate term from the boundary unit, mean_c in-epilogue)
     fbar = ws.get("fbar", (cap, D), act) if fused else None
@@ -407,7 +408,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         o = k * lay["blk"]
         # a7 boundary unit (main)
         call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
-             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(fb[nxt]), ptr(fbar), B, dims, prec, st)
+             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar), B, dims, prec, st)
         mark("boundary_unit")
         ev_bu = None
         if two_chains:
