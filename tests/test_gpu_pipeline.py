@@ -62,6 +62,23 @@ def test_pipeline_from_pinned_host_and_readback():
     assert torch.equal(pipe.counts.cpu(), acc.counts.cpu())
 
 
+def test_pipeline_single_blob_h2d():
+    """pack_host_batch: one pinned blob per batch, one H2D copy; same counts as the eager path."""
+    from vml_b200.pipeline import pack_host_batch
+    cfg = CONFIGS["charadessta"]
+    model = model_for(cfg, "bf16")
+    batches = [synth.make_batch(cfg, 8, 500 + i) for i in range(5)]
+    acc = RecallAccumulator(torch.device("cuda"))
+    for b in batches:
+        d = {k: v.cuda() for k, v in b.items()}
+        out = model(*[d[k] for k in synth.MODEL_INPUT_KEYS])
+        acc.update(out[0], out[1], out[2], d["moment_mask"], d["sm"])
+    pipe = ScoringPipeline(model, slots=2, coalesce=2)
+    for b in batches:
+        pipe.submit(pack_host_batch(b), from_host=True)
+    assert pipe.result() == acc.result()
+
+
 def test_overlap_matches_serial_bitwise():
     """Two-stream overlap inside a step changes scheduling only."""
     cfg = CONFIGS["tacos"]

@@ -77,6 +77,8 @@ int content_attention(const void*, const float*, int, int, int, int, const float
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
                   const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, int, vml_dims_t, int, cudaStream_t);
 int moment_pair(const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
+int gemm_res(const void*, const void*, const float*, const void*, const void*, void*, void*, int, int, int, int, int,
+             const int32_t*, int, cudaStream_t);
 int content_tc(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
                vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
@@ -205,6 +207,9 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
   const int M = cells.capacity * d.C;
   if (prec == VML_BF16 && fbar && mu_operand) {
     VML_CHECK_ARG(d.C == 4 && d.D % 32 == 0);
+    if (d.D % 128 == 0)   // residual tiles through shared memory (TMA in / TMA out)
+      return gemm_res(cc_hat, Wc, bc, fc, fbar, cu, (bf16*)mu_operand + d.D, M, d.D, d.dl, d.dl, 2 * d.D, cells.n_cells, d.C,
+                      ST(stream));
     EpiContentOutFused e{bc, (const bf16*)fc, (const bf16*)fbar, (bf16*)cu, (bf16*)mu_operand, d.D};
     return launch_gemm_umma(cc_hat, Wc, M, d.D, d.dl, d.dl, d.dl, cells.n_cells, d.C, e, ST(stream));
   }
@@ -238,6 +243,8 @@ VML_API int vml_moment_pair(const float* bu, vml_cells_t cells, void* operand, v
 VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* bias_sum, const void* fm, vml_cells_t cells,
                    void* mu, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
+  // (K = 2D makes this stage tensor-bound: the register epilogue with 128 x 256 tiles measured faster than the
+  //  shared-memory residual epilogue of gemm_res.cu, which is used for the byte-bound a6 tail)
   if (prec == VML_BF16) {
     EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D};
     return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));

@@ -26,6 +26,35 @@ from .smin import SMIN, Workspace, smin_core, smin_ingest
 INPUT_KEYS = ("video_features", "video_mask", "query_features", "query_mask", "length_mask", "moment_mask", "sm")
 
 
+def pack_host_batch(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Re-lay one batch (dict with INPUT_KEYS) as views into ONE pinned host blob (key ``"_blob"``), so that
+    ``ScoringPipeline.submit(..., from_host=True)`` moves it with a single H2D copy.  (A collate function
+    can write straight into such a blob; the layout is the INPUT_KEYS order, each tensor 256-byte aligned.)"""
+    offs, total = {}, 0
+    for k in INPUT_KEYS:
+        offs[k] = total
+        total += (batch[k].numel() * batch[k].element_size() + 255) // 256 * 256
+    blob = torch.empty(total, dtype=torch.uint8).pin_memory()
+    out = {"_blob": blob}
+    for k in INPUT_KEYS:
+        t = batch[k].contiguous()
+        nbytes = t.numel() * t.element_size()
+        view = blob[offs[k]: offs[k] + nbytes].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        out[k] = view
+    return out
+
+
+def _blob_views(blob: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    out, total = {}, 0
+    for k in INPUT_KEYS:
+        t = like[k]
+        nbytes = t.numel() * t.element_size()
+        out[k] = blob[total: total + nbytes].view(t.dtype).view(t.shape)
+        total += (nbytes + 255) // 256 * 256
+    return out
+
+
 class Ticket:
     """Handle of one submitted batch; ``event`` is recorded once its pass has been enqueued."""
 
@@ -57,6 +86,7 @@ class _Staging:
 
     def __init__(self):
         self.buf: Optional[Dict[str, torch.Tensor]] = None
+        self.blob: Optional[torch.Tensor] = None
         self.ready = torch.cuda.Event()
         self.free: Optional[torch.cuda.Event] = None
 
@@ -143,13 +173,21 @@ class ScoringPipeline:
             if from_host:
                 stg = self.staging[self._next_staging]
                 self._next_staging = (self._next_staging + 1) % len(self.staging)
+                blob = batch.get("_blob")
                 if stg.buf is None:
-                    stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in INPUT_KEYS}
+                    if blob is not None:                          # one device blob mirroring the host blob: one copy per batch
+                        stg.blob = torch.empty(blob.numel(), dtype=torch.uint8, device=self.device)
+                        stg.buf = _blob_views(stg.blob, batch)
+                    else:
+                        stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in INPUT_KEYS}
                 with torch.cuda.stream(self.copy_stream):
                     if stg.free is not None:
                         self.copy_stream.wait_event(stg.free)     # the previous consumer's ingest has read it
-                    for k in INPUT_KEYS:
-                        stg.buf[k].copy_(batch[k], non_blocking=True)
+                    if blob is not None and getattr(stg, "blob", None) is not None:
+                        stg.blob.copy_(blob, non_blocking=True)
+                    else:
+                        for k in INPUT_KEYS:
+                            stg.buf[k].copy_(batch[k], non_blocking=True)
                     stg.ready.record(self.copy_stream)
                 slot.stream.wait_event(stg.ready)
                 src = stg.buf
