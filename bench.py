@@ -187,6 +187,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
     peaks = load_peaks()
@@ -300,14 +301,16 @@ def main():
     # stream, with L2 flushed (256 MiB memset) before every replay -- so a stage time is pure device
     # time of its kernels on cold caches, free of host launch gaps.
     barrier()
-    b0 = resident[0]
+    # the profiled pass has the shape the pipeline actually runs: `coalesce` batches of 64 scored together
+    PB = BATCH * args.coalesce
+    b0 = {k: torch.cat([resident[i % n_rot][k] for i in range(args.coalesce)], 0) for k in keys}
     rec, marks = [], []
-    ev_out = [torch.empty(BATCH, 5, device=dev, dtype=torch.int32), torch.empty(BATCH, 5, device=dev),
-              torch.empty(BATCH, 5, device=dev), torch.zeros(2, 4, device=dev, dtype=torch.int64)]
+    ev_out = [torch.empty(PB, 5, device=dev, dtype=torch.int32), torch.empty(PB, 5, device=dev),
+              torch.empty(PB, 5, device=dev), torch.zeros(2, 4, device=dev, dtype=torch.int64)]
     lib.set_recorder(rec)
     keep_out = model(*[b0[k] for k in synth.MODEL_INPUT_KEYS], mark=lambda name: marks.append((name, len(rec))))
     lib.call("vml_score_topk_recall", keep_out[0].data_ptr(), keep_out[1].data_ptr(), keep_out[2].data_ptr(),
-             b0["moment_mask"].view(torch.uint8).data_ptr(), b0["sm"].data_ptr(), BATCH, cfg.L, 5, 1, 1, ev_out[0].data_ptr(),
+             b0["moment_mask"].view(torch.uint8).data_ptr(), b0["sm"].data_ptr(), PB, cfg.L, 5, 1, 1, ev_out[0].data_ptr(),
              ev_out[1].data_ptr(), ev_out[2].data_ptr(), ev_out[3].data_ptr(), None, 0, lib.stream_ptr())
     marks.append(("eval_topk_recall", len(rec)))
     lib.set_recorder(None)
@@ -340,12 +343,12 @@ def main():
         torch.cuda.current_stream().wait_stream(side)
         stage_ms[name] = stage_ms.get(name, 0.0) + tot / inst_reps
         stage_calls[name] = stage_calls.get(name, 0) + 1
-    per_step = dict(stage_ms)
-    calls_per_step = {k: float(v) for k, v in stage_calls.items()}
+    per_step = {k: v / args.coalesce for k, v in stage_ms.items()}       # ms per step (= per batch of 64)
+    calls_per_step = {k: float(v) / args.coalesce for k, v in stage_calls.items()}
     total_inst = sum(per_step.values())
     inst_steps = 1
-    mean_cells = float(n_cells[0])
-    work = stage_work(cfg, BATCH, mean_cells, 2 if args.precision == "bf16" else 4)
+    mean_cells = float(sum(n_cells[i % n_rot] for i in range(args.coalesce)))
+    work = stage_work(cfg, PB, mean_cells, 2 if args.precision == "bf16" else 4)
     stages = {}
     for name, ms in sorted(per_step.items(), key=lambda kv: -kv[1]):
         ent = {"ms_per_step": round(ms, 5), "share": round(ms / total_inst, 4), "launch_groups_per_step": calls_per_step[name]}
@@ -411,7 +414,7 @@ def main():
                        "pipeline": f"{args.slots} passes in flight, {args.coalesce} submitted batch(es) of {BATCH} scored per pass; per step one ingest launch, per pass "
                                    + ("eager launches" if args.no_graph else "one CUDA-graph replay"),
                        "l2": f"inputs rotate over {n_rot} resident batches ({n_rot * batch_bytes / 2**20:.0f} MiB > 126 MiB L2)",
-                       "valid_cells_in_profiled_batch": mean_cells},
+                       "valid_cells_in_profiled_pass": mean_cells, "queries_in_profiled_pass": PB},
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "pipeline": f"pinned H2D ring on a copy stream + ingest per step, {args.slots} passes in flight x {args.coalesce} batch(es) per pass; each step's counters read back, "

@@ -107,6 +107,17 @@ VML_API int vml_ingest(const float* video_features, const float* query_features,
 VML_API int vml_linear(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
                        const int32_t* m_dev, int m_scale, int prec, int out_fp32, void* stream);
 
+/* Strided, batched fp32 contraction (CUDA cores), the workhorse of the backward path:
+ *   C[b][m][n] (=|+=) alpha * sum_k A[b][m][k] * B[b][n][k],  element strides sam/sak/sab etc.
+ * so that dX = dY.W, dW = dY^T.X and the per-sample attention products need no transposed copies.
+ * accumulate != 0: add into C.  splits > 1: K is cut into ranges combined with fp32 atomics (requires
+ * accumulate).  m_dev / k_dev (optional): device int32 live counts, live M = min(M, *m_dev*m_scale), same for K.
+ * Replaces the autograd-generated mm/bmm calls behind loss.backward() (main.py:150). */
+VML_API int vml_gemm_strided(const float* A, int64_t sam, int64_t sak, int64_t sab, const float* B, int64_t sbn, int64_t sbk,
+                             int64_t sbb, float* C, int64_t scm, int64_t scn, int64_t scb, int M, int N, int K, int batch,
+                             float alpha, int accumulate, int splits, const int32_t* m_dev, int m_scale,
+                             const int32_t* k_dev, int k_scale, void* stream);
+
 /* a1: VideoEncoder.forward (models.py:25-36).  fv = (v.W^T + b)*mask + pe[t]*mask.
  * v: float [B*T,d0] (VML_FP32) or bf16 [B*T,k_pad] (VML_BF16).  fv: act [B*T, D]. */
 VML_API int vml_clip_projection(const void* v, const void* W, const float* bias, const float* pe,
@@ -180,7 +191,9 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask,
                       const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu,
-                      void* fbar, int B, vml_dims_t d, int prec, void* stream);
+                      void* fbar, float* prob_out, float* u_out, int B, vml_dims_t d, int prec, void* stream);
+/* prob_out (optional, float [B,L,Nq]) and u_out (optional, float [B,L,D] = Aq*lmask + fs) are the saved
+ * activations the backward pass needs (training path only). */
 
 /* ---- a8: MomentUnit (models.py:288-303) ------------------------------------------------------ */
 
@@ -224,6 +237,53 @@ VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float*
                           const float* sm, int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx,
                           float* top_score, float* top_iou, int64_t* counts, int64_t* step_counts, int step_group,
                           void* stream);
+
+/* ---- backward / training path (fp32): adjoints behind loss.backward() (main.py:150) -----------------------
+ * All tensors float.  Outputs documented "+=" accumulate (the caller zeroes gradient buffers once per step);
+ * reductions over cells use fp32 atomics.  Dense products of the backward pass are vml_gemm_strided calls. */
+
+/* out[b][n] += alpha * sum_m X[b][m][n]  (bias gradients, per-sample sums); rows may be device-counted. */
+VML_API int vml_colsum(const float* X, int64_t row_stride, int64_t batch_stride, float* out, int64_t out_batch_stride, int M, int N,
+                       int batch, const int32_t* m_dev, int m_scale, float alpha, void* stream);
+/* a9 backward (models.py:335-344): d_fm [n,D], d_fb [B,L,D] written; dw4 [4,D], db4 [4] += . */
+VML_API int vml_localize_bwd(const float* fm, const float* fb, const float* w4, const float* pm, const float* ps, const float* pe,
+                             const float* pa, const float* g_pm, const float* g_ps, const float* g_pe, const float* g_pa,
+                             const uint8_t* length_mask, vml_cells_t cells, float* d_fm, float* d_fb, float* dw4, float* db4, int B,
+                             vml_dims_t d, void* stream);
+/* a8 backward of bu_i*bu_j (models.py:292-295): d_bu [B,L,D] += gather over the row and the column of every snippet. */
+VML_API int vml_pair_bwd(const float* d_operand, int ld_operand, const float* bu, vml_cells_t cells, float* d_bu, int B, vml_dims_t d,
+                         void* stream);
+/* a6 tail backward, elementwise: dY = d_cu_next (may be NULL) + d_operand[:, D:]/C;  d_gbar = sum_c dY. */
+VML_API int vml_cu_tail_bwd(const float* d_cu_next, const float* d_operand, int ld_operand, vml_cells_t cells, float* dY, float* d_gbar,
+                            vml_dims_t d, void* stream);
+/* a5+a6 attention block backward (models.py:207-226,253-266): d_chat [n*C, dl] written; dq (gradient of the folded
+ * query projection, same layout as qproj) and d_shat [B, s_ld] += . */
+VML_API int vml_content_attn_bwd(const float* c_hat, const float* d_cc, const float* qproj, int ld, int off_what, int off_ktil,
+                                 int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask, vml_cells_t cells,
+                                 float* d_chat, float* dq, float* d_shat, int B, vml_dims_t d, void* stream);
+/* gate term gbar = sigmoid(fm*fs)*fm (models.py:191-194 and 272-274): d_fm [n,D] = d_mu + ..., d_ab [B,L,L] +=, d_fs [B,D] += . */
+VML_API int vml_gbar_bwd(const float* fm, const float* fs, const float* ab, const float* d_bu, const float* d_gbar_cu, const float* d_mu,
+                         vml_cells_t cells, float* d_ab, float* d_fm, float* d_fs, int B, vml_dims_t d, void* stream);
+/* row softmax backward: dS = P*(dP - sum(P*dP))*scale*colmask[b,w]; P, dP, dS [batch*R, W]. */
+VML_API int vml_softmax_bwd(const float* P, const float* dP, const uint8_t* colmask, float* dS, int batch, int R, int W, float scale,
+                            void* stream);
+/* a7 gate backward: G = fb*U: d_fb += dG*U, d_Aq = dG*fb*lmask, tmp = dG*fb (its per-sample column sum is d_fs). */
+VML_API int vml_gate_bwd(const float* dG, const float* fb, const float* U, const uint8_t* length_mask, float* d_fb, float* d_Aq,
+                         float* tmp, int B, vml_dims_t d, void* stream);
+/* Y[r,:] (=|+=) X[r,:] * mask[r] */
+VML_API int vml_mask_rows(const float* X, const uint8_t* mask, float* Y, int64_t rows, int D, int accumulate, void* stream);
+/* a3+a4 backward (models.py:81,88-98,115-126): d_fv [B,T,D] written, d_fs [B,D] += . */
+VML_API int vml_span_pool_bwd(const float* d_fc, const float* d_fm, const float* d_fb, const float* fv, const float* fs,
+                              vml_cells_t cells, float* d_fv, float* d_fs, int B, vml_dims_t d, void* stream);
+/* Fused Adam step over a flat buffer (main.py:83: torch.optim.Adam defaults); step counts from 1; grad_scale multiplies g. */
+VML_API int vml_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                          int step, float grad_scale, void* stream);
+/* a2 training path: packed bi-LSTM layer forward that also saves acts [B,Nq,2,5,H] = (i,f,g,o,c), and its BPTT:
+ * dgin [B*Nq,8H] and dgin_rec (zero at each sequence's first processed step) written. whh_t [2][H][4H], whh [2][4H][H]. */
+VML_API int vml_lstm_train_fwd(const float* gin, const float* whh_t, const int32_t* qlen, float* y, float* fs, float* acts, int B,
+                               int Nq, int H, void* stream);
+VML_API int vml_lstm_train_bwd(const float* dy, const float* dfs, const float* whh, const float* acts, const int32_t* qlen, float* dgin,
+                               float* dgin_rec, int B, int Nq, int H, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,10 +5,12 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_strided.cuh"
 #include "gemm_umma.cuh"
 
 namespace vml {
@@ -25,6 +27,16 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> cur;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& c = cur[func];
+  if (bytes <= c) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) c = bytes;
+  return e;
 }
 void register_kernel(const char* name) {
   std::lock_guard<std::mutex> lk(g_reg_mu);
@@ -75,7 +87,27 @@ int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*,
 int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
                       void*, int, vml_dims_t, int, cudaStream_t);
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
-                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, int, vml_dims_t, int, cudaStream_t);
+                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, float*, float*, int, vml_dims_t, int,
+                  cudaStream_t);
+// backward.cu
+int colsum(const float*, int64_t, int64_t, float*, int64_t, int, int, int, const int32_t*, int, float, cudaStream_t);
+int localize_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                 const float*, const float*, const float*, const uint8_t*, vml_cells_t, float*, float*, float*, float*, int, vml_dims_t,
+                 cudaStream_t);
+int pair_bwd(const float*, int, const float*, vml_cells_t, float*, int, vml_dims_t, cudaStream_t);
+int cu_tail_bwd(const float*, const float*, int, vml_cells_t, float*, float*, vml_dims_t, cudaStream_t);
+int content_attn_bwd(const float*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
+                     float*, float*, float*, int, vml_dims_t, cudaStream_t);
+int gbar_bwd(const float*, const float*, const float*, const float*, const float*, const float*, vml_cells_t, float*, float*, float*,
+             int, vml_dims_t, cudaStream_t);
+int softmax_bwd(const float*, const float*, const uint8_t*, float*, int, int, int, float, cudaStream_t);
+int gate_bwd(const float*, const float*, const float*, const uint8_t*, float*, float*, float*, int, vml_dims_t, cudaStream_t);
+int mask_rows(const float*, const uint8_t*, float*, int64_t, int, int, cudaStream_t);
+int span_pool_bwd(const float*, const float*, const float*, const float*, const float*, vml_cells_t, float*, float*, int, vml_dims_t,
+                  cudaStream_t);
+int adam_step(float*, const float*, float*, float*, int64_t, float, float, float, float, int, float, cudaStream_t);
+int lstm_train_fwd(const float*, const float*, const int32_t*, float*, float*, float*, int, int, int, cudaStream_t);
+int lstm_train_bwd(const float*, const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, cudaStream_t);
 int moment_pair(const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int gemm_res(const void*, const void*, const float*, const void*, const void*, void*, void*, int, int, int, int, int,
              const int32_t*, int, cudaStream_t);
@@ -143,6 +175,14 @@ VML_API int vml_ingest(const float* video_features, const float* query_features,
   VML_PREC_OK(prec);
   return ingest(video_features, query_features, video_mask, query_mask, length_mask, moment_mask, sm, v_out, q_out, vmask_out,
                 qmask_out, lmask_out, mmask_out, sm_out, qlen, B, d, v_kpad, q_kpad, prec, ST(stream));
+}
+
+VML_API int vml_gemm_strided(const float* A, int64_t sam, int64_t sak, int64_t sab, const float* B, int64_t sbn, int64_t sbk,
+                             int64_t sbb, float* C, int64_t scm, int64_t scn, int64_t scb, int M, int N, int K, int batch,
+                             float alpha, int accumulate, int splits, const int32_t* m_dev, int m_scale,
+                             const int32_t* k_dev, int k_scale, void* stream) {
+  SGemm g{A, sam, sak, sab, B, sbn, sbk, sbb, C, scm, scn, scb, M, N, K, batch, alpha, accumulate, splits, m_dev, m_scale, k_dev, k_scale};
+  return launch_gemm_strided(g, ST(stream));
 }
 
 VML_API int vml_linear(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
@@ -223,11 +263,11 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
-                      vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec,
-                      void* stream) {
+                      vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar, float* prob_out, float* u_out,
+                      int B, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
   return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, ab_scratch, bu,
-                       fbar, B, d, prec, ST(stream));
+                       fbar, prob_out, u_out, B, d, prec, ST(stream));
 }
 
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {
@@ -273,6 +313,63 @@ VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float*
                           float* top_iou, int64_t* counts, int64_t* step_counts, int step_group, void* stream) {
   return score_topk_recall(pm, ps, pe, moment_mask, sm, B, L, k, nms_num, nms_den, top_idx, top_score, top_iou, counts,
                            step_counts, step_group, ST(stream));
+}
+
+// ---- backward / training path (fp32) ---------------------------------------------------------------------
+VML_API int vml_colsum(const float* X, int64_t row_stride, int64_t batch_stride, float* out, int64_t out_batch_stride, int M, int N,
+                       int batch, const int32_t* m_dev, int m_scale, float alpha, void* stream) {
+  return colsum(X, row_stride, batch_stride, out, out_batch_stride, M, N, batch, m_dev, m_scale, alpha, ST(stream));
+}
+VML_API int vml_localize_bwd(const float* fm, const float* fb, const float* w4, const float* pm, const float* ps, const float* pe,
+                             const float* pa, const float* g_pm, const float* g_ps, const float* g_pe, const float* g_pa,
+                             const uint8_t* length_mask, vml_cells_t cells, float* d_fm, float* d_fb, float* dw4, float* db4, int B,
+                             vml_dims_t d, void* stream) {
+  return localize_bwd(fm, fb, w4, pm, ps, pe, pa, g_pm, g_ps, g_pe, g_pa, length_mask, cells, d_fm, d_fb, dw4, db4, B, d, ST(stream));
+}
+VML_API int vml_pair_bwd(const float* d_operand, int ld_operand, const float* bu, vml_cells_t cells, float* d_bu, int B, vml_dims_t d,
+                         void* stream) {
+  return pair_bwd(d_operand, ld_operand, bu, cells, d_bu, B, d, ST(stream));
+}
+VML_API int vml_cu_tail_bwd(const float* d_cu_next, const float* d_operand, int ld_operand, vml_cells_t cells, float* dY, float* d_gbar,
+                            vml_dims_t d, void* stream) {
+  return cu_tail_bwd(d_cu_next, d_operand, ld_operand, cells, dY, d_gbar, d, ST(stream));
+}
+VML_API int vml_content_attn_bwd(const float* c_hat, const float* d_cc, const float* qproj, int ld, int off_what, int off_ktil,
+                                 int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask, vml_cells_t cells,
+                                 float* d_chat, float* dq, float* d_shat, int B, vml_dims_t d, void* stream) {
+  return content_attn_bwd(c_hat, d_cc, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, d_chat, dq, d_shat, B,
+                          d, ST(stream));
+}
+VML_API int vml_gbar_bwd(const float* fm, const float* fs, const float* ab, const float* d_bu, const float* d_gbar_cu, const float* d_mu,
+                         vml_cells_t cells, float* d_ab, float* d_fm, float* d_fs, int B, vml_dims_t d, void* stream) {
+  return gbar_bwd(fm, fs, ab, d_bu, d_gbar_cu, d_mu, cells, d_ab, d_fm, d_fs, B, d, ST(stream));
+}
+VML_API int vml_softmax_bwd(const float* P, const float* dP, const uint8_t* colmask, float* dS, int batch, int R, int W, float scale,
+                            void* stream) {
+  return softmax_bwd(P, dP, colmask, dS, batch, R, W, scale, ST(stream));
+}
+VML_API int vml_gate_bwd(const float* dG, const float* fb, const float* U, const uint8_t* length_mask, float* d_fb, float* d_Aq,
+                         float* tmp, int B, vml_dims_t d, void* stream) {
+  return gate_bwd(dG, fb, U, length_mask, d_fb, d_Aq, tmp, B, d, ST(stream));
+}
+VML_API int vml_mask_rows(const float* X, const uint8_t* mask, float* Y, int64_t rows, int D, int accumulate, void* stream) {
+  return mask_rows(X, mask, Y, rows, D, accumulate, ST(stream));
+}
+VML_API int vml_span_pool_bwd(const float* d_fc, const float* d_fm, const float* d_fb, const float* fv, const float* fs,
+                              vml_cells_t cells, float* d_fv, float* d_fs, int B, vml_dims_t d, void* stream) {
+  return span_pool_bwd(d_fc, d_fm, d_fb, fv, fs, cells, d_fv, d_fs, B, d, ST(stream));
+}
+VML_API int vml_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                          int step, float grad_scale, void* stream) {
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, ST(stream));
+}
+VML_API int vml_lstm_train_fwd(const float* gin, const float* whh_t, const int32_t* qlen, float* y, float* fs, float* acts, int B,
+                               int Nq, int H, void* stream) {
+  return lstm_train_fwd(gin, whh_t, qlen, y, fs, acts, B, Nq, H, ST(stream));
+}
+VML_API int vml_lstm_train_bwd(const float* dy, const float* dfs, const float* whh, const float* acts, const int32_t* qlen, float* dgin,
+                               float* dgin_rec, int B, int Nq, int H, void* stream) {
+  return lstm_train_bwd(dy, dfs, whh, acts, qlen, dgin, dgin_rec, B, Nq, H, ST(stream));
 }
 
 }  // extern "C"

@@ -57,7 +57,8 @@ template <bool PRECISE>
 __global__ void __launch_bounds__(BMM_THREADS)
 boundary_gate_mma_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
                          const float* __restrict__ fs, const float* __restrict__ fb, const uint8_t* __restrict__ qmask,
-                         const uint8_t* __restrict__ lmask, float* __restrict__ G, int L, int Nq, int D) {
+                         const uint8_t* __restrict__ lmask, float* __restrict__ G, float* __restrict__ prob_out,
+                         float* __restrict__ u_out, int L, int Nq, int D) {
   extern __shared__ __align__(16) float sg[];
   const int DS = D + 4;
   float* Ks = sg;                                     // [Nq][DS]  kbt
@@ -128,6 +129,7 @@ boundary_gate_mma_kernel(const float* __restrict__ qproj, int ld, int off_kbt, i
       const float mx = warp_max(sv);
       const float ex = lane < Nq ? expf(sv - mx) : 0.f;
       prob[row][lane] = ex / warp_sum(ex);
+      if (prob_out && lane < Nq && i0 + row < L) prob_out[((size_t)b * L + i0 + row) * Nq + lane] = prob[row][lane];   // saved for backward
     }
   }
   __syncthreads();
@@ -162,11 +164,13 @@ boundary_gate_mma_kernel(const float* __restrict__ qproj, int ld, int off_kbt, i
           const float2 x = *reinterpret_cast<const float2*>(Xs + g * DS + col);
           *reinterpret_cast<float2*>(G + ((size_t)b * L + rA) * D + col) =
               make_float2(x.x * (acc[n][0] * lmA + s2.x), x.y * (acc[n][1] * lmA + s2.y));
+          if (u_out) *reinterpret_cast<float2*>(u_out + ((size_t)b * L + rA) * D + col) = make_float2(acc[n][0] * lmA + s2.x, acc[n][1] * lmA + s2.y);
         }
         if (vB) {
           const float2 x = *reinterpret_cast<const float2*>(Xs + (g + 8) * DS + col);
           *reinterpret_cast<float2*>(G + ((size_t)b * L + rB) * D + col) =
               make_float2(x.x * (acc[n][2] * lmB + s2.x), x.y * (acc[n][3] * lmB + s2.y));
+          if (u_out) *reinterpret_cast<float2*>(u_out + ((size_t)b * L + rB) * D + col) = make_float2(acc[n][2] * lmB + s2.x, acc[n][3] * lmB + s2.y);
         }
       }
     }
@@ -414,7 +418,7 @@ static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, fl
   while (JR > 8 && need(JR) > 100 * 1024) JR -= 8;      // <= 100 KB: two CTAs per SM
   const size_t smem = need(JR);
   VML_CHECK_ARG(smem <= 227 * 1024);
-  VML_CUDA(cudaFuncSetAttribute(boundary_rows_mma_kernel<PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VML_CUDA(ensure_dyn_smem((const void*)(boundary_rows_mma_kernel<PRECISE>), (size_t)((int)smem)));
   dim3 grid(ceil_div(d.L, BMM_ROWS), B);
   boundary_rows_mma_kernel<PRECISE><<<grid, BMM_THREADS, smem, st>>>(G, fb, lmask, bu, ab, d.L, d.D, JR);
   return VML_OK;
@@ -430,7 +434,8 @@ static int launch_stream(const float* ab, const float* fs, const void* fm, vml_c
 
 int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                   const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
-                  float* g_scratch, float* ab_scratch, float* bu, void* fbar, int B, vml_dims_t d, int prec, cudaStream_t st) {
+                  float* g_scratch, float* ab_scratch, float* bu, void* fbar, float* prob_out, float* u_out, int B, vml_dims_t d,
+                  int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.Nq <= BMM_MAXQ && d.D % 64 == 0 && d.D <= 64 * BMM_MAXD64 && d.L <= 248 && ld % 4 == 0 && off_kbt % 4 == 0);
   VML_CHECK_ARG(g_scratch != nullptr && ab_scratch != nullptr);
   static bool reg = (register_kernel("boundary_gate_mma_kernel"), register_kernel("boundary_rows_mma_kernel"),
@@ -438,11 +443,11 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   dim3 grid(ceil_div(d.L, BMM_ROWS), B);
   const size_t smem_g = sizeof(float) * (size_t)(2 * d.Nq + BMM_ROWS) * (d.D + 4);
   if (prec == VML_FP32) {
-    VML_CUDA(cudaFuncSetAttribute(boundary_gate_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-    boundary_gate_mma_kernel<true><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
+    VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_mma_kernel<true>), (size_t)((int)smem_g)));
+    boundary_gate_mma_kernel<true><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, d.L, d.Nq, d.D);
   } else {
-    VML_CUDA(cudaFuncSetAttribute(boundary_gate_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-    boundary_gate_mma_kernel<false><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, d.L, d.Nq, d.D);
+    VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_mma_kernel<false>), (size_t)((int)smem_g)));
+    boundary_gate_mma_kernel<false><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, d.L, d.Nq, d.D);
   }
   int rc = prec == VML_FP32 ? launch_rows<true>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st)
                             : launch_rows<false>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st);

@@ -14,6 +14,10 @@ using bf16 = __nv_bfloat16;
 void set_error(const char* fmt, ...);
 void register_kernel(const char* name);
 void count_launches(int n);
+// Raise (never lower) a kernel's opt-in dynamic shared-memory limit.  A captured CUDA-graph node keeps
+// the launch's own size but tools that re-launch graph nodes (ncu) use the CURRENT function attribute,
+// so a later, smaller launch of the same kernel must not shrink it.
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
 
 #define VML_CHECK_ARG(cond)                                                        \
   do {                                                                             \

@@ -339,7 +339,7 @@ template <int NQP>
 static int launch_content_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, const float* bias, const float* qproj,
                              int ld, int off_what, int off_ktil, int off_beta, const float* s_hat, int s_ld,
                              const uint8_t* qmask, vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, cudaStream_t st) {
-  VML_CUDA(cudaFuncSetAttribute(content_tc_kernel<NQP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtCfg<NQP>::SMEM));
+  VML_CUDA(ensure_dyn_smem((const void*)(content_tc_kernel<NQP>), (size_t)(CtCfg<NQP>::SMEM)));
   content_tc_kernel<NQP><<<grid, UG_THREADS, CtCfg<NQP>::SMEM, st>>>(tmA, tmB, d.D, bias, qproj, ld, off_what, off_ktil, off_beta,
                                                                     s_hat, s_ld, qmask, cells.code, cells.n_cells, d.Nq, B,
                                                                     (bf16*)cc_hat);

@@ -243,10 +243,10 @@ int gemm_res(const void* A, const void* W, const float* bias, const void* R1, co
   const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / GR_BN);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   if (R2) {
-    VML_CUDA(cudaFuncSetAttribute(gemm_res_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM));
+    VML_CUDA(ensure_dyn_smem((const void*)(gemm_res_kernel<true>), (size_t)(GR_SMEM)));
     gemm_res_kernel<true><<<grid, UG_GEMM_THREADS, GR_SMEM, st>>>(tmA, tmB, tmR1, tmR2, tmOut, tmSide, M, N, K, m_dev, m_scale, bias);
   } else {
-    VML_CUDA(cudaFuncSetAttribute(gemm_res_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM));
+    VML_CUDA(ensure_dyn_smem((const void*)(gemm_res_kernel<false>), (size_t)(GR_SMEM)));
     gemm_res_kernel<false><<<grid, UG_GEMM_THREADS, GR_SMEM, st>>>(tmA, tmB, tmR1, tmR2, tmOut, tmSide, M, N, K, m_dev, m_scale, bias);
   }
   VML_LAUNCHED(1);

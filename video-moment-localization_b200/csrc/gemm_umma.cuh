@@ -183,7 +183,7 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    VML_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi>), (size_t)(Cfg::SMEM_BYTES)));
     attr_done = true;
   }
   const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);

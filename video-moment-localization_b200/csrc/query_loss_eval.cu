@@ -346,7 +346,7 @@ int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float*
   const size_t smem = sizeof(float) * ((size_t)H * 4 * UH + 2 * (size_t)H * LSTM_CL + (size_t)LSTM_CL * LSTM_CL * 4 * UH +
                                        (size_t)Nq * LSTM_CL * UH);
   VML_CHECK_ARG(smem <= 227 * 1024);
-  VML_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VML_CUDA(ensure_dyn_smem((const void*)(lstm_cluster_kernel), (size_t)((int)smem)));
   const int clusters = 2 * ceil_div(B, LSTM_CL);
   lstm_cluster_kernel<<<clusters * LSTM_CL, H, smem, st>>>(gin, whh_t, qlen, y, (bf16*)y16, fs, (bf16*)fs16, B, Nq, H);
   VML_LAUNCHED(1);
@@ -563,7 +563,7 @@ int score_topk_recall(const float* pm, const float* ps, const float* pe, const u
   VML_CHECK_ARG(B > 0 && L > 0 && k >= 1 && k <= 8 && nms_den > 0 && (size_t)L * L * 4 <= 200 * 1024);
   static bool reg = (register_kernel("score_topk_kernel"), true); (void)reg;
   const size_t smem = sizeof(float) * L * L;
-  VML_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VML_CUDA(ensure_dyn_smem((const void*)(score_topk_kernel), (size_t)((int)smem)));
   score_topk_kernel<<<B, 256, smem, st>>>(pm, ps, pe, mmask, sm, L, k, nms_num, nms_den, top_idx, top_score, top_iou,
                                           (unsigned long long*)counts, (unsigned long long*)counts2, group > 0 ? group : B);
   VML_LAUNCHED(1);

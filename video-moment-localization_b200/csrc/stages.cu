@@ -370,11 +370,11 @@ int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc,
   VML_CHECK_ARG((int64_t)dslice * ceil_div(d.T, 16) <= 8 * threads);     // scan work items per thread
   dim3 grid(B, d.D / dslice);
   if (prec == VML_BF16) {
-    VML_CUDA(cudaFuncSetAttribute(span_pool_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VML_CUDA(ensure_dyn_smem((const void*)(span_pool_kernel<bf16>), (size_t)((int)smem)));
     span_pool_kernel<bf16><<<grid, threads, smem, st>>>((const bf16*)fv, fs, cells.code, cells.row_start, (bf16*)fc,
                                                     (bf16*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
   } else {
-    VML_CUDA(cudaFuncSetAttribute(span_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VML_CUDA(ensure_dyn_smem((const void*)(span_pool_kernel<float>), (size_t)((int)smem)));
     span_pool_kernel<float><<<grid, threads, smem, st>>>((const float*)fv, fs, cells.code, cells.row_start, (float*)fc,
                                                      (float*)fm, fb, d.T, d.L, d.C, d.D, dslice, cells.capacity);
   }
@@ -525,7 +525,7 @@ static int launch_content_attention(const void* c_hat, const float* qproj, int l
                                     vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, cudaStream_t st) {
   constexpr int DL = DPL * 32;
   const size_t smem = sizeof(float) * ((size_t)d.Nq * (DL + 1) + (size_t)d.Nq * DL + DL + 64 + 8 * 4 * DL + 8 * 4 * 32);
-  VML_CUDA(cudaFuncSetAttribute(content_attention_kernel<ActT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VML_CUDA(ensure_dyn_smem((const void*)(content_attention_kernel<ActT, DPL>), (size_t)((int)smem)));
   const int vmax = d.L * (d.L + 1) / 2;
   int chunks = ceil_div(vmax, 8 * 4);             // ~4 cells per warp
   while ((int64_t)chunks * B > (int64_t)kNumSMs * 16 && chunks > 1) chunks = (chunks + 1) / 2;

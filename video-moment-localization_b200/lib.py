@@ -44,6 +44,8 @@ _SIGS = {
     "vml_pack_cells": [_P, _P, Cells, _I, _I, _I, _I, _P],
     "vml_cast_pad_bf16": [_P, _P, _I64, _I, _I, _P],
     "vml_ingest": [_P] * 15 + [_I, Dims, _I, _I, _I, _P],
+    "vml_gemm_strided": [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, C.c_float, _I, _I,
+                         _P, _I, _P, _I, _P],
     "vml_linear": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "vml_clip_projection": [_P, _P, _P, _P, _P, _P, _I, Dims, _I, _I, _P],
     "vml_lstm_layer": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
@@ -53,7 +55,20 @@ _SIGS = {
     "vml_content_attention": [_P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _I, _P],
     "vml_content_in_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _P],
     "vml_content_out": [_P, _P, _P, _P, _P, _P, _P, _P, Cells, _P, Dims, _I, _P],
-    "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_colsum": [_P, _I64, _I64, _P, _I64, _I, _I, _I, _P, _I, C.c_float, _P],
+    "vml_localize_bwd": [_P] * 12 + [Cells, _P, _P, _P, _P, _I, Dims, _P],
+    "vml_pair_bwd": [_P, _I, _P, Cells, _P, _I, Dims, _P],
+    "vml_cu_tail_bwd": [_P, _P, _I, Cells, _P, _P, Dims, _P],
+    "vml_content_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _P, _P, _I, Dims, _P],
+    "vml_gbar_bwd": [_P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _I, Dims, _P],
+    "vml_softmax_bwd": [_P, _P, _P, _P, _I, _I, _I, C.c_float, _P],
+    "vml_gate_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, Dims, _P],
+    "vml_mask_rows": [_P, _P, _P, _I64, _I, _I, _P],
+    "vml_span_pool_bwd": [_P, _P, _P, _P, _P, Cells, _P, _P, _I, Dims, _P],
+    "vml_adam_step": [_P, _P, _P, _P, _I64, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _P],
+    "vml_lstm_train_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vml_lstm_train_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "vml_moment_pair": [_P, Cells, _P, Dims, _I, _P],
     "vml_moment_operand": [_P, _P, Cells, _P, Dims, _I, _P],
     "vml_moment_out": [_P, _P, _P, _P, Cells, _P, Dims, _I, _P],

@@ -1,0 +1,57 @@
+"""Fused Adam over one flat fp32 buffer (drop-in for ``torch.optim.Adam(model.parameters(), lr)``, main.py:83).
+
+Parameters are re-homed as views into a single contiguous buffer at construction, so that a step is ONE
+``vml_adam_step`` launch (plus one gradient flatten) and a data-parallel gradient all-reduce is ONE NCCL call
+on ``flat_grad``.  Defaults are torch.optim.Adam's (betas 0.9/0.999, eps 1e-8, no weight decay, no amsgrad)."""
+from __future__ import annotations
+
+import torch
+
+from . import lib as L_
+from .lib import call, ptr, stream_ptr
+
+
+class FusedAdam:
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params = [p for p in params]
+        if not self.params or not all(p.is_cuda and p.dtype == torch.float32 for p in self.params):
+            raise L_.VmlError("FusedAdam needs fp32 CUDA parameters; there is no CPU path")
+        L_.load()
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        o = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[o:o + k].copy_(p.reshape(-1))
+                p.data = self.flat[o:o + k].view(p.shape)            # the parameter now lives inside the flat buffer
+                o += k
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        """Copy the per-parameter .grad tensors into ``flat_grad`` (zeros where a parameter has no grad)."""
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is None:
+                self.flat_grad[o:o + k].zero_()
+            else:
+                self.flat_grad[o:o + k].copy_(p.grad.reshape(-1))
+            o += k
+        return self.flat_grad
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0, gathered: bool = False):
+        if not gathered:
+            self.gather_grads()
+        self.t += 1
+        call("vml_adam_step", ptr(self.flat), ptr(self.flat_grad), ptr(self.m), ptr(self.v), self.flat.numel(), self.lr,
+             self.betas[0], self.betas[1], self.eps, self.t, grad_scale, stream_ptr())
+        self.flat.add_(0)     # in-place torch op: bumps the version counter the parameter views share (drives SMIN's packed-weight cache)

@@ -117,6 +117,41 @@ def query_layout(dims: Dims):
     return lay
 
 
+FOLDED_KEYS = ("content_unit.linear_w_hat", "content_unit.attn_layer.W_k", "content_unit.attn_layer.W_q",
+               "boundary_unit.attn_layer.W_k", "boundary_unit.attn_layer.W_q", "content_unit.linear_s_hat")
+
+
+def fold_query_weights(p: Dict[str, torch.Tensor], dims: Dims):
+    """The folded query projection (see ``pack_weights``) as a differentiable function of the reference-named
+    ``smis.*`` parameters: returns (qw [ld, D], qb [ld]) in the dtype of ``p``.  The training path back-propagates
+    d qw / d qb through this function to obtain the gradients of the twelve folded parameters per layer."""
+    D, dl, layers = dims.D, dims.dl, dims.layers
+    lay = query_layout(dims)
+    any_t = next(iter(p.values()))
+    rows_w, rows_b = [], []
+    s_w, s_b = [], []
+    for k in range(layers):
+        cu, bu = f"smis.{k}.content_unit.", f"smis.{k}.boundary_unit.attn_layer."
+        Ww, bw = p[cu + "linear_w_hat.weight"], p[cu + "linear_w_hat.bias"]
+        Wk, bk = p[cu + "attn_layer.W_k.weight"], p[cu + "attn_layer.W_k.bias"]
+        Wq, bq = p[cu + "attn_layer.W_q.weight"], p[cu + "attn_layer.W_q.bias"]
+        WK, bK = p[bu + "W_k.weight"], p[bu + "W_k.bias"]
+        WQ, bQ = p[bu + "W_q.weight"], p[bu + "W_q.bias"]
+        kc_w, kc_b = Wk @ Ww, Wk @ bw + bk                    # kc = fw.kc_w^T + kc_b
+        pad_w, pad_b = any_t.new_zeros(6, D), any_t.new_zeros(6)
+        rows_w += [Ww, Wq.t() @ kc_w, WQ.t() @ WK, (kc_w.t() @ bq)[None], (WK.t() @ bQ)[None], pad_w]
+        rows_b += [bw, Wq.t() @ kc_b, WQ.t() @ bK, (kc_b @ bq)[None], (bK @ bQ)[None], pad_b]
+        s_w.append(p[cu + "linear_s_hat.weight"])
+        s_b.append(p[cu + "linear_s_hat.bias"])
+    qw = torch.cat(rows_w + s_w, 0)
+    qb = torch.cat(rows_b + s_b, 0)
+    padn = lay["ld"] - qw.shape[0]
+    if padn:
+        qw = torch.cat([qw, any_t.new_zeros(padn, D)], 0)
+        qb = torch.cat([qb, any_t.new_zeros(padn)], 0)
+    return qw, qb
+
+
 def pack_lstm_fragments(w_fwd: torch.Tensor, w_rev: torch.Tensor) -> torch.Tensor:
     """W_hh of both directions ([4H, H], H = 256) -> the bf16 mma.sync B-fragment order consumed by
     ``vml_lstm_layer_tc`` (layout documented in include/vml_b200.h): int32 [2, 4, 8, 32, 32, 4]."""
@@ -181,28 +216,14 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: Dims, prec: int, device) -> 
                              f32(sd[f"{ls}weight_hh_l{layer}_reverse"]).t().contiguous()], 0)
         pk[f"lstm_wih{layer}"] = gemm_weight(wih, pk["q_kpad"] if layer == 0 else None)
         pk[f"lstm_b{layer}"], pk[f"lstm_whht{layer}"] = bias.contiguous(), whh_t.contiguous()
+        pk[f"lstm_whh{layer}"] = torch.stack([f32(sd[f"{ls}weight_hh_l{layer}"]), f32(sd[f"{ls}weight_hh_l{layer}_reverse"])], 0).contiguous()
         if prec == L_.BF16 and H == 256:
             pk[f"lstm_frag{layer}"] = pack_lstm_fragments(f32(sd[f"{ls}weight_hh_l{layer}"]), f32(sd[f"{ls}weight_hh_l{layer}_reverse"]))
 
     lay = query_layout(dims)
-    qw = torch.zeros(lay["ld"], D, device=device, dtype=torch.float64)
-    qb = torch.zeros(lay["ld"], device=device, dtype=torch.float64)
+    qw, qb = fold_query_weights({k: f64(v) for k, v in sd.items() if k.startswith("smis.")}, dims)
     for k in range(layers):
-        cu, bu, mu = f"smis.{k}.content_unit.", f"smis.{k}.boundary_unit.attn_layer.", f"smis.{k}.moment_unit."
-        Ww, bw = f64(sd[cu + "linear_w_hat.weight"]), f64(sd[cu + "linear_w_hat.bias"])
-        Wk, bk = f64(sd[cu + "attn_layer.W_k.weight"]), f64(sd[cu + "attn_layer.W_k.bias"])
-        Wq, bq = f64(sd[cu + "attn_layer.W_q.weight"]), f64(sd[cu + "attn_layer.W_q.bias"])
-        WK, bK = f64(sd[bu + "W_k.weight"]), f64(sd[bu + "W_k.bias"])
-        WQ, bQ = f64(sd[bu + "W_q.weight"]), f64(sd[bu + "W_q.bias"])
-        kc_w, kc_b = Wk @ Ww, Wk @ bw + bk                    # kc = fw.kc_w^T + kc_b
-        o = k * lay["blk"]
-        qw[o: o + dl], qb[o: o + dl] = Ww, bw                                        # w_hat
-        qw[o + dl: o + 2 * dl], qb[o + dl: o + 2 * dl] = Wq.t() @ kc_w, Wq.t() @ kc_b    # ktil
-        qw[o + 2 * dl: o + 2 * dl + D], qb[o + 2 * dl: o + 2 * dl + D] = WQ.t() @ WK, WQ.t() @ bK   # kbt
-        qw[o + 2 * dl + D], qb[o + 2 * dl + D] = kc_w.t() @ bq, kc_b @ bq            # beta
-        qw[o + 2 * dl + D + 1], qb[o + 2 * dl + D + 1] = WK.t() @ bQ, bK @ bQ        # beta_b
-        so = lay["s0"] + k * dl
-        qw[so: so + dl], qb[so: so + dl] = f64(sd[cu + "linear_s_hat.weight"]), f64(sd[cu + "linear_s_hat.bias"])
+        cu, mu = f"smis.{k}.content_unit.", f"smis.{k}.moment_unit."
         pk[f"chat_b{k}"], pk[f"cout_b{k}"] = f32(sd[cu + "linear_c_hat.bias"]), f32(sd[cu + "linear_c.bias"])
         pk[f"chat_w{k}"] = gemm_weight(f32(sd[cu + "linear_c_hat.weight"]))
         pk[f"cout_w{k}"] = gemm_weight(f32(sd[cu + "linear_c.weight"]))
@@ -408,7 +429,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         o = k * lay["blk"]
         # a7 boundary unit (main)
         call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
-             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar), B, dims, prec, st)
+             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar), None, None, B, dims, prec, st)
         mark("boundary_unit")
         ev_bu = None
         if two_chains:
@@ -509,6 +530,16 @@ class SMIN(nn.Module):
         dev = video_features.device
         if video_features.shape[0] >= 32768:
             raise ValueError("batch size must be < 32768")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step (main.py:136-150): fp32 forward that saves its activations + hand-written backward
+            from .training import SminTrainFunction
+            ws = self._ws.setdefault(str(dev), Workspace(dev))
+            with torch.no_grad():
+                inp = smin_ingest(self._dims, L_.FP32, ws, video_features, video_mask, query_features, query_mask, length_mask,
+                                  moment_mask)
+                inp["qlen"] = inp["qlen"].clone()          # the tape outlives the workspace's next use
+            names = [n for n, _ in self.named_parameters()]
+            return SminTrainFunction.apply(self, inp, names, *[p for _, p in self.named_parameters()])
         with torch.no_grad():
             pk = self._weights(dev, prec)
             ws = self._ws.setdefault(str(dev), Workspace(dev))
