@@ -194,7 +194,7 @@ def main():
 
     model = SMIN(*cfg.ctor_args(), device=dev, precision=args.precision)
     model.load_state_dict(init_params(cfg, 43))
-    model = model.to(dev)
+    model = model.to(dev).eval()
 
     # rotating set of resident batches larger than L2 (timing rule: inputs > L2)
     keys = synth.MODEL_INPUT_KEYS + ("sm",)

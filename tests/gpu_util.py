@@ -21,7 +21,7 @@ def to_dev(batch, dev="cuda"):
 def model_for(cfg, precision, params=None):
     m = SMIN(*cfg.ctor_args(), device=torch.device("cuda"), precision=precision)
     m.load_state_dict(params if params is not None else init_params(cfg, 43), strict=True)
-    return m.to("cuda")
+    return m.to("cuda").eval()
 
 
 def unpack(packed, cells, B, L, inner, prec):

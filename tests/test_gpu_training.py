@@ -41,7 +41,7 @@ def test_gemm_strided_matches_torch():
     assert ((C2 - ref2).abs() / ref2.abs().clamp_min(1.0)).max() < 1e-4
 
 
-@pytest.mark.parametrize("name,B,seed", [("tiny", 5, 21), ("tiny_r2", 4, 22)])
+@pytest.mark.parametrize("name,B,seed", [("tiny", 5, 21), ("tiny_r2", 4, 22), ("charadessta", 3, 23), ("activitynet", 2, 24)])
 def test_backward_matches_oracle_autograd(name, B, seed):
     cfg = CONFIGS[name]
     params = init_params(cfg, 43)

@@ -15,7 +15,7 @@ prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 cfg = CONFIGS[name]
 m = SMIN(*cfg.ctor_args(), device=torch.device("cuda"), precision=prec)
 m.load_state_dict(init_params(cfg, 43))
-m = m.cuda()
+m = m.cuda().eval()
 b = {k: v.cuda() for k, v in synth.make_batch(cfg, B, 5).items()}
 for it in range(2):
     out = m(*[b[k] for k in synth.MODEL_INPUT_KEYS], overlap=(it == 1))

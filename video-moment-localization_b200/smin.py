@@ -530,8 +530,10 @@ class SMIN(nn.Module):
         dev = video_features.device
         if video_features.shape[0] >= 32768:
             raise ValueError("batch size must be < 32768")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # training step (main.py:136-150): fp32 forward that saves its activations + hand-written backward
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step (model.train() + autograd recording, main.py:136-150): fp32 forward that saves its
+            # activations + hand-written backward.  model.eval() (main.py:168,194) always takes the inference path,
+            # also when the caller forgot torch.no_grad() as the reference's eval_epoch does.
             from .training import SminTrainFunction
             ws = self._ws.setdefault(str(dev), Workspace(dev))
             with torch.no_grad():
