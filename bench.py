@@ -99,8 +99,11 @@ def stage_work(cfg, B, n_cells, prec_bytes):
     w["clip_projection"] = ("tensor", 2.0 * B * T * d0 * D)
     w["span_pool_fuse"] = ("hbm", a * (B * T * D + n_cells * C * D + n_cells * D) + 4 * (B * D + B * L * D))
     w["content_in_gemm"] = ("tensor", 2.0 * n_cells * C * D * dl)
-    w["content_attention"] = ("hbm", 2 * a * n_cells * C * dl)
-    w["content_out_gemm"] = ("tensor", 2.0 * n_cells * C * dl * D)
+    # whole content unit in one kernel: fc in, cu out (not for the last layer), fbar in, mean_c cu out
+    w["content_unit"] = ("hbm", a * (n_cells * C * D * (2.0 - 1.0 / cfg.layers) + 2 * n_cells * D))
+    # two-kernel version (--split-content): front reads fc and writes cc_hat; the tail is byte-bound (K = dl)
+    w["content_attention"] = ("hbm", a * (n_cells * C * D + n_cells * C * dl))
+    w["content_out_gemm"] = ("hbm", a * (2 * n_cells * C * D + 2 * n_cells * D + n_cells * C * dl))
     # fast mode: only the bu_i*bu_j half is built here (the mean_c cu half comes from the content-out epilogue)
     w["moment_operand"] = ("hbm", a * n_cells * D + 4 * B * L * D) if a == 2 and C == 4 else ("hbm", a * (n_cells * C * D + n_cells * 2 * D))
     w["moment_out_gemm"] = ("tensor", 4.0 * n_cells * D * D)
@@ -158,6 +161,7 @@ def main():
     ap.add_argument("--slots", type=int, default=2, help="batches in flight (ScoringPipeline)")
     ap.add_argument("--coalesce", type=int, default=3, help="submitted batches scored per pass (ScoringPipeline)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--split-content", action="store_true", help="content unit as two kernels (A/B against vml_content_unit)")
     args = ap.parse_args()
 
     import vml_b200  # noqa: F401
@@ -208,11 +212,12 @@ def main():
     n_cells = [int(b["moment_mask"].sum().item()) for b in host]
 
     acc = RecallAccumulator(dev)
-    pipe = ScoringPipeline(model, slots=args.slots, coalesce=args.coalesce, use_graph=not args.no_graph)
+    pipe = ScoringPipeline(model, slots=args.slots, coalesce=args.coalesce, use_graph=not args.no_graph,
+                           split_content=args.split_content)
 
     def step(b, mark=None):
         """Serial eager step through the drop-in module API (instrumented pass only)."""
-        pm, ps, pe, pa = model(*[b[k] for k in synth.MODEL_INPUT_KEYS], mark=mark)
+        pm, ps, pe, pa = model(*[b[k] for k in synth.MODEL_INPUT_KEYS], mark=mark, split_content=args.split_content)
         acc.update(pm, ps, pe, b["moment_mask"], b["sm"])
         if mark:
             mark("eval_topk_recall")
@@ -308,7 +313,8 @@ def main():
     ev_out = [torch.empty(PB, 5, device=dev, dtype=torch.int32), torch.empty(PB, 5, device=dev),
               torch.empty(PB, 5, device=dev), torch.zeros(2, 4, device=dev, dtype=torch.int64)]
     lib.set_recorder(rec)
-    keep_out = model(*[b0[k] for k in synth.MODEL_INPUT_KEYS], mark=lambda name: marks.append((name, len(rec))))
+    keep_out = model(*[b0[k] for k in synth.MODEL_INPUT_KEYS], mark=lambda name: marks.append((name, len(rec))),
+                     split_content=args.split_content)
     lib.call("vml_score_topk_recall", keep_out[0].data_ptr(), keep_out[1].data_ptr(), keep_out[2].data_ptr(),
              b0["moment_mask"].view(torch.uint8).data_ptr(), b0["sm"].data_ptr(), PB, cfg.L, 5, 1, 1, ev_out[0].data_ptr(),
              ev_out[1].data_ptr(), ev_out[2].data_ptr(), ev_out[3].data_ptr(), None, 0, lib.stream_ptr())

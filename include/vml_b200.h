@@ -171,6 +171,20 @@ VML_API int vml_content_in_attention(const void* fc, const void* W, const float*
                                      const uint8_t* query_mask, vml_cells_t cells, void* cc_hat, int B,
                                      vml_dims_t d, void* stream);
 
+/* The WHOLE unit in one kernel (VML_BF16, dl = 128, C = 4, D % 128 == 0, D <= 512, Nq <= 31; query with
+ * vml_content_unit_supported): a tile's 128 (cell, clip) rows of fc stay resident in shared memory from the
+ * c_hat contraction to the residual add, so a layer reads fc once and writes cu once:
+ *   cu = ContentUnit(fc) = cc_hat.Wc^T + bc + fc + fbar   (models.py:242-276; fbar = sigmoid(fm*fs)*fm per cell,
+ *   see vml_boundary_unit),  mu_operand[n, D:2D] = mean_c cu (models.py:297).
+ * store_cu = 0 skips the cu store (last SMI layer: only mean_c cu is consumed downstream; cu may alias fc).
+ * fc, cu bf16 [cap*4, D]; W_chat bf16 [128, D]; Wc bf16 [D, 128]; fbar bf16 [cap, D]; mu_operand bf16 [cap, 2D]. */
+VML_API int vml_content_unit(const void* fc, const void* W_chat, const float* b_chat, const float* qproj, int ld,
+                             int off_what, int off_ktil, int off_beta, const float* s_hat, int s_ld,
+                             const uint8_t* query_mask, vml_cells_t cells, const void* Wc, const float* bc,
+                             const void* fbar, void* cu, void* mu_operand, int B, vml_dims_t d, int store_cu,
+                             void* stream);
+VML_API int vml_content_unit_supported(vml_dims_t d);
+
 /* cu = cc_hat.Wc^T + bc + fc + sigmoid(fm*fs)*fm   (models.py:269-276).  VML_BF16 with fbar and
  * mu_operand non-NULL selects the fused epilogue: the gate term is read from fbar (see
  * vml_boundary_unit) and mean_c cu (models.py:297) is written to mu_operand[n, D:2D]. */

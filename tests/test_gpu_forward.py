@@ -149,3 +149,32 @@ def test_cpu_input_raises():
     batch = synth.make_batch(cfg, 2, 1)
     with pytest.raises(L_.VmlError):
         m(*[batch[k] for k in synth.MODEL_INPUT_KEYS])
+
+
+@pytest.mark.parametrize("name,B,rng", [("charadessta", 48, None), ("charadessta", 24, (1, 12)), ("tacos", 9, None),
+                                        ("tacos", 16, (4, 20)), ("activitynet", 5, None), ("activitynet", 12, (2, 9))])
+def test_one_kernel_content_unit_is_bit_identical_to_split(name, B, rng):
+    """vml_content_unit (fc tile resident in shared memory, one kernel per layer) performs the same arithmetic in the
+    same order as vml_content_in_attention + vml_content_out: every layer's cu / fm / fb and the final scores are
+    bit-identical, over full tiles, ragged last tiles, multi-sample tiles and the skipped last-layer cu store."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    params = init_params(cfg, 43)
+    batch = synth.make_batch(cfg, B, 1300 + B, **({"nfeats_range": rng} if rng else {}))
+    dims = dims_of(cfg)
+    pk = pack_weights(params, dims, L_.BF16, torch.device("cuda"))
+    dev_in = [batch[k].cuda() for k in synth.MODEL_INPUT_KEYS]
+    got, want = {}, {}
+    out_f = smin_forward(pk, dims, L_.BF16, Workspace(torch.device("cuda")), *dev_in, keep=got)
+    out_s = smin_forward(pk, dims, L_.BF16, Workspace(torch.device("cuda")), *dev_in, keep=want, split_content=True)
+    n = int(batch["moment_mask"].sum())
+    for k in range(1, cfg.layers + 1):
+        assert torch.equal(got[f"fc{k}"][:n], want[f"fc{k}"][:n]), (k, "cu")
+        assert torch.equal(got[f"fm{k}"][:n], want[f"fm{k}"][:n]), (k, "fm")
+        assert torch.equal(got[f"fb{k}"], want[f"fb{k}"]), (k, "fb")
+    # production path (no `keep`): last layer's cu store skipped, two-stream overlap
+    model = model_for(cfg, "bf16", params)
+    prod = model(*dev_in)
+    prod_split = model(*dev_in, split_content=True)
+    for a, b_, c in zip(prod, prod_split, out_s):
+        assert torch.equal(a, b_) and torch.equal(a, c)

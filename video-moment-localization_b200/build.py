@@ -23,7 +23,7 @@ OBJ_DIR = os.path.join(ROOT, "build", "vml_b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("VML_EXTRA_CFLAGS", "").split()
 
 
 def sources():

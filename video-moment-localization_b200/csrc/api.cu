@@ -113,6 +113,9 @@ int gemm_res(const void*, const void*, const float*, const void*, const void*, v
              const int32_t*, int, cudaStream_t);
 int content_tc(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
                vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
+int content_unit(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
+                 vml_cells_t, const void*, const float*, const void*, void*, void*, int, int, vml_dims_t, int, cudaStream_t);
+bool content_unit_supported(vml_dims_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
              float*, int, vml_dims_t, int, cudaStream_t);
@@ -239,6 +242,17 @@ VML_API int vml_content_in_attention(const void* fc, const void* W, const float*
                              vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, void* stream) {
   return content_tc(fc, W, bias, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, cc_hat, B, d,
                     ST(stream));
+}
+
+VML_API int vml_content_unit_supported(vml_dims_t d) { return content_unit_supported(d) ? 1 : 0; }
+
+VML_API int vml_content_unit(const void* fc, const void* W_chat, const float* b_chat, const float* qproj, int ld, int off_what,
+                     int off_ktil, int off_beta, const float* s_hat, int s_ld, const uint8_t* query_mask, vml_cells_t cells,
+                     const void* Wc, const float* bc, const void* fbar, void* cu, void* mu_operand, int B, vml_dims_t d,
+                     int store_cu, void* stream) {
+  VML_CHECK_ARG(fc && W_chat && Wc && fbar && cu && mu_operand);
+  return content_unit(fc, W_chat, b_chat, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, Wc, bc, fbar, cu,
+                      (bf16*)mu_operand + d.D, 2 * d.D, B, d, store_cu, ST(stream));
 }
 
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm, const float* fs,

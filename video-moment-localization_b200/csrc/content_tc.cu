@@ -141,7 +141,6 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t row_off = (uint32_t)((r & 7) * 16 + (r >> 3) * 2048);        // Cs: own row, chunk 0
     const uint32_t prow_off = (uint32_t)((r & 7) * 16 + (r >> 3) * (KG * 128)); // Ps: own row, chunk 0
     const float inv_sqrt_dl = 1.0f / sqrtf((float)CT_DL);
-    const float sqrt_dl = sqrtf((float)CT_DL);
     if (at < CT_DL) s_bias[at] = bias[at];
     int acc = 0; uint32_t acc_phase = 0, s_phase = 0, a_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -236,7 +235,7 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float raw = sl == 1 ? sv[NQP + k] : sv[k];
             const int slot = (sl == 1 ? NQP : 0) + k;
             const float mk = mine ? s_mask[slot] : 0.f;
-            float s = (raw + (mine ? s_beta[slot] : 0.f)) / sqrt_dl;
+            float s = (raw + (mine ? s_beta[slot] : 0.f)) * inv_sqrt_dl;
             s = s * mk;
             if (mk == 0.f) s = -1e9f;
             p[k] = s;
@@ -245,10 +244,10 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float den = 0.f;
 #pragma unroll
           for (int k = 0; k < NQP; ++k) {
-            const float ex = k < Nq ? expf(p[k] - mx) : 0.f;
+            const float ex = k < Nq ? __expf(p[k] - mx) : 0.f;
             p[k] = ex; den += ex;
           }
-          const float inv_den = mine ? 1.0f / den : 0.f;
+          const float inv_den = mine ? __fdividef(1.0f, den) : 0.f;
 #pragma unroll
           for (int k = 0; k < NQP; ++k) p[k] = k == Nq ? (mine ? 1.0f : 0.f) : p[k] * inv_den;
           const uint4 zero4 = make_uint4(0, 0, 0, 0);
@@ -276,7 +275,8 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::tc_fence_after();
       }
       // ---- gate G = c_hat * (A + s_hat), Gram of the cell's 4 clips (adjacent lanes) -------------------
-      float gg[4] = {0.f, 0.f, 0.f, 0.f};
+      // (summed as two 64-column halves, the order content_unit.cu's thread pairs use: the kernels stay bit-identical)
+      float gg[4] = {0.f, 0.f, 0.f, 0.f}, gh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < CT_DL; c += 32) {
         float a[32];
@@ -297,8 +297,11 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           g2 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 2), g2);
           g3 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 3), g3);
         }
-        gg[0] += g0; gg[1] += g1; gg[2] += g2; gg[3] += g3;
+        if (c < 64) { gg[0] += g0; gg[1] += g1; gg[2] += g2; gg[3] += g3; }
+        else { gh[0] += g0; gh[1] += g1; gh[2] += g2; gh[3] += g3; }
       }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) gg[m] += gh[m];
       ptx::tc_fence_before();
       // ---- 4x4 clip self-attention (models.py:259-266): softmax over the cell's clips, mix c_hat rows ----
       float am = -INFINITY;
@@ -306,8 +309,8 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int m = 0; m < 4; ++m) { gg[m] = gg[m] * inv_sqrt_dl; am = fmaxf(am, gg[m]); }
       float ad = 0.f;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) { gg[m] = expf(gg[m] - am); ad += gg[m]; }
-      const float inv_ad = 1.0f / ad;
+      for (int m = 0; m < 4; ++m) { gg[m] = __expf(gg[m] - am); ad += gg[m]; }
+      const float inv_ad = __fdividef(1.0f, ad);
 #pragma unroll
       for (int m = 0; m < 4; ++m) gg[m] *= inv_ad;
       uint32_t sib[4];

@@ -1,0 +1,593 @@
+// a5+a6: the WHOLE content unit of one SMI layer as ONE persistent tcgen05 kernel (bf16 fast mode,
+// dl = 128, C = 4, D <= 512):
+//
+//   c_hat = fc.W_c_hat^T + b -> content-word attention -> gate -> CxC clip self-attention -> cc_hat
+//   cu    = cc_hat.W_c^T + b_c + fc + fbar,      side = mean_c cu  (the moment unit's operand half)
+//   reference: ContentUnit.forward models.py:242-276, ContentAttention.forward models.py:207-226, :297
+//
+// The two-kernel version (content_tc.cu + gemm_res.cu) reads the fc tile twice from HBM and round-trips
+// cc_hat; here a tile's 128 (cell, clip) rows of fc stay RESIDENT in shared memory (D/64 TMA boxes of
+// 128 x 64, 128B-swizzled = 128 KB at D = 512) from the first contraction to the residual add, so the
+// layer moves fc exactly once in and once out:
+//   (1) main    c_hat[128 x 128]  = X[128 x D] . W1^T        A = the resident boxes, B = W1 K-blocks (ring)
+//   (2) scores  S[128 x NW]       = c_hat_bf16 . ktil^T      as content_tc.cu
+//   (3) attend  A[128 x 128]      = P[128 x NW] . [w_hat ; s_hat]
+//   (4) tail    Y_nb[128 x 128]   = cc_hat[128 x 128] . W2[nb]^T   for the D/128 column blocks; A = cc_hat
+//               written in place of c_hat (un-swizzled core-matrix layout), B = W2 boxes through the ring
+//   epilogue(4) out = Y + b_c + X + fbar  written IN PLACE into the resident boxes and TMA-stored; fbar is
+//               prefetched into registers, mean_c(out) (4 adjacent lanes) goes straight to global memory.
+// The next tile's boxes are re-loaded as soon as the store of their column block has left shared memory,
+// so its HBM reads and its main loop overlap the tail epilogue of the current tile.
+//
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer for (1) and (4), warps 2..9 row warps: a
+// pair of threads (same TMEM lane, warps w and w + 4) == tile row == (cell, clip), each owning 64 of a row's 128
+// columns in every per-row loop; thread 64 issues (2) and (3); warp 10 issues the TMA stores and waits for them.  The row warps are latency-bound
+// (measured: 24.5 us per tile with 4 row warps at IPC ~0.3), hence two of them per SM scheduler.
+//
+// TMEM columns: [0,128) c_hat accumulator; [128,256) A, later Y (even column blocks); [256,256+NW) S,
+// [256,384) later Y (odd column blocks) -- the aliases are phase-exclusive (Y MMAs are issued only after
+// every attention thread has finished reading S and A; the next tile's S/A only after Y was drained).
+#include "common.cuh"
+#include "gemm_umma.cuh"
+#include "sm100.cuh"
+
+namespace vml {
+
+#ifdef VML_CU_TIMING
+__device__ long long g_cu_dbg[512];
+__device__ __forceinline__ long long cu_now() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CU_T(slot) do { if (issuer && blockIdx.x == 0 && it < 4) g_cu_dbg[it * 48 + (slot)] = cu_now(); } while (0)
+#define CU_TX(slot) do { if (blockIdx.x == 0 && it < 4) g_cu_dbg[it * 48 + (slot)] = cu_now(); } while (0)
+int cu_debug_read(long long* host, int n) { return (int)cudaMemcpyFromSymbol(host, g_cu_dbg, sizeof(long long) * n); }
+#else
+#define CU_T(slot) do { } while (0)
+#define CU_TX(slot) do { } while (0)
+#endif
+
+constexpr int CU_DL = 128, CU_WST = 2, CU_MAXKB = 8;
+constexpr int CU_ROW_WARPS = 8, CU_ROW_THREADS = 32 * CU_ROW_WARPS, CU_THREADS = 64 + CU_ROW_THREADS + 32;   // + store warp
+#define CU_ROW_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
+static_assert(CU_ROW_THREADS == 256, "CU_ROW_BAR names the thread count");
+constexpr int CU_BOX = UG_BM * UG_BK * 2;            // one 128 x 64 bf16 box (16 KB)
+constexpr int CU_CS_BYTES = UG_BM * CU_DL * 2;       // c_hat / cc_hat tile
+constexpr int CU_TMEM_A = 128, CU_TMEM_S = 256, CU_TMEM_Y0 = 128, CU_TMEM_Y1 = 256;
+
+template <int NQP, int GS>
+struct CuCfg {
+  static constexpr int NW = GS * NQP;                // word slots of a GS-sample group
+  static constexpr int KG = NW / 8;
+  static constexpr int KS_BYTES = NW * CU_DL * 2;    // keys,   K-major (rows = word slots), lbo 128, sbo 2048
+  static constexpr int WT_BYTES = NW * CU_DL * 2;    // values, MN-major, lbo 128, sbo KG*128
+  static constexpr int PS_BYTES = UG_BM * NW * 2;    // probabilities, K-major, lbo 128, sbo KG*128
+  static constexpr int U_RAW = KS_BYTES + WT_BYTES + PS_BYTES;
+  static constexpr int U_BYTES = (U_RAW + 1023) / 1024 * 1024;
+  static constexpr int SIDE_FLOATS = 2 * NW + CU_DL + CU_MAXKB * 64;   // beta | mask | b1 | b2
+  static constexpr int X_BYTES = CU_MAXKB * CU_BOX;
+  static constexpr int SMEM = X_BYTES + CU_CS_BYTES + U_BYTES + CU_WST * CU_BOX + SIDE_FLOATS * 4 + 1024 + 256;
+};
+
+__device__ __forceinline__ uint4 cu_pack8(const float* v) {
+  uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return u;
+}
+
+template <int NQP, int GS>
+__global__ void __launch_bounds__(CU_THREADS, 1)
+content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, int D,
+                    const bf16* __restrict__ fbar, bf16* __restrict__ side, int ld_side,
+                    const float* __restrict__ bias1, const float* __restrict__ bias2, const float* __restrict__ qproj, int ld,
+                    int off_what, int off_ktil, int off_beta, const float* __restrict__ s_hat, int s_ld,
+                    const uint8_t* __restrict__ qmask, const int32_t* __restrict__ code, const int32_t* __restrict__ n_cells,
+                    int Nq, int B, int store_cu) {
+  using Cfg = CuCfg<NQP, GS>;
+  constexpr int NW = Cfg::NW, KG = Cfg::KG;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* Xs = smem;                                    // resident fc tile: KB boxes
+  unsigned char* Cs = Xs + Cfg::X_BYTES;                       // c_hat, then cc_hat
+  unsigned char* U = Cs + CU_CS_BYTES;                         // Ks | Wt | Ps: the attention operands
+  unsigned char* Ks = U;
+  unsigned char* Wt = Ks + Cfg::KS_BYTES;
+  unsigned char* Ps = Wt + Cfg::WT_BYTES;
+  unsigned char* Wr = U + Cfg::U_BYTES;                        // weight ring
+  float* s_beta = reinterpret_cast<float*>(Wr + CU_WST * CU_BOX);   // [NW]
+  float* s_mask = s_beta + NW;                                      // [NW]
+  float* s_b1 = s_mask + NW;                                        // [128]
+  float* s_b2 = s_b1 + CU_DL;                                       // [D]
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(s_b2 + CU_MAXKB * 64);
+  uint64_t* xfree = xfull + CU_MAXKB;      // [4] per column block
+  uint64_t* wfull = xfree + 4;
+  uint64_t* wempty = wfull + CU_WST;
+  uint64_t* chat_full = wempty + CU_WST;
+  uint64_t* cc_ready = chat_full + 1;
+  uint64_t* sfull_bar = cc_ready + 1;
+  uint64_t* afull_bar = sfull_bar + 1;
+  uint64_t* yfull = afull_bar + 1;         // [2]
+  uint64_t* yempty = yfull + 2;            // [2]
+  uint64_t* sready = yempty + 2;           // [2] column block finished in shared memory -> store warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sready + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int M = *n_cells * 4;
+  const int num_tiles = (M + UG_BM - 1) / UG_BM;
+  const int KB = D / UG_BK, NB = D / 128;
+  // a CTA walks a contiguous range of tiles: consecutive tiles mostly belong to the same sample(s), whose query
+  // operands then stay staged in shared memory
+  const int tiles_per_cta = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = min((int)blockIdx.x * tiles_per_cta, num_tiles), tile_end = min(tile_begin + tiles_per_cta, num_tiles);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmX); ptx::prefetch_tensormap(&tmW1); ptx::prefetch_tensormap(&tmW2);
+    ptx::prefetch_tensormap(&tmOut);
+    for (int i = 0; i < CU_MAXKB; ++i) ptx::mbar_init(&xfull[i], 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&xfree[i], 1);
+    for (int i = 0; i < CU_WST; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
+    ptx::mbar_init(chat_full, 1);
+    ptx::mbar_init(cc_ready, CU_ROW_THREADS);
+    ptx::mbar_init(sfull_bar, 1);
+    ptx::mbar_init(afull_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&yfull[i], 1); ptx::mbar_init(&yempty[i], CU_ROW_WARPS);
+      ptx::mbar_init(&sready[i], CU_ROW_THREADS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                    // ===================== TMA producer =====================
+      int wst = 0; uint32_t wph = 0;
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const uint32_t ph = it & 1;
+        const int m0 = tile * UG_BM;
+        for (int kb = 0; kb < KB; ++kb) {
+          if ((kb & 1) == 0) ptx::mbar_wait(&xfree[kb >> 1], ph ^ 1);      // previous tile's column block has been stored
+          ptx::mbar_arrive_expect_tx(&xfull[kb], CU_BOX);
+          ptx::tma_load_2d(Xs + kb * CU_BOX, &tmX, &xfull[kb], kb * UG_BK, m0);
+          ptx::mbar_wait(&wempty[wst], wph ^ 1);
+          ptx::mbar_arrive_expect_tx(&wfull[wst], CU_BOX);
+          ptx::tma_load_2d(Wr + wst * CU_BOX, &tmW1, &wfull[wst], kb * UG_BK, 0);
+          if (++wst == CU_WST) { wst = 0; wph ^= 1; }
+        }
+        for (int nb = 0; nb < NB; ++nb) {
+          for (int kh = 0; kh < 2; ++kh) {
+            ptx::mbar_wait(&wempty[wst], wph ^ 1);
+            if (kh == 0) CU_TX(30 + nb);
+            ptx::mbar_arrive_expect_tx(&wfull[wst], CU_BOX);
+            ptx::tma_load_2d(Wr + wst * CU_BOX, &tmW2, &wfull[wst], kh * UG_BK, nb * 128);
+            if (++wst == CU_WST) { wst = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                    // ===================== MMA issuer: (1) and (4) =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(UG_BM, CU_DL);
+      int wst = 0; uint32_t wph = 0;
+      uint32_t yi = 0, it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const uint32_t ph = it & 1;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&xfull[kb], ph);
+          ptx::mbar_wait(&wfull[wst], wph);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(Xs + kb * CU_BOX));
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(Wr + wst * CU_BOX));
+#pragma unroll
+          for (int k = 0; k < UG_BK / 16; ++k)
+            ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          ptx::umma_commit(&wempty[wst]);
+          if (++wst == CU_WST) { wst = 0; wph ^= 1; }
+        }
+        ptx::umma_commit(chat_full);
+        ptx::mbar_wait(cc_ready, ph);                    // cc_hat is in Cs; S and A have been read out of TMEM
+        ptx::tc_fence_after();
+        const uint32_t c0 = ptx::smem_u32(Cs);
+        for (int nb = 0; nb < NB; ++nb, ++yi) {
+          const uint32_t yb = yi & 1;
+          ptx::mbar_wait(&yempty[yb], ((yi >> 1) & 1) ^ 1);
+          CU_TX(18 + 3 * nb);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0);
+          for (int kh = 0; kh < 2; ++kh) {
+            ptx::mbar_wait(&wfull[wst], wph);
+            if (kh == 1) CU_TX(19 + 3 * nb);
+            ptx::tc_fence_after();
+            const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(Wr + wst * CU_BOX));
+#pragma unroll
+            for (int k = 0; k < UG_BK / 16; ++k)
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_nosw(c0 + (uint32_t)((kh * 4 + k) * 256), 128, 2048), bdesc + (uint64_t)(k * 2),
+                             idesc, (kh | k) != 0);
+            ptx::umma_commit(&wempty[wst]);
+            if (++wst == CU_WST) { wst = 0; wph ^= 1; }
+          }
+          ptx::umma_commit(&yfull[yb]);
+          CU_TX(20 + 3 * nb);
+        }
+      }
+    }
+  } else if (warp == 2 + CU_ROW_WARPS) {
+    if (lane == 0) {                                    // ===================== store warp =====================
+      // Waiting for a TMA store to finish READING shared memory takes ~1 us; done here, off the row warps' path.
+      uint32_t yi = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int m0 = tile * UG_BM;
+        for (int nb = 0; nb < NB; ++nb, ++yi) {
+          const uint32_t yb = yi & 1;
+          ptx::mbar_wait(&sready[yb], (yi >> 1) & 1);
+          if (store_cu) {
+            ptx::tma_store_2d(&tmOut, Xs + (2 * nb) * CU_BOX, nb * 128, m0);
+            ptx::tma_store_2d(&tmOut, Xs + (2 * nb + 1) * CU_BOX, nb * 128 + 64, m0);
+            ptx::bulk_commit();
+            if (nb > 0) {                                      // the previous column block has left shared memory
+              ptx::bulk_wait_read<1>();
+              ptx::mbar_arrive(&xfree[nb - 1]);
+            }
+            if (nb == NB - 1) {
+              ptx::bulk_wait_read<0>();
+              ptx::mbar_arrive(&xfree[nb]);
+            }
+          } else {
+            ptx::mbar_arrive(&xfree[nb]);                      // nothing to store: the boxes are free at once
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== row warps (8): thread pair == tile row == (cell, clip) =====================
+    // warp w serves TMEM lane quadrant w % 4; the two warps of a quadrant (grp 0 / 1) split every per-row loop by
+    // columns, so each SM scheduler interleaves two of these latency-bound warps.
+    const int quad = warp % 4;
+    const int grp = (warp - 2) >> 2;                      // column half this thread owns
+    const int r = quad * 32 + lane;                       // row within the tile == TMEM lane
+    const int at = threadIdx.x - 64;                      // 0..255
+    const bool issuer = at == 0;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t row_off = (uint32_t)((r & 7) * 16 + (r >> 3) * 2048);        // Cs: own row, chunk 0
+    const uint32_t prow_off = (uint32_t)((r & 7) * 16 + (r >> 3) * (KG * 128)); // Ps: own row, chunk 0
+    const float inv_sqrt_dl = 1.0f / sqrtf((float)CU_DL);
+    float4* s_gg = reinterpret_cast<float4*>(Ps);         // partial Grams, exchanged between a row's two threads (Ps is dead by then)
+    if (at < CU_DL) s_b1[at] = bias1[at];
+    for (int e = at; e < D; e += CU_ROW_THREADS) s_b2[e] = bias2[e];
+    uint32_t s_phase = 0, a_phase = 0, yi = 0, it = 0;
+    int staged_bg = -1;                                   // sample group whose query operands sit in Ks / Wt / s_beta / s_mask
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const uint32_t ph = it & 1;
+      const int m0 = tile * UG_BM;
+      const int row = m0 + r;
+      const bool valid = row < M;
+      const int b = valid ? (code[row >> 2] >> 16) : -1;
+      const int b_first = code[tile * (UG_BM / 4)] >> 16;
+      const int b_last = code[(min(m0 + UG_BM, M) - 1) >> 2] >> 16;
+      const int ngroups = (b_last - b_first) / GS + 1;
+      for (int g = 0; g < ngroups; ++g) {
+        const int bg = b_first + GS * g;
+        const int sl = b - bg;                              // 0 .. GS-1: this row's sample is in the group
+        const bool mine = valid && sl >= 0 && sl < GS;
+        if (g == 0) CU_T(0);
+        CU_ROW_BAR();                                       // previous users of U / side data / Cs are done
+        // ---- stage the group's query-side operands (a CTA walks consecutive tiles, so the group often repeats) ----
+        if (bg != staged_bg) {
+          for (int e = at; e < NW * (CU_DL / 8); e += CU_ROW_THREADS) {
+            const int w = e / (CU_DL / 8), ch = e % (CU_DL / 8);   // word slot, 8-feature chunk
+            const int s2 = w / NQP, k = w % NQP;
+            const int bb = min(bg + s2, B - 1);
+            float kt[8], wh[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { kt[q] = 0.f; wh[q] = 0.f; }
+            if (k < Nq) {
+              const float* src = qproj + ((size_t)bb * Nq + k) * ld;
+              const float4 k0 = __ldg(reinterpret_cast<const float4*>(src + off_ktil + ch * 8));
+              const float4 k1 = __ldg(reinterpret_cast<const float4*>(src + off_ktil + ch * 8 + 4));
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(src + off_what + ch * 8));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(src + off_what + ch * 8 + 4));
+              kt[0] = k0.x; kt[1] = k0.y; kt[2] = k0.z; kt[3] = k0.w; kt[4] = k1.x; kt[5] = k1.y; kt[6] = k1.z; kt[7] = k1.w;
+              wh[0] = w0.x; wh[1] = w0.y; wh[2] = w0.z; wh[3] = w0.w; wh[4] = w1.x; wh[5] = w1.y; wh[6] = w1.z; wh[7] = w1.w;
+            } else if (k == Nq) {                             // spare slot: s_hat, taken with probability 1
+              const float* sh = s_hat + (size_t)bb * s_ld + ch * 8;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) wh[q] = sh[q];
+            }
+            *reinterpret_cast<uint4*>(Ks + (w & 7) * 16 + (w >> 3) * 2048 + ch * 128) = cu_pack8(kt);
+            *reinterpret_cast<uint4*>(Wt + (w & 7) * 16 + ch * (KG * 128) + (w >> 3) * 128) = cu_pack8(wh);
+          }
+          if (at < NW) {
+            const int s2 = at / NQP, k = at % NQP;
+            const int bb = min(bg + s2, B - 1);
+            s_beta[at] = k < Nq ? qproj[((size_t)bb * Nq + k) * ld + off_beta] : 0.f;
+            s_mask[at] = (k < Nq && qmask[(size_t)bb * Nq + k]) ? 1.f : 0.f;
+          }
+        }
+        staged_bg = bg;
+        if (g == 0) CU_T(1);
+        if (g == 0) {
+          // ---- c_hat row out of TMEM: + bias, round to bf16 (what the unfused path stores), park in Cs ----
+          ptx::mbar_wait(chat_full, ph);
+          CU_T(2);
+          ptx::tc_fence_after();
+          const uint32_t t_addr = tmem_base + lane_base;
+#pragma unroll 1
+          for (int c = grp * 64; c < grp * 64 + 64; c += 32) {
+            float v[32];
+            ptx::tmem_ld32(t_addr + (uint32_t)c, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              float t[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) t[q] = v[e + q] + s_b1[c + e + q];
+              *reinterpret_cast<uint4*>(Cs + row_off + ((c + e) >> 3) * 128) = cu_pack8(t);
+            }
+          }
+        }
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();
+        CU_ROW_BAR();
+        if (g == 0) CU_T(3);
+        if (issuer) {                                          // ---- (2) S = c_hat . ktil^T ----
+          ptx::tc_fence_after();
+          constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(UG_BM, NW);
+          const uint32_t a0 = ptx::smem_u32(Cs), b0 = ptx::smem_u32(Ks);
+#pragma unroll
+          for (int k = 0; k < CU_DL / 16; ++k)
+            ptx::umma_bf16(tmem_base + CU_TMEM_S, ptx::umma_desc_nosw(a0 + k * 256, 128, 2048),
+                           ptx::umma_desc_nosw(b0 + k * 256, 128, 2048), idesc_s, k != 0);
+          ptx::umma_commit(sfull_bar);
+        }
+        if (grp == 0) {
+          ptx::mbar_wait(sfull_bar, s_phase);
+          if (g == 0) CU_T(4);
+          ptx::tc_fence_after();
+          // ---- masked softmax over this row's words (models.py:211-220), P row -> Ps ----------------------
+          float sv[NW];
+#pragma unroll
+          for (int c = 0; c < NW; c += 16) ptx::tmem_ld16(tmem_base + lane_base + CU_TMEM_S + (uint32_t)c, sv + c);
+          ptx::tmem_ld_wait();
+          float p[NQP];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < NQP; ++k) {
+            const float raw = (GS == 2 && sl == 1) ? sv[(GS - 1) * NQP + k] : sv[k];
+            const int slot = ((GS == 2 && sl == 1) ? NQP : 0) + k;
+            const float mk = mine ? s_mask[slot] : 0.f;
+            float s = (raw + (mine ? s_beta[slot] : 0.f)) * inv_sqrt_dl;
+            s = s * mk;
+            if (mk == 0.f) s = -1e9f;
+            p[k] = s;
+            if (k < Nq) mx = fmaxf(mx, s);
+          }
+          float den = 0.f;
+#pragma unroll
+          for (int k = 0; k < NQP; ++k) {
+            const float ex = k < Nq ? __expf(p[k] - mx) : 0.f;
+            p[k] = ex; den += ex;
+          }
+          const float inv_den = mine ? __fdividef(1.0f, den) : 0.f;
+#pragma unroll
+          for (int k = 0; k < NQP; ++k) p[k] = k == Nq ? (mine ? 1.0f : 0.f) : p[k] * inv_den;
+          const uint4 zero4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int kc = 0; kc < NQP / 8; ++kc) {
+            const uint4 pk = cu_pack8(p + kc * 8);
+            if (GS == 2) {
+              *reinterpret_cast<uint4*>(Ps + prow_off + kc * 128) = sl == 0 ? pk : zero4;
+              *reinterpret_cast<uint4*>(Ps + prow_off + (NQP / 8 + kc) * 128) = sl == 1 ? pk : zero4;
+            } else {
+              *reinterpret_cast<uint4*>(Ps + prow_off + kc * 128) = pk;      // rows of other samples carry zeros (inv_den = 0)
+            }
+          }
+          ptx::fence_proxy_async();
+        }
+        s_phase ^= 1;
+        ptx::tc_fence_before();
+        CU_ROW_BAR();
+        if (g == 0) CU_T(5);
+        if (issuer) {                                          // ---- (3) A (+)= P . [w_hat ; s_hat] ----
+          ptx::tc_fence_after();
+          constexpr uint32_t idesc_a = ptx::umma_idesc_bf16_bmn(UG_BM, CU_DL);
+          const uint32_t a0 = ptx::smem_u32(Ps), b0 = ptx::smem_u32(Wt);
+#pragma unroll
+          for (int k = 0; k < NW / 16; ++k)
+            ptx::umma_bf16(tmem_base + CU_TMEM_A, ptx::umma_desc_nosw(a0 + k * 256, 128, KG * 128),
+                           ptx::umma_desc_nosw(b0 + k * 256, 128, KG * 128), idesc_a, (g | k) != 0);
+          ptx::umma_commit(afull_bar);
+        }
+        ptx::mbar_wait(afull_bar, a_phase); a_phase ^= 1;
+        ptx::tc_fence_after();
+      }
+      CU_T(6);
+      // ---- gate G = c_hat * (A + s_hat), Gram of the cell's 4 clips (adjacent lanes); this thread: 64 columns ----
+      float gg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = grp * 64; c < grp * 64 + 64; c += 32) {
+        float a[32];
+        ptx::tmem_ld32(tmem_base + lane_base + CU_TMEM_A + (uint32_t)c, a);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          const f8 ch = unpack8(*reinterpret_cast<const uint4*>(Cs + row_off + ((c + e) >> 3) * 128));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a[e + q] = valid ? ch.v[q] * a[e + q] : 0.f;
+        }
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float gv = a[e];
+          g0 = fmaf(gv, gv, g0);
+          g1 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 1), g1);
+          g2 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 2), g2);
+          g3 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 3), g3);
+        }
+        gg[0] += g0; gg[1] += g1; gg[2] += g2; gg[3] += g3;
+      }
+      ptx::tc_fence_before();
+      s_gg[grp * 128 + r] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      CU_ROW_BAR();
+      {
+        const float4 lo = s_gg[r], hi = s_gg[128 + r];       // (columns 0..63) + (columns 64..127), same order in both threads
+        gg[0] = lo.x + hi.x; gg[1] = lo.y + hi.y; gg[2] = lo.z + hi.z; gg[3] = lo.w + hi.w;
+      }
+      CU_T(7);
+      // ---- 4x4 clip self-attention (models.py:259-266): softmax over the cell's clips, mix c_hat rows ----
+      float am = -INFINITY;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { gg[m] = gg[m] * inv_sqrt_dl; am = fmaxf(am, gg[m]); }
+      float ad = 0.f;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { gg[m] = __expf(gg[m] - am); ad += gg[m]; }
+      const float inv_ad = __fdividef(1.0f, ad);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) gg[m] *= inv_ad;
+      uint32_t sib[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { const int rr = r ^ m; sib[m] = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 2048); }
+      // cc_hat row written IN PLACE of the c_hat row: a row's siblings (r ^ 1..3) are lanes of the same warp, and
+      // every chunk is read by all four before any of them overwrites it (__syncwarp between read and write)
+#pragma unroll 4
+      for (int c = grp * 64; c < grp * 64 + 64; c += 8) {
+        f8 o;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o.v[q] = 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const f8 sv = unpack8(*reinterpret_cast<const uint4*>(Cs + sib[m] + (c >> 3) * 128));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o.v[q] = fmaf(gg[m], sv.v[q], o.v[q]);
+        }
+        if (!valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o.v[q] = 0.f;
+        }
+        __syncwarp();
+        *reinterpret_cast<uint4*>(Cs + row_off + (c >> 3) * 128) = cu_pack8(o.v);
+      }
+      ptx::fence_proxy_async();                              // cc_hat -> visible to the tail MMAs
+      ptx::mbar_arrive(cc_ready);
+      CU_T(8);
+
+      // ---- (4) epilogue: out = Y + b_c + X + fbar in place, side = mean over the cell's 4 clips; this thread: the
+      //      64-column box `grp` of every 128-column block.  fbar comes straight from global memory (L2: the boundary
+      //      unit has just written it), fetched before the wait for the accumulator ------------------------------
+      const bf16* frow = fbar + (size_t)(row >> 2) * D + grp * 64;
+      bf16* srow = side + (size_t)(row >> 2) * ld_side + grp * 64;
+      // fbar is ~1 us away (L2 / HBM): block nb + 1's pieces are requested right after block nb has consumed its own,
+      // and the first half of a block's arithmetic (accumulator + bias + residual) runs while they are in flight
+      uint4 fq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
+      for (int nb = 0; nb < NB; ++nb, ++yi) {
+        const uint32_t yb = yi & 1, yph = (yi >> 1) & 1;
+        unsigned char* xb = Xs + (2 * nb + grp) * CU_BOX;
+        ptx::mbar_wait_relaxed(&yfull[yb], yph);              // TMEM data: ordered by the tcgen05 fence below
+        CU_T(9 + 2 * nb);
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + lane_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0) + (uint32_t)(grp * 64);
+        const float* bcol = s_b2 + nb * 128 + grp * 64;
+        float acc[64];
+        ptx::tmem_ld32(t_addr, acc);
+        ptx::tmem_ld32(t_addr + 32u, acc + 32);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+          const f8 xv = unpack8(*reinterpret_cast<const uint4*>(xb + ptx::sw128_off(r, pc)));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[pc * 8 + q] = (acc[pc * 8 + q] + bcol[pc * 8 + q]) + xv.v[q];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)      // fbar is consumed only from here on (keeps the unpacking below the loop above)
+          asm volatile("" : "+r"(fq[i].x), "+r"(fq[i].y), "+r"(fq[i].z), "+r"(fq[i].w));
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+          const f8 fv = unpack8(fq[pc]);
+          f8 o;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o.v[q] = acc[pc * 8 + q] + fv.v[q];
+          *reinterpret_cast<uint4*>(xb + ptx::sw128_off(r, pc)) = cu_pack8(o.v);      // result in place of the residual
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {                      // mean over the cell's 4 rows (adjacent lanes)
+            float t = o.v[q];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            o.v[q] = t * 0.25f;
+          }
+          if ((lane & 3) == 0 && valid) *reinterpret_cast<uint4*>(srow + nb * 128 + pc * 8) = cu_pack8(o.v);
+        }
+        CU_T(38 + nb);
+        if (nb + 1 < NB) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow + (nb + 1) * 128) + i) : make_uint4(0, 0, 0, 0);
+        }
+        CU_T(34 + nb);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&yempty[yb]);          // accumulator drained
+        ptx::fence_proxy_async();                              // shared-memory writes -> visible to the TMA stores
+        ptx::mbar_arrive(&sready[yb]);                         // the store warp takes it from here; no barrier among the row warps
+        CU_T(10 + 2 * nb);
+      }
+      CU_T(17);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
+}
+
+template <int NQP, int GS>
+static int launch_content_unit(const CUtensorMap* tm, int grid, const bf16* fbar, bf16* side, int ld_side, const float* b1, const float* b2, const float* qproj, int ld,
+                               int off_what, int off_ktil, int off_beta, const float* s_hat, int s_ld, const uint8_t* qmask,
+                               vml_cells_t cells, int B, vml_dims_t d, int store_cu, cudaStream_t st) {
+  using Cfg = CuCfg<NQP, GS>;
+  static_assert(Cfg::SMEM <= 232448, "content_unit_kernel exceeds the 227 KB shared-memory limit");
+  VML_CUDA(ensure_dyn_smem((const void*)(content_unit_kernel<NQP, GS>), (size_t)(Cfg::SMEM)));
+  content_unit_kernel<NQP, GS><<<grid, CU_THREADS, Cfg::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], d.D, fbar, side, ld_side, b1, b2, qproj, ld,
+                                                                    off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells.code,
+                                                                    cells.n_cells, d.Nq, B, store_cu);
+  VML_LAUNCHED(1);
+  return VML_OK;
+}
+
+bool content_unit_supported(vml_dims_t d) {
+  return d.dl == CU_DL && d.C == 4 && d.D % 128 == 0 && d.D <= CU_MAXKB * 64 && d.Nq <= 31;
+}
+
+// fc, cu bf16 [cap*4, D]; W1 bf16 [128, D]; W2 bf16 [D, 128]; fbar bf16 [cap, D]; side bf16 [cap, D] with row
+// stride ld_side (may point into a wider matrix).  store_cu = 0: only the side output is produced (last layer).
+int content_unit(const void* fc, const void* W1, const float* b1, const float* qproj, int ld, int off_what, int off_ktil,
+                 int off_beta, const float* s_hat, int s_ld, const uint8_t* qmask, vml_cells_t cells, const void* W2,
+                 const float* b2, const void* fbar, void* cu, void* side, int ld_side, int B, vml_dims_t d, int store_cu,
+                 cudaStream_t st) {
+  VML_CHECK_ARG(content_unit_supported(d) && ld % 4 == 0 && off_what % 4 == 0 && off_ktil % 4 == 0 && s_ld % 4 == 0 &&
+                ld_side % 8 == 0 && cells.capacity > 0);
+  static bool reg = (register_kernel("content_unit_kernel"), true); (void)reg;
+  CUtensorMap tm[4];
+  const uint64_t M = (uint64_t)cells.capacity * 4, D = (uint64_t)d.D;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tm[0], fc, M, D, D, UG_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm[1], W1, CU_DL, D, D, CU_DL))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm[2], W2, D, CU_DL, CU_DL, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm[3], cu, M, D, D, UG_BM))) return rc;
+  VML_CHECK_ARG((reinterpret_cast<uintptr_t>(fbar) & 15) == 0 && (reinterpret_cast<uintptr_t>(side) & 15) == 0);
+  const int tiles = ceil_div((int)M, UG_BM);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+#define VML_CU(NQP, GS) return launch_content_unit<NQP, GS>(tm, grid, (const bf16*)fbar, (bf16*)side, ld_side, b1, b2, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, B, d, store_cu, st)
+  if (d.Nq + 1 <= 8) VML_CU(8, 2);
+  if (d.Nq + 1 <= 16) VML_CU(16, 2);
+  VML_CU(32, 1);
+#undef VML_CU
+}
+
+}  // namespace vml
+
+#ifdef VML_CU_TIMING
+extern "C" __attribute__((visibility("default"))) int vml_debug_cu_timing(long long* host, int n) { return vml::cu_debug_read(host, n); }
+#endif

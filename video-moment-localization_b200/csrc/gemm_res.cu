@@ -28,16 +28,6 @@ constexpr int GR_R2_BYTES = (UG_BM / 4) * GR_BN * 2;      // two 64-column boxes
 constexpr int GR_RES_BYTES = GR_R1_BYTES + GR_R2_BYTES;
 constexpr int GR_SMEM = GR_STAGES * GR_STAGE_BYTES + 2 * GR_RES_BYTES + 1024 + 256;
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// byte offset of the 16-byte piece (8 bf16) `piece` (0..7) of row r inside a 128B-swizzled 64-column box
-__device__ __forceinline__ uint32_t sw128_off(int r, int piece) { return (uint32_t)(r * 128 + ((piece ^ (r & 7)) << 4)); }
-
 template <bool HAS_R2>
 __global__ void __launch_bounds__(UG_GEMM_THREADS, 1)
 gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -141,7 +131,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * UG_BM, n0 = (tile % tiles_n) * GR_BN;
       if (storer && pending >= 0) {                        // hand the previous tile's slot back to the producer
-        bulk_wait_read0();
+        ptx::bulk_wait_read<0>();
         ptx::mbar_arrive(&rempty_bar[pending]);
         pending = -1;
       }
@@ -160,11 +150,11 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           const int piece = (c + e) >> 3;
-          uint4* px = reinterpret_cast<uint4*>(r1 + sw128_off(r, piece));
+          uint4* px = reinterpret_cast<uint4*>(r1 + ptx::sw128_off(r, piece));
           const f8 xv = unpack8(*px);
           f8 o;
           if (HAS_R2) {
-            const f8 fv = unpack8(*reinterpret_cast<const uint4*>(r2 + sw128_off(r >> 2, piece)));
+            const f8 fv = unpack8(*reinterpret_cast<const uint4*>(r2 + ptx::sw128_off(r >> 2, piece)));
 #pragma unroll
             for (int q = 0; q < 8; ++q) o.v[q] = (v[e + q] + __ldg(bcol + c + e + q)) + xv.v[q] + fv.v[q];
           } else {
@@ -191,7 +181,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pm);
 #pragma unroll
               for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o.v[2 * q], o.v[2 * q + 1]);
-              *reinterpret_cast<uint4*>(r2 + sw128_off(r >> 2, piece)) = pm;
+              *reinterpret_cast<uint4*>(r2 + ptx::sw128_off(r >> 2, piece)) = pm;
             }
           }
         }
@@ -203,19 +193,19 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       asm volatile("bar.sync 1, 256;" ::: "memory");       // all 8 epilogue warps have finished the tile
       if (storer) {
         unsigned char* base = res + rb * GR_RES_BYTES;
-        tma_store_2d(&tmOut, base, n0, m0);
-        tma_store_2d(&tmOut, base + GR_R1_BYTES / 2, n0 + 64, m0);
+        ptx::tma_store_2d(&tmOut, base, n0, m0);
+        ptx::tma_store_2d(&tmOut, base + GR_R1_BYTES / 2, n0 + 64, m0);
         if (HAS_R2) {
-          tma_store_2d(&tmSide, base + GR_R1_BYTES, n0, m0 / 4);
-          tma_store_2d(&tmSide, base + GR_R1_BYTES + GR_R2_BYTES / 2, n0 + 64, m0 / 4);
+          ptx::tma_store_2d(&tmSide, base + GR_R1_BYTES, n0, m0 / 4);
+          ptx::tma_store_2d(&tmSide, base + GR_R1_BYTES + GR_R2_BYTES / 2, n0 + 64, m0 / 4);
         }
-        bulk_commit();
+        ptx::bulk_commit();
         pending = rb;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (++rb == 2) { rb = 0; rphase ^= 1; }
     }
-    if (storer && pending >= 0) bulk_wait_read0();         // shared memory must outlive the last store's reads
+    if (storer && pending >= 0) ptx::bulk_wait_read<0>();         // shared memory must outlive the last store's reads
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -46,6 +46,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Relaxed variant: no acquire ordering against this thread's other memory operations (an acquiring try_wait was
+// measured to hold back until the thread's outstanding global loads had returned).  Use only where the data guarded
+// by the barrier is fenced separately (TMEM results: tcgen05.fence::after_thread_sync).
+__device__ __forceinline__ bool mbar_try_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait_relaxed(bar, parity); ++spin) {
+    if (spin > (1u << 26)) { asm volatile("trap;"); }
+  }
+}
+
 // ---- distributed shared memory -----------------------------------------------------------
 // shared::cta address -> shared::cluster address of the same variable in CTA `rank`
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, int rank) {
@@ -70,6 +88,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// TMA store of a shared-memory tile (bulk async group) and its completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until all but the N most recent bulk groups of this thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// byte offset of the 16-byte piece (8 bf16) `piece` (0..7) of row r inside a 128B-swizzled 64-column box
+__device__ __forceinline__ uint32_t sw128_off(int r, int piece) { return (uint32_t)(r * 128 + ((piece ^ (r & 7)) << 4)); }
 
 // ---- tcgen05 ----------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

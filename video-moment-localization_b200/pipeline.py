@@ -92,8 +92,10 @@ class _Staging:
 
 
 class ScoringPipeline:
-    def __init__(self, model: SMIN, slots: int = 3, coalesce: int = 1, use_graph: bool = True, nms_threshold: float = 1.0):
+    def __init__(self, model: SMIN, slots: int = 3, coalesce: int = 1, use_graph: bool = True, nms_threshold: float = 1.0,
+                 split_content: bool = False):
         L_.load()
+        self.split_content = split_content
         self.model = model
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
@@ -115,7 +117,7 @@ class ScoringPipeline:
 
     # -- one pass on a slot ------------------------------------------------------------------------------
     def _core_and_eval(self, slot: _Slot, pk, inp, group):
-        out = smin_core(pk, self.dims, self.prec, slot.ws, inp)
+        out = smin_core(pk, self.dims, self.prec, slot.ws, inp, split_content=self.split_content)
         slot.step_counts.zero_()
         top = score_topk_recall(out[0], out[1], out[2], inp["mmask"], inp["sm"], 5, self.nms_threshold, self.counts,
                                 step_counts=slot.step_counts, step_group=group)

@@ -328,12 +328,14 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
 
 
 def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace, inp: dict, keep: Optional[dict] = None,
-              mark=None, overlap: bool = True):
+              mark=None, overlap: bool = True, split_content: bool = False):
     """Everything after ``smin_ingest``; reads only library-owned buffers.
     ``overlap``: independent branches run on a second stream (query encoder || clip projection +
     cell compaction; content chain || boundary/moment chain of every SMI layer), joined with
     events -- also valid under CUDA-graph capture.  ``keep`` (tests only) receives intermediates;
-    ``mark(name)`` (bench only) is called after each stage has been enqueued (serial mode)."""
+    ``mark(name)`` (bench only) is called after each stage has been enqueued (serial mode).
+    ``split_content`` (tests / A-B timing): run the content unit as its two-kernel version
+    (``vml_content_in_attention`` + ``vml_content_out``) instead of the single ``vml_content_unit`` kernel."""
     serial = (mark is not None) or (keep is not None) or not overlap
     mark = mark or (lambda name: None)
     B = inp["B"]
@@ -418,6 +420,8 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     mu_op = ws.get("mu_op", (cap, 2 * D), act)
     fused = bf and Cc == 4          # fused epilogues of the tcgen05 path (gate term from the boundary unit, mean_c in-epilogue)
     fbar = ws.get("fbar", (cap, D), act) if fused else None
+    # whole content unit in one kernel (fc tile resident in shared memory: read once, written once per layer)
+    one_kernel_cu = fused and dl == 128 and Nq <= 31 and D % 128 == 0 and D <= 512 and not split_content
     n_dev = cells.n_cells
     two_chains = fused and side is not main
     cside = side if two_chains else main
@@ -438,7 +442,16 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         # a5+a6 content unit (side when overlapping: the next layer's front half only needs this layer's cu)
         with torch.cuda.stream(cside):
             sst = stream_ptr()
-            if fused and dl == 128 and Nq <= 31:
+            if one_kernel_cu:
+                if ev_bu is not None:
+                    cside.wait_event(ev_bu)         # fbar of this layer
+                # the last layer's cu is consumed only through mean_c cu (the moment operand): skip its store
+                store_cu = 1 if (k + 1 < layers or keep is not None) else 0
+                call("vml_content_unit", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o, o + dl,
+                     o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]),
+                     ptr(fbar), ptr(fc[nxt]), ptr(mu_op), B, dims, store_cu, sst)
+                mark("content_unit")
+            elif fused and dl == 128 and Nq <= 31:
                 call("vml_content_in_attention", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o,
                      o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(cc_hat), B, dims, sst)
             else:
@@ -447,12 +460,13 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
                 mark("content_in_gemm")
                 call("vml_content_attention", ptr(c_hat), ptr(qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
                      ptr(qmask), cells, ptr(cc_hat), B, dims, prec, sst)
-            mark("content_attention")
-            if ev_bu is not None:
-                cside.wait_event(ev_bu)         # fbar of this layer
-            call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]), ptr(fs),
-                 ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
-            mark("content_out_gemm")
+            if not one_kernel_cu:
+                mark("content_attention")
+                if ev_bu is not None:
+                    cside.wait_event(ev_bu)         # fbar of this layer
+                call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]),
+                     ptr(fs), ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
+                mark("content_out_gemm")
         # a8 moment unit (main)
         if fused:
             call("vml_moment_pair", ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
@@ -480,12 +494,12 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
 
 def smin_forward(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace, video_features, video_mask,
                  query_features, query_mask, length_mask, moment_mask, keep: Optional[dict] = None, mark=None,
-                 overlap: bool = True):
+                 overlap: bool = True, split_content: bool = False):
     """The whole hot path: ``smin_ingest`` + ``smin_core``."""
     inp = smin_ingest(dims, prec, ws, video_features, video_mask, query_features, query_mask, length_mask, moment_mask)
     if mark:
         mark("ingest")
-    return smin_core(pk, dims, prec, ws, inp, keep=keep, mark=mark, overlap=overlap)
+    return smin_core(pk, dims, prec, ws, inp, keep=keep, mark=mark, overlap=overlap, split_content=split_content)
 
 
 class SMIN(nn.Module):
@@ -521,7 +535,7 @@ class SMIN(nn.Module):
         return self._packed
 
     def forward(self, video_features, video_mask, query_features, query_mask, length_mask, moment_mask, mark=None,
-                overlap: bool = True):
+                overlap: bool = True, split_content: bool = False):
         if not video_features.is_cuda:
             raise L_.VmlError("vml_b200.SMIN runs on CUDA (sm_100a) only; there is no CPU path. "
                               "Move the module and its inputs to a B200 device.")
@@ -546,4 +560,4 @@ class SMIN(nn.Module):
             pk = self._weights(dev, prec)
             ws = self._ws.setdefault(str(dev), Workspace(dev))
             return smin_forward(pk, self._dims, prec, ws, video_features, video_mask, query_features,
-                                query_mask, length_mask, moment_mask, mark=mark, overlap=overlap)
+                                query_mask, length_mask, moment_mask, mark=mark, overlap=overlap, split_content=split_content)
