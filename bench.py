@@ -149,13 +149,137 @@ def run_reference(args, cfg, rank, world):
     }))
 
 
+def run_train(args, cfg, rank, world, local_rank):
+    """BASELINE.json configs[3]: training step (forward that saves activations, scaled-IoU BCE loss, hand-written
+    backward, ONE NCCL all-reduce of the flat gradient, fused Adam) on a per-GPU batch of 64, fp32."""
+    import vml_b200  # noqa: F401
+    from vml_b200 import lib, synth
+    from vml_b200.configs import init_params
+    from vml_b200.optim import FusedAdam
+    from vml_b200.smin import SMIN
+    from vml_b200.trainer import train_step
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    model = SMIN(*cfg.ctor_args(), device=dev, precision="fp32")
+    model.load_state_dict(init_params(cfg, 43))
+    model = model.to(dev).train()
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    keys = synth.MODEL_INPUT_KEYS + synth.LOSS_LABEL_KEYS
+    one = synth.make_batch(cfg, BATCH, 2000 + 97 * rank)
+    batch_bytes = sum(one[k].numel() * one[k].element_size() for k in keys)
+    n_rot = max(2, min(8, -(-2 * L2_BYTES // batch_bytes)))
+    host = [one] + [synth.make_batch(cfg, BATCH, 2001 + 97 * rank + i) for i in range(n_rot - 1)]
+    pinned = [{k: b[k].pin_memory() for k in keys} for b in host]
+    resident = [{k: b[k].to(dev) for k in keys} for b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        train_step(model, opt, resident[i % n_rot])
+    barrier()
+    l0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            loss = train_step(model, opt, resident[i % n_rot])
+        e1.record()
+        barrier()
+    launches = lib.launch_count() - l0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+    last_loss = float(loss.item())
+
+    # end to end: all 13 collated tensors from pinned host memory every step (main.py:118-133), loss read back (main.py:151)
+    stage = {k: torch.empty_like(resident[0][k]) for k in keys}
+
+    def e2e_step(i):
+        for k in keys:
+            stage[k].copy_(pinned[i % n_rot][k], non_blocking=True)
+        return float(train_step(model, opt, stage).item())
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import smin_forward as oracle_forward
+        from oracle import metrics_oracle as mo
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        nb = 16
+        params = {k: v.clone().requires_grad_(True) for k, v in init_params(cfg, 43).items()}
+        topt = torch.optim.Adam(list(params.values()), lr=1e-4)
+        b = {k: v[:nb] for k, v in host[0].items()}
+
+        def cpu_step():
+            topt.zero_grad()
+            o = oracle_forward(params, cfg, *[b[k] for k in synth.MODEL_INPUT_KEYS])
+            mo.loss_fn(o[0], b["ym"], b["sm"], b["moment_mask"], o[1], b["ys"], b["ss"], o[2], b["ye"], b["se"], o[3], b["ya"],
+                       b["length_mask"]).backward()
+            topt.step()
+        cpu_step()
+        n_cpu, t0 = 0, time.perf_counter()
+        while n_cpu < 6 and (time.perf_counter() - t0 < 15.0 or n_cpu < 2):
+            cpu_step()
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": nb * n_cpu / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                        "sample": f"{n_cpu} training step(s) (fwd + loss + autograd bwd + torch Adam) on {nb} {cfg.name} queries after 1 warm-up, "
+                                  f"fp32 torch CPU oracle port, {torch.get_num_threads()} threads"}
+    if rank == 0:
+        n_param = sum(p.numel() for p in model.parameters())
+        print(json.dumps({
+            "metric": "train queries/sec (fwd+loss+bwd+grad allreduce+Adam)", "mode": "train", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{cfg.name}: SMIN training step, batch {BATCH} per GPU, random-init weights (T={cfg.T} L={cfg.L} C={cfg.C} "
+                                   f"D={cfg.D} dl={cfg.dl} d0={cfg.d0} Nq={cfg.Nq}, {cfg.layers} SMI layers)",
+                       "global_batch": BATCH * world,
+                       "parallelism": f"dp{world}: batch sharded by rank, one NCCL all-reduce of the flat fp32 gradient "
+                                      f"({n_param} params = {n_param * 4 / 1e6:.1f} MB) per step",
+                       "l2": f"inputs rotate over {n_rot} resident batches ({n_rot * batch_bytes / 2**20:.0f} MiB > 126 MiB L2)"},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(batch_bytes), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": None, "cpu_baseline": cpu_baseline,
+            "final_loss": last_loss, "kernels": lib.kernel_names(),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="charadessta", choices=["charadessta", "tacos", "activitynet"])
+    ap.add_argument("--mode", default="eval", choices=["eval", "train"],
+                    help="eval: forward + R@n,IoU=m (the headline metric); train: the training step of BASELINE configs[3]")
+    ap.add_argument("--config", default=None, choices=["charadessta", "tacos", "activitynet"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=2, help="batches in flight (ScoringPipeline)")
@@ -166,6 +290,8 @@ def main():
 
     import vml_b200  # noqa: F401
     from vml_b200.configs import CONFIGS
+    if args.config is None:
+        args.config = "tacos" if args.mode == "train" else "charadessta"
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,6 +304,11 @@ def main():
         run_reference(args, cfg, rank, world)
         return
 
+    if args.mode == "train":
+        args.steps = args.steps if args.steps is not None else 20
+        args.warmup = max(3, args.warmup if args.warmup is not None else 3)
+        run_train(args, cfg, rank, world, local_rank)
+        return
     args.steps = args.steps if args.steps is not None else 200
     args.warmup = max(3, args.warmup if args.warmup is not None else 10)
 

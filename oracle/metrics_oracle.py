@@ -13,10 +13,11 @@ import torch
 
 
 def _bce_terms(p, y):
-    """Elementwise BCE with PyTorch's clamp of the logs at -100 (aten binary_cross_entropy)."""
-    logp = torch.clamp(torch.log(p), min=-100.0)
-    log1mp = torch.clamp(torch.log(1.0 - p), min=-100.0)
-    return -(y * logp + (1.0 - y) * log1mp)
+    """Elementwise BCE exactly as the reference computes it: ``nn.BCELoss(reduction='none')`` (main.py:94-96) is
+    aten ``binary_cross_entropy`` -- logs clamped at -100 in the forward, and the ANALYTIC backward
+    (p - y) / max(p (1 - p), 1e-12), which stays finite at the masked entries p == 0 (autograd through
+    ``clamp(log(p))`` would give 0 * inf = NaN there, which the reference never produces)."""
+    return torch.nn.functional.binary_cross_entropy(p, y, reduction="none")
 
 
 def scaled_iou_bce(p, y, s, mask):

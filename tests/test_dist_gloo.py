@@ -81,3 +81,49 @@ def test_single_process_collectives_are_noops():
     c = torch.arange(8, dtype=torch.int64).view(2, 4)
     total, n = vdist.allreduce_recall(c, 5)
     assert torch.equal(total, c) and n == 5
+
+
+def _grad_worker(rank, world, port, n_total, out):
+    """Data-parallel training math (trainer.allreduce_mean_): every rank back-propagates the loss of its own slice
+    (autograd of the CPU oracle stands in for the CUDA backward), flattens the gradients in parameter order like
+    FusedAdam.flat_grad, and one all-reduce yields the global-batch gradient."""
+    from vml_b200.trainer import allreduce_mean_
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    vdist.init_from_env(backend="gloo")
+    cfg = CONFIGS["tiny"]
+    params = {k: v.clone().double().requires_grad_(True) for k, v in init_params(cfg, 43).items()}
+    mine = {k: (v.double() if v.is_floating_point() else v)
+            for k, v in vdist.shard_batch(synth.make_batch(cfg, n_total, 78), rank, world).items()}
+    pm, ps, pe, pa = smin_forward(params, cfg, *[mine[k] for k in synth.MODEL_INPUT_KEYS])
+    loss = mo.loss_fn(pm, mine["ym"], mine["sm"], mine["moment_mask"], ps, mine["ys"], mine["ss"], pe, mine["ye"], mine["se"], pa,
+                      mine["ya"], mine["length_mask"])
+    loss.backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in params.values()])
+    assert allreduce_mean_(flat) == 1.0
+    if rank == 0:
+        torch.save(flat, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_equals_global_batch_gradient(tmp_path):
+    out = str(tmp_path / "g.pt")
+    n_total = 6                                        # equal slices: mean of local means == global mean (main.py:106)
+    mp.spawn(_grad_worker, args=(2, _free_port(), n_total, out), nprocs=2, join=True)
+    got = torch.load(out)
+    cfg = CONFIGS["tiny"]
+    params = {k: v.clone().double().requires_grad_(True) for k, v in init_params(cfg, 43).items()}
+    full = {k: (v.double() if v.is_floating_point() else v) for k, v in synth.make_batch(cfg, n_total, 78).items()}
+    pm, ps, pe, pa = smin_forward(params, cfg, *[full[k] for k in synth.MODEL_INPUT_KEYS])
+    mo.loss_fn(pm, full["ym"], full["sm"], full["moment_mask"], ps, full["ys"], full["ss"], pe, full["ye"], full["se"], pa,
+               full["ya"], full["length_mask"]).backward()
+    want = torch.cat([p.grad.reshape(-1) for p in params.values()])
+    assert got.shape == want.shape
+    assert torch.isfinite(want).all() and want.abs().max() > 0
+    assert (got - want).abs().max() <= 1e-9 * want.abs().max()
+
+
+def test_allreduce_mean_single_process_is_noop():
+    from vml_b200.trainer import allreduce_mean_
+    g = torch.arange(5, dtype=torch.float32)
+    assert allreduce_mean_(g, scale_here=False) == 1.0 and torch.equal(g, torch.arange(5, dtype=torch.float32))
