@@ -152,6 +152,18 @@ VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, i
 VML_API int vml_span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb,
                        int B, vml_dims_t d, int prec, void* stream);
 
+/* ---- labels and masks of a batch from the annotation scalars (dataset.py:95-127,139-158) ------- */
+
+/* times double [B,2] = ground-truth (start, end) seconds, duration double [B], nfeats int64 [B] (clips kept of T).
+ * Outputs (any may be NULL): sm float [B,L,L] IoU map, ym u8 = sm > 0.5; ss / se float [B,L] Gaussian boundary
+ * penalties, ys / ye u8 = . > 0.5; ya u8 [B,L] snippet inside the moment; length_mask u8 [B,L];
+ * moment_mask u8 [B,L,L] (upper triangle of valid snippets); video_mask u8 [B,T].  The u8 outputs hold 0/1 and can
+ * be viewed as bool.  sm / ym / ya / masks are bit-exact with the reference's float32 CPU arithmetic; ss / se up
+ * to the exp implementation (<= 2 ulp). */
+VML_API int vml_make_labels(const double* times, const double* duration, const int64_t* nfeats, int B, int T, int L,
+                            float* sm, uint8_t* ym, float* ss, uint8_t* ys, float* se, uint8_t* ye, uint8_t* ya,
+                            uint8_t* length_mask, uint8_t* moment_mask, uint8_t* video_mask, void* stream);
+
 /* ---- a5+a6: ContentUnit (models.py:207-226,242-276) ----------------------------------------- */
 
 /* middle of the unit: c_hat act [n*C, dl] -> cc_hat act [n*C, dl]

@@ -116,6 +116,8 @@ int content_tc(const void*, const void*, const float*, const float*, int, int, i
 int content_unit(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
                  vml_cells_t, const void*, const float*, const void*, void*, void*, int, int, vml_dims_t, int, cudaStream_t);
 bool content_unit_supported(vml_dims_t);
+int make_labels(const double*, const double*, const int64_t*, int, int, int, float*, uint8_t*, float*, uint8_t*, float*, uint8_t*,
+                uint8_t*, uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
 int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
              float*, int, vml_dims_t, int, cudaStream_t);
@@ -242,6 +244,12 @@ VML_API int vml_content_in_attention(const void* fc, const void* W, const float*
                              vml_cells_t cells, void* cc_hat, int B, vml_dims_t d, void* stream) {
   return content_tc(fc, W, bias, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, cc_hat, B, d,
                     ST(stream));
+}
+
+VML_API int vml_make_labels(const double* times, const double* duration, const int64_t* nfeats, int B, int T, int L, float* sm,
+                    uint8_t* ym, float* ss, uint8_t* ys, float* se, uint8_t* ye, uint8_t* ya, uint8_t* length_mask,
+                    uint8_t* moment_mask, uint8_t* video_mask, void* stream) {
+  return make_labels(times, duration, nfeats, B, T, L, sm, ym, ss, ys, se, ye, ya, length_mask, moment_mask, video_mask, ST(stream));
 }
 
 VML_API int vml_content_unit_supported(vml_dims_t d) { return content_unit_supported(d) ? 1 : 0; }

@@ -85,7 +85,9 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   using Cfg = CuCfg<NQP, GS>;
   constexpr int NW = Cfg::NW, KG = Cfg::KG;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
+  // compiler (LDS/STS instead of generic LD/ST, which an integer round-trip of the pointer would force)
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* Xs = smem;                                    // resident fc tile: KB boxes
   unsigned char* Cs = Xs + Cfg::X_BYTES;                       // c_hat, then cc_hat
   unsigned char* U = Cs + CU_CS_BYTES;                         // Ks | Wt | Ps: the attention operands

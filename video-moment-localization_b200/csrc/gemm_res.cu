@@ -35,7 +35,9 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmSide, int M, int N, int K,
                 const int32_t* __restrict__ m_dev, int m_scale, const float* __restrict__ bias) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
+  // compiler (LDS/STS instead of generic LD/ST, which an integer round-trip of the pointer would force)
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* res = smem + GR_STAGES * GR_STAGE_BYTES;                  // [2][R1 | R2]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(res + 2 * GR_RES_BYTES);
   uint64_t* empty_bar = full_bar + GR_STAGES;

@@ -52,7 +52,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
   using Cfg = UmmaCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
+  // compiler (LDS/STS instead of generic LD/ST, which an integer round-trip of the pointer would force)
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
