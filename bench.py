@@ -382,8 +382,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         e0.record()
+        t_host = time.perf_counter()
         for i in range(args.steps):
             pipe.submit(resident[i % n_rot])
+        t_host = time.perf_counter() - t_host        # host time to ENQUEUE the steps (the launch queue absorbs it while < device time)
         pipe.wait_all()
         e1.record()
         barrier()
@@ -543,7 +545,8 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{cfg.name}: SMIN forward + R@n,IoU=m eval, batch {BATCH} per GPU, random-init weights "
                                    f"(T={cfg.T} L={cfg.L} C={cfg.C} D={cfg.D} dl={cfg.dl} d0={cfg.d0} Nq={cfg.Nq}, {cfg.layers} SMI layers)",

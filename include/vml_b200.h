@@ -152,6 +152,12 @@ VML_API int vml_query_lengths(const uint8_t* query_mask, int32_t* qlen, int B, i
 VML_API int vml_span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb,
                        int B, vml_dims_t d, int prec, void* stream);
 
+/* ---- input pipeline (main.py:118-133: 13 blocking, un-pinned copies per step in the reference) ---- */
+
+/* One asynchronous host-to-device copy of a pinned host blob on `stream` (the whole collated batch travels as
+ * ONE blob, see pipeline.pack_host_batch); no allocation, no synchronisation. */
+VML_API int vml_copy_h2d_async(void* dst, const void* src_pinned, int64_t bytes, void* stream);
+
 /* ---- labels and masks of a batch from the annotation scalars (dataset.py:95-127,139-158) ------- */
 
 /* times double [B,2] = ground-truth (start, end) seconds, duration double [B], nfeats int64 [B] (clips kept of T).

@@ -246,6 +246,12 @@ VML_API int vml_content_in_attention(const void* fc, const void* W, const float*
                     ST(stream));
 }
 
+VML_API int vml_copy_h2d_async(void* dst, const void* src_pinned, int64_t bytes, void* stream) {
+  VML_CHECK_ARG(dst && src_pinned && bytes >= 0);
+  VML_CUDA(cudaMemcpyAsync(dst, src_pinned, (size_t)bytes, cudaMemcpyHostToDevice, ST(stream)));
+  return VML_OK;
+}
+
 VML_API int vml_make_labels(const double* times, const double* duration, const int64_t* nfeats, int B, int T, int L, float* sm,
                     uint8_t* ym, float* ss, uint8_t* ys, float* se, uint8_t* ye, uint8_t* ya, uint8_t* length_mask,
                     uint8_t* moment_mask, uint8_t* video_mask, void* stream) {

@@ -54,6 +54,7 @@ _SIGS = {
     "vml_span_pool_fuse": [_P, _P, Cells, _P, _P, _P, _I, Dims, _I, _P],
     "vml_content_attention": [_P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _I, _P],
     "vml_content_in_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _P],
+    "vml_copy_h2d_async": [_P, _P, _I64, _P],
     "vml_make_labels": [_P, _P, _P, _I, _I, _I] + [_P] * 10 + [_P],
     "vml_content_unit": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_content_unit_supported": [Dims],

@@ -88,7 +88,34 @@ class _Staging:
         self.buf: Optional[Dict[str, torch.Tensor]] = None
         self.blob: Optional[torch.Tensor] = None
         self.ready = torch.cuda.Event()
-        self.free: Optional[torch.cuda.Event] = None
+        self.free = torch.cuda.Event()         # re-recorded by every consumer
+        self.used = False
+        self.src_ptrs = None                   # device pointers of the 7 views, in vml_ingest argument order
+
+
+# canonical dtypes of a collated batch (dataset.py:165-176); anything else takes the generic (converting) path
+_CANON = {"video_features": torch.float32, "video_mask": torch.uint8, "query_features": torch.float32,
+          "query_mask": torch.uint8, "length_mask": torch.bool, "moment_mask": torch.bool, "sm": torch.float32}
+# vml_ingest takes (vf, qf, vmask, qmask, lmask, mmask, sm)
+_INGEST_ORDER = ("video_features", "query_features", "video_mask", "query_mask", "length_mask", "moment_mask", "sm")
+
+
+class _Plan:
+    """The recorded ingest launch of one (slot, position in the group)."""
+
+    def __init__(self, inp: dict, stream_ptr: int):
+        a = inp["_ingest_args"]
+        self.tail = tuple(a[7:-1]) + (stream_ptr,)
+        self.inp = inp
+        self.ev = torch.cuda.Event()
+
+
+def _canonical(batch: Dict[str, torch.Tensor]) -> bool:
+    for k, dt in _CANON.items():
+        t = batch[k]
+        if t.dtype is not dt or not t.is_contiguous():
+            return False
+    return True
 
 
 class ScoringPipeline:
@@ -114,6 +141,11 @@ class ScoringPipeline:
         self._cur = 0
         self._batch = None
         self._pk = None
+        # per-step fast path: the ingest launch of (slot, position) re-issued with new source pointers -- ~20 us of host
+        # work per submitted batch instead of ~180 us through the generic module path (measured; the device step is ~210 us)
+        self._plans: Dict[tuple, "_Plan"] = {}
+        self._ingest_fn = getattr(L_.load(), "vml_ingest")
+        self._h2d_fn = getattr(L_.load(), "vml_copy_h2d_async")
 
     # -- one pass on a slot ------------------------------------------------------------------------------
     def _core_and_eval(self, slot: _Slot, pk, inp, group):
@@ -163,46 +195,65 @@ class ScoringPipeline:
         if B != self._batch:
             raise ValueError(f"ScoringPipeline is set up for batches of {self._batch} (got {B}); score a ragged tail batch "
                              "with the module API or a second pipeline")
-        with torch.no_grad():
-            pk = self.model._weights(self.device, self.prec)
-            if pk is not self._pk:                   # (re)packed on the caller's stream: publish to every slot stream
-                torch.cuda.synchronize(self.device)
-                self._pk = pk
-                self.invalidate()
         slot = self.slots[self._cur]
-        caller = torch.cuda.current_stream(self.device)
-        with torch.no_grad(), torch.cuda.stream(slot.stream):
-            if from_host:
-                stg = self.staging[self._next_staging]
-                self._next_staging = (self._next_staging + 1) % len(self.staging)
-                blob = batch.get("_blob")
-                if stg.buf is None:
-                    if blob is not None:                          # one device blob mirroring the host blob: one copy per batch
-                        stg.blob = torch.empty(blob.numel(), dtype=torch.uint8, device=self.device)
-                        stg.buf = _blob_views(stg.blob, batch)
-                    else:
-                        stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in INPUT_KEYS}
-                with torch.cuda.stream(self.copy_stream):
-                    if stg.free is not None:
-                        self.copy_stream.wait_event(stg.free)     # the previous consumer's ingest has read it
-                    if blob is not None and getattr(stg, "blob", None) is not None:
-                        stg.blob.copy_(blob, non_blocking=True)
-                    else:
-                        for k in INPUT_KEYS:
-                            stg.buf[k].copy_(batch[k], non_blocking=True)
-                    stg.ready.record(self.copy_stream)
-                slot.stream.wait_event(stg.ready)
-                src = stg.buf
+        if slot.fill == 0 or self._pk is None:       # parameters are looked at once per pass, not per batch
+            with torch.no_grad():
+                pk = self.model._weights(self.device, self.prec)
+                if pk is not self._pk:               # (re)packed on the caller's stream: publish to every slot stream
+                    torch.cuda.synchronize(self.device)
+                    self._pk = pk
+                    self.invalidate()
+        plan = self._plans.get((self._cur, slot.fill))
+        fast = plan is not None and _canonical(batch)
+        stg = None
+        if from_host:
+            stg = self.staging[self._next_staging]
+            self._next_staging = (self._next_staging + 1) % len(self.staging)
+            blob = batch.get("_blob")
+            if stg.buf is None:
+                if blob is not None:                          # one device blob mirroring the host blob: one copy per batch
+                    stg.blob = torch.empty(blob.numel(), dtype=torch.uint8, device=self.device)
+                    stg.buf = _blob_views(stg.blob, batch)
+                else:
+                    stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in INPUT_KEYS}
+                stg.src_ptrs = tuple(stg.buf[k].data_ptr() for k in _INGEST_ORDER)
+            if stg.used:
+                self.copy_stream.wait_event(stg.free)         # the previous consumer's ingest has read it
+            if blob is not None and stg.blob is not None:
+                L_.check(self._h2d_fn(stg.blob.data_ptr(), blob.data_ptr(), blob.numel(), self.copy_stream.cuda_stream),
+                         "vml_copy_h2d_async")
             else:
-                ev = torch.cuda.Event()
-                ev.record(caller)
-                slot.stream.wait_event(ev)           # the caller's tensors are ready
-                src = batch
-            slot.inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True,
-                                   b_off=slot.fill * B, b_total=self.coalesce * B)
-            if from_host:
-                stg.free = torch.cuda.Event()
-                stg.free.record(slot.stream)
+                with torch.cuda.stream(self.copy_stream):
+                    for k in INPUT_KEYS:
+                        stg.buf[k].copy_(batch[k], non_blocking=True)
+            stg.ready.record(self.copy_stream)
+            slot.stream.wait_event(stg.ready)
+            src = stg.buf
+        else:
+            src = batch
+        if fast:
+            if not from_host:
+                plan.ev.record(torch.cuda.current_stream(self.device))
+                slot.stream.wait_event(plan.ev)               # the caller's tensors are ready
+                ptrs = tuple(batch[k].data_ptr() for k in _INGEST_ORDER)
+            else:
+                ptrs = stg.src_ptrs
+            L_.check(self._ingest_fn(*ptrs, *plan.tail), "vml_ingest")
+            slot.inp = plan.inp
+        else:
+            with torch.no_grad():
+                if not from_host:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    slot.stream.wait_event(ev)               # the caller's tensors are ready
+                with torch.cuda.stream(slot.stream):
+                    slot.inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True,
+                                           b_off=slot.fill * B, b_total=self.coalesce * B)
+            if _canonical(src):
+                self._plans[(self._cur, slot.fill)] = _Plan(slot.inp, slot.stream.cuda_stream)
+        if from_host:
+            stg.free.record(slot.stream)
+            stg.used = True
         ticket = Ticket(slot, slot.fill)
         slot.tickets.append(ticket)
         slot.readbacks.append(readback)

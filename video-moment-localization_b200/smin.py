@@ -318,8 +318,10 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
     def at(t):                      # device pointer of sample b_off inside a [Bt, ...] operand buffer
         return None if t is None else t.data_ptr() + b_off * (t.numel() // Bt) * t.element_size()
 
-    call("vml_ingest", ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
-         *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, stream_ptr())
+    args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
+            *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, stream_ptr())
+    call("vml_ingest", *args)
+    inp["_ingest_args"] = args          # ScoringPipeline re-issues this launch with new source pointers (its per-step fast path)
     inp.update(v=v_out if v_out is not None else vf, q=q_out if q_out is not None else qf, qlen=qlen,
                vmask=m_out[0] if static else vmask, qmask=m_out[1] if static else qmask,
                lmask=m_out[2] if static else lmask, mmask=m_out[3] if static else mmask,
