@@ -19,10 +19,11 @@
 // The next tile's boxes are re-loaded as soon as the store of their column block has left shared memory,
 // so its HBM reads and its main loop overlap the tail epilogue of the current tile.
 //
-// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer for (1) and (4), warps 2..9 row warps: a
-// pair of threads (same TMEM lane, warps w and w + 4) == tile row == (cell, clip), each owning 64 of a row's 128
-// columns in every per-row loop; thread 64 issues (2) and (3); warp 10 issues the TMA stores and waits for them.  The row warps are latency-bound
-// (measured: 24.5 us per tile with 4 row warps at IPC ~0.3), hence two of them per SM scheduler.
+// Warp roles (608 threads): warp 0 TMA producer, warp 1 MMA issuer for (1) and (4), warps 2..17 row warps: four
+// threads (same TMEM lane, warps w, w + 4, w + 8, w + 12) == tile row == (cell, clip), each owning 32 of a row's 128
+// columns in every per-row loop; thread 64 issues (2) and (3); the last warp issues the TMA stores and waits for
+// them.  The row warps bound the kernel (measured per tile at the bench shape: 24.5 us with 4 row warps, 17.5 us
+// with 8, 15.3 us with 16 at 96 registers per thread), the tensor cores and HBM are far from their roofs.
 //
 // TMEM columns: [0,128) c_hat accumulator; [128,256) A, later Y (even column blocks); [256,256+NW) S,
 // [256,384) later Y (odd column blocks) -- the aliases are phase-exclusive (Y MMAs are issued only after
@@ -45,9 +46,14 @@ int cu_debug_read(long long* host, int n) { return (int)cudaMemcpyFromSymbol(hos
 #endif
 
 constexpr int CU_DL = 128, CU_WST = 2, CU_MAXKB = 8;
-constexpr int CU_ROW_WARPS = 8, CU_ROW_THREADS = 32 * CU_ROW_WARPS, CU_THREADS = 64 + CU_ROW_THREADS + 32;   // + store warp
-#define CU_ROW_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
-static_assert(CU_ROW_THREADS == 256, "CU_ROW_BAR names the thread count");
+#ifndef VML_CU_ROW_WARPS
+#define VML_CU_ROW_WARPS 16
+#endif
+constexpr int CU_ROW_WARPS = VML_CU_ROW_WARPS, CU_ROW_THREADS = 32 * CU_ROW_WARPS, CU_THREADS = 64 + CU_ROW_THREADS + 32;   // + store warp
+constexpr int CU_SPLIT = CU_ROW_WARPS / 4;           // threads per tile row (one per TMEM-lane-sharing warp)
+constexpr int CU_COLS = 128 / CU_SPLIT;              // columns of a 128-column block each of them owns
+static_assert(CU_ROW_WARPS == 8 || CU_ROW_WARPS == 16, "2 or 4 row warps per TMEM lane quadrant");
+#define CU_ROW_BAR() asm volatile("bar.sync 1, %0;" ::"n"(CU_ROW_THREADS) : "memory")
 constexpr int CU_BOX = UG_BM * UG_BK * 2;            // one 128 x 64 bf16 box (16 KB)
 constexpr int CU_CS_BYTES = UG_BM * CU_DL * 2;       // c_hat / cc_hat tile
 constexpr int CU_TMEM_A = 128, CU_TMEM_S = 256, CU_TMEM_Y0 = 128, CU_TMEM_Y1 = 256;
@@ -59,7 +65,8 @@ struct CuCfg {
   static constexpr int KS_BYTES = NW * CU_DL * 2;    // keys,   K-major (rows = word slots), lbo 128, sbo 2048
   static constexpr int WT_BYTES = NW * CU_DL * 2;    // values, MN-major, lbo 128, sbo KG*128
   static constexpr int PS_BYTES = UG_BM * NW * 2;    // probabilities, K-major, lbo 128, sbo KG*128
-  static constexpr int U_RAW = KS_BYTES + WT_BYTES + PS_BYTES;
+  static constexpr int GG_BYTES = CU_SPLIT * UG_BM * 16;   // partial Grams (float4 per row thread), aliased onto Ps
+  static constexpr int U_RAW = KS_BYTES + WT_BYTES + (PS_BYTES > GG_BYTES ? PS_BYTES : GG_BYTES);
   static constexpr int U_BYTES = (U_RAW + 1023) / 1024 * 1024;
   static constexpr int SIDE_FLOATS = 2 * NW + CU_DL + CU_MAXKB * 64;   // beta | mask | b1 | b2
   static constexpr int X_BYTES = CU_MAXKB * CU_BOX;
@@ -248,7 +255,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // warp w serves TMEM lane quadrant w % 4; the two warps of a quadrant (grp 0 / 1) split every per-row loop by
     // columns, so each SM scheduler interleaves two of these latency-bound warps.
     const int quad = warp % 4;
-    const int grp = (warp - 2) >> 2;                      // column half this thread owns
+    const int grp = (warp - 2) >> 2;                      // which CU_COLS-column share of a row this thread owns
     const int r = quad * 32 + lane;                       // row within the tile == TMEM lane
     const int at = threadIdx.x - 64;                      // 0..255
     const bool issuer = at == 0;
@@ -317,7 +324,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           ptx::tc_fence_after();
           const uint32_t t_addr = tmem_base + lane_base;
 #pragma unroll 1
-          for (int c = grp * 64; c < grp * 64 + 64; c += 32) {
+          for (int c = grp * CU_COLS; c < grp * CU_COLS + CU_COLS; c += 32) {
             float v[32];
             ptx::tmem_ld32(t_addr + (uint32_t)c, v);
             ptx::tmem_ld_wait();
@@ -325,7 +332,10 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int e = 0; e < 32; e += 8) {
               float t[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) t[q] = v[e + q] + s_b1[c + e + q];
+              for (int q = 0; q < 8; q += 2) {
+                t[q] = v[e + q]; t[q + 1] = v[e + q + 1];
+                ptx::add2(t[q], t[q + 1], s_b1[c + e + q], s_b1[c + e + q + 1]);
+              }
               *reinterpret_cast<uint4*>(Cs + row_off + ((c + e) >> 3) * 128) = cu_pack8(t);
             }
           }
@@ -409,7 +419,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       // ---- gate G = c_hat * (A + s_hat), Gram of the cell's 4 clips (adjacent lanes); this thread: 64 columns ----
       float gg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = grp * 64; c < grp * 64 + 64; c += 32) {
+      for (int c = grp * CU_COLS; c < grp * CU_COLS + CU_COLS; c += 32) {
         float a[32];
         ptx::tmem_ld32(tmem_base + lane_base + CU_TMEM_A + (uint32_t)c, a);
         ptx::tmem_ld_wait();
@@ -417,7 +427,10 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int e = 0; e < 32; e += 8) {
           const f8 ch = unpack8(*reinterpret_cast<const uint4*>(Cs + row_off + ((c + e) >> 3) * 128));
 #pragma unroll
-          for (int q = 0; q < 8; ++q) a[e + q] = valid ? ch.v[q] * a[e + q] : 0.f;
+          for (int q = 0; q < 8; q += 2) {
+            ptx::mul2(a[e + q], a[e + q + 1], ch.v[q], ch.v[q + 1]);
+            if (!valid) { a[e + q] = 0.f; a[e + q + 1] = 0.f; }
+          }
         }
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
@@ -434,7 +447,13 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       s_gg[grp * 128 + r] = make_float4(gg[0], gg[1], gg[2], gg[3]);
       CU_ROW_BAR();
       {
-        const float4 lo = s_gg[r], hi = s_gg[128 + r];       // (columns 0..63) + (columns 64..127), same order in both threads
+        // (columns 0..63) + (columns 64..127), the same order in every thread of the row (and in content_tc.cu)
+        float4 lo = s_gg[r], hi = s_gg[(CU_SPLIT / 2) * 128 + r];
+        if (CU_SPLIT == 4) {
+          const float4 l1 = s_gg[128 + r], h1 = s_gg[3 * 128 + r];
+          lo = make_float4(lo.x + l1.x, lo.y + l1.y, lo.z + l1.z, lo.w + l1.w);
+          hi = make_float4(hi.x + h1.x, hi.y + h1.y, hi.z + h1.z, hi.w + h1.w);
+        }
         gg[0] = lo.x + hi.x; gg[1] = lo.y + hi.y; gg[2] = lo.z + hi.z; gg[3] = lo.w + hi.w;
       }
       CU_T(7);
@@ -454,7 +473,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       // cc_hat row written IN PLACE of the c_hat row: a row's siblings (r ^ 1..3) are lanes of the same warp, and
       // every chunk is read by all four before any of them overwrites it (__syncwarp between read and write)
 #pragma unroll 4
-      for (int c = grp * 64; c < grp * 64 + 64; c += 8) {
+      for (int c = grp * CU_COLS; c < grp * CU_COLS + CU_COLS; c += 8) {
         f8 o;
 #pragma unroll
         for (int q = 0; q < 8; ++q) o.v[q] = 0.f;
@@ -462,7 +481,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int m = 0; m < 4; ++m) {
           const f8 sv = unpack8(*reinterpret_cast<const uint4*>(Cs + sib[m] + (c >> 3) * 128));
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o.v[q] = fmaf(gg[m], sv.v[q], o.v[q]);
+          for (int q = 0; q < 8; q += 2) ptx::fma2(o.v[q], o.v[q + 1], gg[m], gg[m], sv.v[q], sv.v[q + 1]);
         }
         if (!valid) {
 #pragma unroll
@@ -478,54 +497,64 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       // ---- (4) epilogue: out = Y + b_c + X + fbar in place, side = mean over the cell's 4 clips; this thread: the
       //      64-column box `grp` of every 128-column block.  fbar comes straight from global memory (L2: the boundary
       //      unit has just written it), fetched before the wait for the accumulator ------------------------------
-      const bf16* frow = fbar + (size_t)(row >> 2) * D + grp * 64;
-      bf16* srow = side + (size_t)(row >> 2) * ld_side + grp * 64;
+      constexpr int NP = CU_COLS / 8;                        // 16-byte pieces per thread and column block
+      const bf16* frow = fbar + (size_t)(row >> 2) * D + grp * CU_COLS;
+      bf16* srow = side + (size_t)(row >> 2) * ld_side + grp * CU_COLS;
+      const int box_of = (grp * CU_COLS) >> 6, pc0 = ((grp * CU_COLS) & 63) >> 3;   // 64-column box and first piece inside it
       // fbar is ~1 us away (L2 / HBM): block nb + 1's pieces are requested right after block nb has consumed its own,
       // and the first half of a block's arithmetic (accumulator + bias + residual) runs while they are in flight
-      uint4 fq[8];
+      uint4 fq[NP];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < NP; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
       for (int nb = 0; nb < NB; ++nb, ++yi) {
         const uint32_t yb = yi & 1, yph = (yi >> 1) & 1;
-        unsigned char* xb = Xs + (2 * nb + grp) * CU_BOX;
+        unsigned char* xb = Xs + (2 * nb + box_of) * CU_BOX;
         ptx::mbar_wait_relaxed(&yfull[yb], yph);              // TMEM data: ordered by the tcgen05 fence below
         CU_T(9 + 2 * nb);
         ptx::tc_fence_after();
-        const uint32_t t_addr = tmem_base + lane_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0) + (uint32_t)(grp * 64);
-        const float* bcol = s_b2 + nb * 128 + grp * 64;
-        float acc[64];
+        const uint32_t t_addr = tmem_base + lane_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0) + (uint32_t)(grp * CU_COLS);
+        const float* bcol = s_b2 + nb * 128 + grp * CU_COLS;
+        float acc[CU_COLS];
         ptx::tmem_ld32(t_addr, acc);
-        ptx::tmem_ld32(t_addr + 32u, acc + 32);
+        if (CU_COLS == 64) ptx::tmem_ld32(t_addr + 32u, acc + (CU_COLS - 32));
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
-          const f8 xv = unpack8(*reinterpret_cast<const uint4*>(xb + ptx::sw128_off(r, pc)));
+        for (int pc = 0; pc < NP; ++pc) {
+          const f8 xv = unpack8(*reinterpret_cast<const uint4*>(xb + ptx::sw128_off(r, pc0 + pc)));
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[pc * 8 + q] = (acc[pc * 8 + q] + bcol[pc * 8 + q]) + xv.v[q];
+          for (int q = 0; q < 8; q += 2) {
+            float* a = acc + pc * 8 + q;
+            ptx::add2(a[0], a[1], bcol[pc * 8 + q], bcol[pc * 8 + q + 1]);       // (acc + bias)
+            ptx::add2(a[0], a[1], xv.v[q], xv.v[q + 1]);                          //   + residual
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)      // fbar is consumed only from here on (keeps the unpacking below the loop above)
+        for (int i = 0; i < NP; ++i)     // fbar is consumed only from here on (keeps the unpacking below the loop above)
           asm volatile("" : "+r"(fq[i].x), "+r"(fq[i].y), "+r"(fq[i].z), "+r"(fq[i].w));
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
+        for (int pc = 0; pc < NP; ++pc) {
           const f8 fv = unpack8(fq[pc]);
           f8 o;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o.v[q] = acc[pc * 8 + q] + fv.v[q];
-          *reinterpret_cast<uint4*>(xb + ptx::sw128_off(r, pc)) = cu_pack8(o.v);      // result in place of the residual
+          for (int q = 0; q < 8; q += 2) {
+            o.v[q] = acc[pc * 8 + q]; o.v[q + 1] = acc[pc * 8 + q + 1];
+            ptx::add2(o.v[q], o.v[q + 1], fv.v[q], fv.v[q + 1]);                  //   + fbar
+          }
+          *reinterpret_cast<uint4*>(xb + ptx::sw128_off(r, pc0 + pc)) = cu_pack8(o.v);      // result in place of the residual
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {                      // mean over the cell's 4 rows (adjacent lanes)
-            float t = o.v[q];
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            o.v[q] = t * 0.25f;
+          for (int q = 0; q < 8; q += 2) {                   // mean over the cell's 4 rows (adjacent lanes)
+            float t0 = o.v[q], t1 = o.v[q + 1];
+            ptx::add2(t0, t1, __shfl_xor_sync(0xffffffffu, t0, 1), __shfl_xor_sync(0xffffffffu, t1, 1));
+            ptx::add2(t0, t1, __shfl_xor_sync(0xffffffffu, t0, 2), __shfl_xor_sync(0xffffffffu, t1, 2));
+            ptx::mul2(t0, t1, 0.25f, 0.25f);
+            o.v[q] = t0; o.v[q + 1] = t1;
           }
           if ((lane & 3) == 0 && valid) *reinterpret_cast<uint4*>(srow + nb * 128 + pc * 8) = cu_pack8(o.v);
         }
         CU_T(38 + nb);
         if (nb + 1 < NB) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < NP; ++i)
             fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow + (nb + 1) * 128) + i) : make_uint4(0, 0, 0, 0);
         }
         CU_T(34 + nb);

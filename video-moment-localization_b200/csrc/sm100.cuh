@@ -101,6 +101,35 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // byte offset of the 16-byte piece (8 bf16) `piece` (0..7) of row r inside a 128B-swizzled 64-column box
 __device__ __forceinline__ uint32_t sw128_off(int r, int piece) { return (uint32_t)(r * 128 + ((piece ^ (r & 7)) << 4)); }
 
+// ---- packed fp32 (sm_100: FADD2 / FMUL2 / FFMA2 take two IEEE-rn fp32 lanes per issue slot) ------------------
+// The fma pipe issues one warp instruction per 2 cycles per SM sub-partition; epilogues that are bound by it
+// (elementwise fp32 over whole tiles) halve their issue count with these.  Results are bit-identical to the
+// scalar add.rn / mul.rn / fma.rn.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// (a0, a1) += (b0, b1)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a = pk2(a0, a1);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(pk2(b0, b1)));
+  upk2(a, a0, a1);
+}
+// (a0, a1) *= (b0, b1)
+__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a = pk2(a0, a1);
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(pk2(b0, b1)));
+  upk2(a, a0, a1);
+}
+// (d0, d1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  uint64_t d = pk2(d0, d1);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(pk2(a0, a1)), "l"(pk2(b0, b1)));
+  upk2(d, d0, d1);
+}
+
 // ---- tcgen05 ----------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
