@@ -112,6 +112,35 @@ def stage_work(cfg, B, n_cells, prec_bytes):
     return w
 
 
+# stage of the bench -> kernels of the ncu --set full capture (profiles/*_traffic.json, tools/ncu_summary.py --json)
+STAGE_KERNELS = {
+    "content_unit": ("content_unit_kernel",), "content_attention": ("content_tc_kernel",), "content_out_gemm": ("gemm_res_kernel",),
+    "boundary_unit": ("boundary_gate_mma_kernel", "boundary_rows_mma_kernel", "boundary_stream_kernel"),
+    "moment_out_gemm": ("gemm_umma_kernel<256, EpiMomentOutPre>", "gemm_umma_kernel<128, EpiMomentOutPre>"),
+    "span_pool_fuse": ("span_pool_kernel",), "moment_operand": ("moment_pair_kernel",),
+    "clip_projection": ("gemm_umma_kernel<128, EpiClip", "gemm_umma_kernel<256, EpiClip"),
+}
+
+
+def ncu_traffic(stage, cfg_name, queries_in_pass):
+    """DRAM bytes per launch group of `stage` from the committed ncu --set full capture of the same pass shape
+    (dram__bytes_read.sum + dram__bytes_write.sum), or None when no capture of this shape is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path) or stage not in STAGE_KERNELS:
+        return None
+    with open(path) as f:
+        cap = json.load(f)
+    if cap.get("config") != cfg_name or cap.get("queries_in_pass") != queries_in_pass:
+        return None
+    tot, hit = 0.0, False
+    for want in STAGE_KERNELS[stage]:
+        for name, ent in cap["kernels"].items():
+            if name.startswith(want):
+                tot += ent["traffic_bytes_per_launch"]
+                hit = True
+    return tot if hit else None
+
+
 def run_reference(args, cfg, rank, world):
     """CPU arm: the oracle port (the reference is pure Python and cannot travel; oracle/ is its
     pinned restatement) on all host threads.  Rank 0 only."""
@@ -282,7 +311,7 @@ def main():
     ap.add_argument("--config", default=None, choices=["charadessta", "tacos", "activitynet"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slots", type=int, default=2, help="batches in flight (ScoringPipeline)")
+    ap.add_argument("--slots", type=int, default=3, help="passes in flight (ScoringPipeline)")
     ap.add_argument("--coalesce", type=int, default=3, help="submitted batches scored per pass (ScoringPipeline)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--split-content", action="store_true", help="content unit as two kernels (A/B against vml_content_unit)")
@@ -507,7 +536,9 @@ def main():
         t = stages[top]
         roofline = {"kernel": top, "bound": t["bound"], "achieved": t["achieved"],
                     "peak": peaks["hbm_gbs"] if t["bound"] == "hbm" else peaks["bf16_tflops"], "unit": t["unit"],
-                    "frac": t["frac"], "traffic": None, "share_of_step": t["share"], "peak_source": peaks["source"],
+                    "frac": t["frac"], "traffic": ncu_traffic(top, cfg.name, PB), "traffic_unit": "bytes per launch group (ncu --set full, profiles/ncu_traffic.json)",
+                    "algorithmic_bytes_or_flops": work[top][1],
+                    "share_of_step": t["share"], "peak_source": peaks["source"],
                     "how": "stage launches replayed as a CUDA graph between CUDA events, L2 flushed before each replay"}
 
     # ---------------- counters across ranks (the only collective) -----------------------------------

@@ -74,7 +74,16 @@ def main():
         # per-kernel mean traffic per launch -> bench.py's roofline.traffic
         agg = {}
         for e in out:
-            base = e["kernel"].split("<")[0].replace("void ", "").replace("vml::", "").split("(")[0]
+            # "void vml::gemm_umma_kernel<256, vml::EpiMomentOutPre>(CUtensorMap_st, ...)" -> "gemm_umma_kernel<256, EpiMomentOutPre>"
+            base = e["kernel"].replace("void ", "").replace("vml::", "").replace("(int)", "")
+            depth, cut = 0, len(base)
+            for i, ch in enumerate(base):
+                depth += ch == "<"
+                depth -= ch == ">"
+                if ch == "(" and depth == 0:
+                    cut = i
+                    break
+            base = base[:cut].strip()
             a = agg.setdefault(base, {"launches": 0, "traffic_bytes": 0.0, "dur_us": 0.0})
             a["launches"] += 1
             a["traffic_bytes"] += e["traffic_bytes"]
@@ -82,8 +91,13 @@ def main():
         for a in agg.values():
             a["traffic_bytes_per_launch"] = a["traffic_bytes"] / a["launches"]
             a["dur_us_per_launch"] = a["dur_us"] / a["launches"]
+        doc = {"kernels": agg}
+        if "--meta" in sys.argv:                      # e.g. --meta config=charadessta,queries_in_pass=192
+            for kv in sys.argv[sys.argv.index("--meta") + 1].split(","):
+                k, v = kv.split("=")
+                doc[k] = int(v) if v.isdigit() else v
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
-            json.dump(agg, f, indent=1)
+            json.dump(doc, f, indent=1)
 
 
 if __name__ == "__main__":
