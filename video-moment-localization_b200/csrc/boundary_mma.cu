@@ -328,18 +328,21 @@ boundary_rows_mma_kernel(const float* __restrict__ G, const float* __restrict__ 
 }
 
 // ---- stream:  fbar_ij = sigmoid(fm_ij*fs)*fm_ij for every valid cell;  bu[i] += sum_j A_b[i,j] fbar_ij ----------------
-// One CTA (4 warps) per map row (b, i): warp w takes the row's cells w, w+4, ..., four at a time; a lane owns
-// the 8 consecutive columns {256*q + 8*lane} (one 16-byte load per cell and column group in fast mode).
-// The four partial sums are combined in warp order, so the result does not depend on scheduling.
+// One WARP per map row (b, i), four rows per CTA, no shared memory and no block barrier: a lane owns the 8
+// consecutive columns {256*q + 8*lane} of every cell (one 16-byte load per cell and column group in fast mode),
+// walks the row's cells four at a time (8 independent 16-byte loads in flight per lane) and keeps the row's sum in
+// registers.  The row's attention weights A_b[i, j(cell)] are fetched once per 32 cells (one coalesced load of the
+// cell codes, one gather) and handed out by shuffle, so the per-cell loop has no dependent loads.  Cells are
+// summed in map order j: the result does not depend on scheduling or on the batch.
 template <typename ActT, int NG, bool PRECISE>
 __global__ void __launch_bounds__(128)
 boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const ActT* __restrict__ fm,
                        const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
-                       ActT* __restrict__ fbar, int L, int D, int capacity) {
-  extern __shared__ __align__(16) float sred[];        // [3][D] partial sums of warps 1..3
-  const int grow = blockIdx.x;                         // b * L + i
-  const int b = grow / L;
+                       ActT* __restrict__ fbar, int n_rows, int L, int D, int capacity) {
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int grow = blockIdx.x * 4 + warp;              // b * L + i
+  if (grow >= n_rows) return;
+  const int b = grow / L;
   const int n_lo = row_start[grow], n_hi = min(row_start[grow + 1], capacity);
   if (n_lo >= n_hi) return;                            // empty row: bu stays f_bb + f_b (A_b row is all zero there)
   const float* arow = ab + (size_t)grow * L;
@@ -351,62 +354,50 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
     if (q * 256 + lane * 8 < D) s8[q] = ld8(fs + (size_t)b * D + q * 256 + lane * 8);
   }
   constexpr int CB = 4;
-  for (int n0 = n_lo + warp * CB; n0 < n_hi; n0 += 4 * CB) {
-    f8 m[CB][NG];
-    float a4[CB];
+  for (int seg = n_lo; seg < n_hi; seg += 32) {        // 32 cells of the row per segment
+    const int seg_n = min(32, n_hi - seg);
+    const float a_lane = lane < seg_n ? __ldg(arow + (__ldg(code + seg + lane) & 0xff)) : 0.f;
+    for (int c0 = 0; c0 < seg_n; c0 += CB) {
+      f8 m[CB][NG];
 #pragma unroll
-    for (int u = 0; u < CB; ++u) {
-      const int n = min(n0 + u, n_hi - 1);
-      a4[u] = (n0 + u < n_hi) ? __ldg(arow + (code[n] & 0xff)) : 0.f;
+      for (int u = 0; u < CB; ++u) {
+        const int n = min(seg + c0 + u, n_hi - 1);
 #pragma unroll
-      for (int q = 0; q < NG; ++q) {
+        for (int q = 0; q < NG; ++q) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) m[u][q].v[e] = 0.f;
-        if (q * 256 + lane * 8 < D) m[u][q] = ld8(fm + (size_t)n * D + q * 256 + lane * 8);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < CB; ++u) {
-      if (n0 + u < n_hi) {
-#pragma unroll
-        for (int q = 0; q < NG; ++q)
-          if (q * 256 + lane * 8 < D) {
-            f8 gv;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = m[u][q].v[e], z = x * s8[q].v[e];
-              gv.v[e] = PRECISE ? sigmoidf_(z) * x : __fdividef(x, 1.0f + __expf(-z));
-              bm[q].v[e] = fmaf(a4[u], gv.v[e], bm[q].v[e]);
-            }
-            if (fbar) st8(fbar + (size_t)(n0 + u) * D + q * 256 + lane * 8, gv);
-          }
-      }
-    }
-  }
-  if (warp > 0) {
-#pragma unroll
-    for (int q = 0; q < NG; ++q)
-      if (q * 256 + lane * 8 < D) st8(sred + (size_t)(warp - 1) * D + q * 256 + lane * 8, bm[q]);
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int q = 0; q < NG; ++q)
-      if (q * 256 + lane * 8 < D) {
-        f8 tot = bm[q];
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-          const f8 p = ld8(sred + (size_t)w * D + q * 256 + lane * 8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) tot.v[e] += p.v[e];
+          for (int e = 0; e < 8; ++e) m[u][q].v[e] = 0.f;
+          if (q * 256 + lane * 8 < D) m[u][q] = ld8(fm + (size_t)n * D + q * 256 + lane * 8);
         }
-        float* o = bu + (size_t)grow * D + q * 256 + lane * 8;
-        const f8 base = ld8(o);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) tot.v[e] = base.v[e] + tot.v[e];
-        st8(o, tot);
       }
+#pragma unroll
+      for (int u = 0; u < CB; ++u) {
+        const float a = __shfl_sync(0xffffffffu, a_lane, (c0 + u) & 31);
+        if (c0 + u < seg_n) {                          // warp-uniform
+#pragma unroll
+          for (int q = 0; q < NG; ++q)
+            if (q * 256 + lane * 8 < D) {
+              f8 gv;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float x = m[u][q].v[e], z = x * s8[q].v[e];
+                gv.v[e] = PRECISE ? sigmoidf_(z) * x : __fdividef(x, 1.0f + __expf(-z));
+                bm[q].v[e] = fmaf(a, gv.v[e], bm[q].v[e]);
+              }
+              if (fbar) st8(fbar + (size_t)(seg + c0 + u) * D + q * 256 + lane * 8, gv);
+            }
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int q = 0; q < NG; ++q)
+    if (q * 256 + lane * 8 < D) {
+      float* o = bu + (size_t)grow * D + q * 256 + lane * 8;
+      f8 tot = ld8(o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tot.v[e] = tot.v[e] + bm[q].v[e];
+      st8(o, tot);
+    }
 }
 
 template <bool PRECISE>
@@ -427,8 +418,8 @@ static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, fl
 template <typename ActT, int NG, bool PRECISE>
 static int launch_stream(const float* ab, const float* fs, const void* fm, vml_cells_t cells, float* bu, void* fbar, int B,
                          vml_dims_t d, cudaStream_t st) {
-  boundary_stream_kernel<ActT, NG, PRECISE><<<B * d.L, 128, sizeof(float) * 3 * d.D, st>>>(
-      ab, fs, (const ActT*)fm, cells.code, cells.row_start, bu, (ActT*)fbar, d.L, d.D, cells.capacity);
+  boundary_stream_kernel<ActT, NG, PRECISE><<<ceil_div(B * d.L, 4), 128, 0, st>>>(
+      ab, fs, (const ActT*)fm, cells.code, cells.row_start, bu, (ActT*)fbar, B * d.L, d.L, d.D, cells.capacity);
   return VML_OK;
 }
 
