@@ -81,3 +81,40 @@ def test_adam_step_matches_torch():
         ours.step(); ref.step()
     for p, r in zip(ps, ref_ps):
         assert (p - r).abs().max() < 1e-6
+
+
+def test_fused_adam_checkpoint_round_trips_with_torch_adam():
+    """optimizer.state_dict() of the reference's checkpoints (main.py:270-274) moves between FusedAdam and torch.optim.Adam."""
+    from vml_b200.optim import FusedAdam
+    torch.manual_seed(2)
+    shapes = [(40, 9), (13,), (3, 5, 2)]
+    ps = [torch.randn(*sh, device="cuda", requires_grad=True) for sh in shapes]
+    ref_ps = [p.detach().clone().requires_grad_(True) for p in ps]
+    ours, ref = FusedAdam(ps, lr=3e-3), torch.optim.Adam(ref_ps, lr=3e-3)
+
+    def step_both(a, a_ps, b, b_ps):
+        for p, r in zip(a_ps, b_ps):
+            gr = torch.randn_like(p)
+            p.grad, r.grad = gr.clone(), gr.clone()
+        a.step(); b.step()
+
+    for _ in range(2):
+        step_both(ours, ps, ref, ref_ps)
+    # ours -> stock Adam
+    ps2 = [p.detach().clone().requires_grad_(True) for p in ps]
+    stock = torch.optim.Adam(ps2, lr=1.0)
+    stock.load_state_dict(ours.state_dict())
+    assert stock.param_groups[0]["lr"] == 3e-3
+    # stock Adam -> ours
+    ps3 = [r.detach().clone().requires_grad_(True) for r in ref_ps]
+    mine = FusedAdam(ps3, lr=1.0)
+    mine.load_state_dict(ref.state_dict())
+    assert mine.t == 2 and mine.lr == 3e-3
+    for _ in range(2):
+        grads = [torch.randn_like(p) for p in ps]
+        for group in (ps, ref_ps, ps2, ps3):
+            for p, g in zip(group, grads):
+                p.grad = g.clone()
+        ours.step(); ref.step(); stock.step(); mine.step()
+    for a, b, c, d in zip(ps, ref_ps, ps2, ps3):
+        assert (a - b).abs().max() < 1e-6 and (c - b).abs().max() < 1e-6 and (d - b).abs().max() < 1e-6

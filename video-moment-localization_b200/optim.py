@@ -31,6 +31,49 @@ class FusedAdam:
                 p.data = self.flat[o:o + k].view(p.shape)            # the parameter now lives inside the flat buffer
                 o += k
 
+    # -- checkpoint compatibility (main.py:270-274 saves {"epoch", "model", "optimizer": optimizer.state_dict()}) -----
+    @property
+    def param_groups(self):
+        return [{"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.params)))}]
+
+    def state_dict(self):
+        """Same layout as ``torch.optim.Adam.state_dict()``: loads into a stock Adam over the same parameter list
+        (and vice versa through ``load_state_dict``), so checkpoints move freely between the two."""
+        state, o = {}, 0
+        if self.t > 0:
+            for i, p in enumerate(self.params):
+                k = p.numel()
+                state[i] = {"step": torch.tensor(float(self.t)), "exp_avg": self.m[o:o + k].view(p.shape).clone(),
+                            "exp_avg_sq": self.v[o:o + k].view(p.shape).clone()}
+                o += k
+        return {"state": state, "param_groups": self.param_groups}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if sum(len(g["params"]) for g in groups) != len(self.params):
+            raise ValueError("loaded state dict has a different number of parameters")
+        g0 = groups[0]
+        self.lr, self.betas, self.eps = float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"])
+        if any(g.get("weight_decay", 0) or g.get("amsgrad", False) for g in groups):
+            raise L_.VmlError("FusedAdam implements plain Adam only (no weight decay / amsgrad)")
+        order = [i for g in groups for i in g["params"]]
+        self.m.zero_(); self.v.zero_()
+        steps, o = set(), 0
+        with torch.no_grad():
+            for idx, p in zip(order, self.params):
+                k = p.numel()
+                st = sd["state"].get(idx)
+                if st is not None:
+                    self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                    self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(float(st["step"])))
+                o += k
+        if len(steps) > 1:
+            raise L_.VmlError("FusedAdam keeps one step counter; the loaded state has several")
+        self.t = steps.pop() if steps else 0
+
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None
