@@ -327,6 +327,237 @@ boundary_rows_mma_kernel(const float* __restrict__ G, const float* __restrict__ 
   }
 }
 
+// ---- gate + rows in ONE kernel for maps with L <= 16 (one 16-row block per sample, e.g. Charades) ---------------------
+// Same arithmetic, in the same order, as boundary_gate_mma_kernel followed by boundary_rows_mma_kernel (JR = 16): the
+// gated rows G stay in shared memory (over the dead key / word tiles) instead of a round trip through global memory,
+// and one launch + one staging pass disappear.  One CTA per sample.
+template <bool PRECISE>
+__global__ void __launch_bounds__(BMM_THREADS)
+boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
+                          const float* __restrict__ fs, const float* __restrict__ fb, const uint8_t* __restrict__ qmask,
+                          const uint8_t* __restrict__ lmask, float* __restrict__ G, float* __restrict__ prob_out,
+                          float* __restrict__ u_out, float* __restrict__ bu, float* __restrict__ ab_out, int L, int Nq, int D) {
+  extern __shared__ __align__(16) float sg[];
+  const int DS = D + 4;
+  float* Ks = sg;                                     // [Nq][DS]  kbt          (later: G rows, [16][DS])
+  float* Ws = Ks + (size_t)Nq * DS;                   // [Nq][DS]  fw
+  float* Xs = sg + (size_t)max(2 * Nq, BMM_ROWS) * DS;   // [16][DS]  the sample's fb rows (later: f_bb + f_b)
+  float* Gs = sg;
+  __shared__ float part[BMM_WARPS][BMM_ROWS][BMM_MAXQ + 1];
+  __shared__ float prob[BMM_ROWS][BMM_MAXQ + 4];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
+  const int dq = D / 4;
+  for (int e = tid; e < Nq * dq; e += BMM_THREADS) {
+    const int k = e / dq, c4 = (e - k * dq) * 4;
+    *reinterpret_cast<float4*>(Ks + (size_t)k * DS + c4) = __ldg(reinterpret_cast<const float4*>(qproj + ((size_t)b * Nq + k) * ld + off_kbt + c4));
+    *reinterpret_cast<float4*>(Ws + (size_t)k * DS + c4) = __ldg(reinterpret_cast<const float4*>(fw + ((size_t)b * Nq + k) * D + c4));
+  }
+  for (int e = tid; e < BMM_ROWS * dq; e += BMM_THREADS) {
+    const int rr = e / dq, c4 = (e - rr * dq) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < L) v = __ldg(reinterpret_cast<const float4*>(fb + ((size_t)b * L + rr) * D + c4));
+    *reinterpret_cast<float4*>(Xs + (size_t)rr * DS + c4) = v;
+  }
+  __syncthreads();
+  const int rA = g, rB = g + 8;
+  const bool vA = rA < L, vB = rB < L;
+  const int nq_tiles = (Nq + 7) / 8;
+  const int dpw = D / BMM_WARPS;                       // D columns (or K range) owned by this warp
+  const int ntd = dpw / 8;
+  // ---- word scores, split over K ---------------------------------------------------------------------
+  {
+    float acc[BMM_MAXQ / 8][4];
+#pragma unroll
+    for (int n = 0; n < BMM_MAXQ / 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    for (int k0 = warp * dpw; k0 < (warp + 1) * dpw; k0 += 8) {
+      const float a[4] = {Xs[g * DS + k0 + t], Xs[(g + 8) * DS + k0 + t], Xs[g * DS + k0 + t + 4], Xs[(g + 8) * DS + k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < BMM_MAXQ / 8; ++n) {
+        if (n < nq_tiles) {
+          const int w = n * 8 + g;
+          float bf[2] = {0.f, 0.f};
+          if (w < Nq) { bf[0] = Ks[(size_t)w * DS + k0 + t]; bf[1] = Ks[(size_t)w * DS + k0 + t + 4]; }
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < BMM_MAXQ / 8; ++n) {
+      part[warp][g][n * 8 + 2 * t] = acc[n][0]; part[warp][g][n * 8 + 2 * t + 1] = acc[n][1];
+      part[warp][g + 8][n * 8 + 2 * t] = acc[n][2]; part[warp][g + 8][n * 8 + 2 * t + 1] = acc[n][3];
+    }
+  }
+  __syncthreads();
+  // ---- masked softmax over the words (models.py:143-150); warp w owns rows 2w, 2w+1, lane = word ---------
+  {
+    const float mk = (lane < Nq && qmask[(size_t)b * Nq + lane]) ? 1.f : 0.f;
+    const float beta = lane < Nq ? qproj[((size_t)b * Nq + lane) * ld + off_betab] : 0.f;
+    const float sqrt_d = sqrtf((float)D);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = 2 * warp + rr;
+      float s = 0.f;
+#pragma unroll
+      for (int p = 0; p < BMM_WARPS; ++p) s += part[p][row][lane];
+      float sv = (s + beta) / sqrt_d;
+      sv = sv * mk;
+      if (mk == 0.f) sv = -1e9f;                       // masked_fill(mask == 0, -1e9)
+      if (lane >= Nq) sv = -INFINITY;                  // not a word at all
+      const float mx = warp_max(sv);
+      const float ex = lane < Nq ? expf(sv - mx) : 0.f;
+      prob[row][lane] = ex / warp_sum(ex);
+      if (prob_out && lane < Nq && row < L) prob_out[((size_t)b * L + row) * Nq + lane] = prob[row][lane];   // saved for backward
+    }
+  }
+  __syncthreads();
+  // ---- attended words for this warp's D/8 columns, gate; G to global now, to shared memory once Ws is dead ----
+  float gA[BMM_MAXD64][2], gB[BMM_MAXD64][2];
+  {
+    float acc[BMM_MAXD64][4];
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    for (int k0 = 0; k0 < nq_tiles * 8; k0 += 8) {
+      const float a[4] = {prob[g][k0 + t], prob[g + 8][k0 + t], prob[g][k0 + t + 4], prob[g + 8][k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < BMM_MAXD64; ++n) {
+        if (n < ntd) {
+          const int col = warp * dpw + n * 8 + g;
+          float bf[2];
+          bf[0] = (k0 + t < Nq) ? Ws[(size_t)(k0 + t) * DS + col] : 0.f;
+          bf[1] = (k0 + t + 4 < Nq) ? Ws[(size_t)(k0 + t + 4) * DS + col] : 0.f;
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+    const float lmA = (vA && lmask[(size_t)b * L + rA]) ? 1.f : 0.f, lmB = (vB && lmask[(size_t)b * L + rB]) ? 1.f : 0.f;
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n) {
+      gA[n][0] = gA[n][1] = gB[n][0] = gB[n][1] = 0.f;
+      if (n < ntd) {
+        const int col = warp * dpw + n * 8 + 2 * t;
+        const float2 s2 = __ldg(reinterpret_cast<const float2*>(fs + (size_t)b * D + col));
+        if (vA) {
+          const float2 x = *reinterpret_cast<const float2*>(Xs + g * DS + col);
+          gA[n][0] = x.x * (acc[n][0] * lmA + s2.x); gA[n][1] = x.y * (acc[n][1] * lmA + s2.y);
+          *reinterpret_cast<float2*>(G + ((size_t)b * L + rA) * D + col) = make_float2(gA[n][0], gA[n][1]);
+          if (u_out) *reinterpret_cast<float2*>(u_out + ((size_t)b * L + rA) * D + col) = make_float2(acc[n][0] * lmA + s2.x, acc[n][1] * lmA + s2.y);
+        }
+        if (vB) {
+          const float2 x = *reinterpret_cast<const float2*>(Xs + (g + 8) * DS + col);
+          gB[n][0] = x.x * (acc[n][2] * lmB + s2.x); gB[n][1] = x.y * (acc[n][3] * lmB + s2.y);
+          *reinterpret_cast<float2*>(G + ((size_t)b * L + rB) * D + col) = make_float2(gB[n][0], gB[n][1]);
+          if (u_out) *reinterpret_cast<float2*>(u_out + ((size_t)b * L + rB) * D + col) = make_float2(acc[n][2] * lmB + s2.x, acc[n][3] * lmB + s2.y);
+        }
+      }
+    }
+  }
+  __syncthreads();                                     // every warp is done with Ks / Ws: G rows take their place
+#pragma unroll
+  for (int n = 0; n < BMM_MAXD64; ++n) {
+    if (n < ntd) {
+      const int col = warp * dpw + n * 8 + 2 * t;
+      *reinterpret_cast<float2*>(Gs + g * DS + col) = make_float2(gA[n][0], gA[n][1]);
+      *reinterpret_cast<float2*>(Gs + (g + 8) * DS + col) = make_float2(gB[n][0], gB[n][1]);
+    }
+  }
+  __syncthreads();
+  // ================= rows part (boundary_rows_mma_kernel with a single key block) =================
+  const int LP = (L + 7) & ~7;                         // 8 or 16
+  const int ntl = LP / 8;
+  {
+    float acc[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    for (int k0 = warp * dpw; k0 < (warp + 1) * dpw; k0 += 8) {
+      const float a[4] = {Gs[g * DS + k0 + t], Gs[(g + 8) * DS + k0 + t], Gs[g * DS + k0 + t + 4], Gs[(g + 8) * DS + k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        if (n < ntl) {
+          const float bf[2] = {Gs[(size_t)(n * 8 + g) * DS + k0 + t], Gs[(size_t)(n * 8 + g) * DS + k0 + t + 4]};
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      if (n < ntl) {
+        part[warp][g][n * 8 + 2 * t] = acc[n][0]; part[warp][g][n * 8 + 2 * t + 1] = acc[n][1];
+        part[warp][g + 8][n * 8 + 2 * t] = acc[n][2]; part[warp][g + 8][n * 8 + 2 * t + 1] = acc[n][3];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- masked softmax over the keys (models.py:176-184); warp w owns rows 2w, 2w+1; prob[][] now holds A_b -------
+  {
+    const float sqrt_d = sqrtf((float)D);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = 2 * warp + rr;
+      const bool row_on = row < L && lmask[(size_t)b * L + row] != 0;
+      float sc = -INFINITY;
+      if (lane < LP) {
+        float s = 0.f;
+#pragma unroll
+        for (int p = 0; p < BMM_WARPS; ++p) s += part[p][row][lane];
+        if (lane < L) {
+          const float mk = lmask[(size_t)b * L + lane] ? 1.f : 0.f;
+          sc = (s / sqrt_d) * mk;
+          if (mk == 0.f) sc = -1e9f;
+        }
+      }
+      const float mx = warp_max(sc);
+      const float ex = lane < L ? expf(sc - mx) : 0.f;
+      const float den = warp_sum(ex);
+      if (lane < LP) prob[row][lane] = row_on ? ex / den : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- f_bb = A_b . fb for this warp's D/8 columns; bu = f_bb + f_b -------------------------------------------
+  {
+    float acc[BMM_MAXD64][4];
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    for (int k0 = 0; k0 < LP; k0 += 8) {
+      const float a[4] = {prob[g][k0 + t], prob[g + 8][k0 + t], prob[g][k0 + t + 4], prob[g + 8][k0 + t + 4]};
+#pragma unroll
+      for (int n = 0; n < BMM_MAXD64; ++n) {
+        if (n < ntd) {
+          const int col = warp * dpw + n * 8 + g;
+          const float bf[2] = {Xs[(size_t)(k0 + t) * DS + col], Xs[(size_t)(k0 + t + 4) * DS + col]};
+          mma_16x8x8<PRECISE>(acc[n], a, bf);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < BMM_MAXD64; ++n) {
+      if (n < ntd) {
+        const int col = warp * dpw + n * 8 + 2 * t;
+        if (vA) {
+          const float2 x = *reinterpret_cast<const float2*>(Xs + g * DS + col);
+          *reinterpret_cast<float2*>(bu + ((size_t)b * L + rA) * D + col) = make_float2(acc[n][0] + x.x, acc[n][1] + x.y);
+        }
+        if (vB) {
+          const float2 x = *reinterpret_cast<const float2*>(Xs + (g + 8) * DS + col);
+          *reinterpret_cast<float2*>(bu + ((size_t)b * L + rB) * D + col) = make_float2(acc[n][2] + x.x, acc[n][3] + x.y);
+        }
+      }
+    }
+  }
+  for (int e = tid; e < BMM_ROWS * LP; e += BMM_THREADS) {
+    const int rr = e / LP, j = e - rr * LP;
+    if (rr < L && j < L) ab_out[((size_t)b * L + rr) * L + j] = prob[rr][j];
+  }
+}
+
 // ---- stream:  fbar_ij = sigmoid(fm_ij*fs)*fm_ij for every valid cell;  bu[i] += sum_j A_b[i,j] fbar_ij ----------------
 // One WARP per map row (b, i), four rows per CTA, no shared memory and no block barrier: a lane owns the 8
 // consecutive columns {256*q + 8*lane} of every cell (one 16-byte load per cell and column group in fast mode),
@@ -431,6 +662,21 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   VML_CHECK_ARG(g_scratch != nullptr && ab_scratch != nullptr);
   static bool reg = (register_kernel("boundary_gate_mma_kernel"), register_kernel("boundary_rows_mma_kernel"),
                      register_kernel("boundary_stream_kernel"), true); (void)reg;
+  int rc = VML_OK;
+  if (d.L <= BMM_ROWS) {
+    // one row block per sample: gate + rows in one launch, G never leaves the SM
+    static bool reg2 = (register_kernel("boundary_gate_rows_kernel"), true); (void)reg2;
+    const int rows_kw = 2 * d.Nq > BMM_ROWS ? 2 * d.Nq : BMM_ROWS;
+    const size_t smem_f = sizeof(float) * (size_t)(rows_kw + BMM_ROWS) * (d.D + 4);
+    if (prec == VML_FP32) {
+      VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<true>), (size_t)((int)smem_f)));
+      boundary_gate_rows_kernel<true><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D);
+    } else {
+      VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<false>), (size_t)((int)smem_f)));
+      boundary_gate_rows_kernel<false><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D);
+    }
+    count_launches(-1);                                  // two launches in this branch (VML_LAUNCHED(3) below)
+  } else {
   dim3 grid(ceil_div(d.L, BMM_ROWS), B);
   const size_t smem_g = sizeof(float) * (size_t)(2 * d.Nq + BMM_ROWS) * (d.D + 4);
   if (prec == VML_FP32) {
@@ -440,9 +686,10 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
     VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_mma_kernel<false>), (size_t)((int)smem_g)));
     boundary_gate_mma_kernel<false><<<grid, BMM_THREADS, smem_g, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, d.L, d.Nq, d.D);
   }
-  int rc = prec == VML_FP32 ? launch_rows<true>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st)
-                            : launch_rows<false>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st);
+  rc = prec == VML_FP32 ? launch_rows<true>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st)
+                        : launch_rows<false>(g_scratch, fb, lmask, bu, ab_scratch, B, d, st);
   if (rc) return rc;
+  }
   const int ng = ceil_div(d.D, 256);
   if (prec == VML_FP32) rc = ng <= 1 ? launch_stream<float, 1, true>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st)
                                      : launch_stream<float, 2, true>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st);
