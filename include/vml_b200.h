@@ -96,6 +96,14 @@ VML_API int vml_ingest(const float* video_features, const float* query_features,
                        void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out, uint8_t* lmask_out,
                        uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad, int q_kpad,
                        int prec, void* stream);
+/* Same, for callers that keep the clip features / word vectors as bf16 on the host (half the H2D bytes of a step;
+ * in VML_BF16 mode the operands are bit-identical to those vml_ingest makes from the fp32 tensors, because the
+ * fp32 -> bf16 rounding is round-to-nearest on either side of the copy). */
+VML_API int vml_ingest_bf16(const void* video_features, const void* query_features, const uint8_t* video_mask,
+                            const uint8_t* query_mask, const uint8_t* length_mask, const uint8_t* moment_mask,
+                            const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
+                            uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d,
+                            int v_kpad, int q_kpad, int prec, void* stream);
 
 /* ---- dense contractions --------------------------------------------------------------- */
 

@@ -90,3 +90,42 @@ def test_overlap_matches_serial_bitwise():
         o = model(*[b[k] for k in synth.MODEL_INPUT_KEYS], overlap=True)
         for x, y in zip(a, o):
             assert torch.equal(x, y)
+
+
+def test_bf16_host_features_are_bit_identical_in_bf16_mode():
+    """Half-width host features (vml_ingest_bf16): the fp32 -> bf16 rounding is round-to-nearest on either side of the
+    H2D copy, so in bf16 precision every score is bit-identical to the fp32-host path -- through the module API and
+    through the pipeline's blob path (generic first pass + recorded fast path), counts included."""
+    from vml_b200.pipeline import pack_host_batch
+    cfg = CONFIGS["charadessta"]
+    model = model_for(cfg, "bf16")
+    batches = [synth.make_batch(cfg, 8, 600 + i) for i in range(7)]
+    d = {k: v.cuda() for k, v in batches[0].items()}
+    want = model(*[d[k] for k in synth.MODEL_INPUT_KEYS])
+    want = [t.clone() for t in want]
+    d16 = dict(d, video_features=d["video_features"].bfloat16(), query_features=d["query_features"].bfloat16())
+    got = model(*[d16[k] for k in synth.MODEL_INPUT_KEYS])
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    pipes = []
+    for dt in (None, torch.bfloat16):
+        pipe = ScoringPipeline(model, slots=2, coalesce=2)
+        for b in batches:
+            pipe.submit(pack_host_batch(b, feature_dtype=dt), from_host=True)
+        pipes.append(pipe)
+    r0, r1 = pipes[0].result(), pipes[1].result()          # result() flushes the partial last group and synchronises
+    assert r0 == r1 and torch.equal(pipes[0].counts.cpu(), pipes[1].counts.cpu())
+    blob16 = pack_host_batch(batches[0], feature_dtype=torch.bfloat16)["_blob"].numel()
+    assert blob16 < 0.55 * pack_host_batch(batches[0])["_blob"].numel()
+
+
+def test_fp32_mode_accepts_bf16_host_features():
+    """fp32 validation mode with bf16 inputs == fp32 mode on the same values widened to float32."""
+    cfg = CONFIGS["tiny"]
+    model = model_for(cfg, "fp32")
+    d = {k: v.cuda() for k, v in synth.make_batch(cfg, 5, 610).items()}
+    v16, q16 = d["video_features"].bfloat16(), d["query_features"].bfloat16()
+    a = model(v16, d["video_mask"], q16, d["query_mask"], d["length_mask"], d["moment_mask"])
+    b = model(v16.float(), d["video_mask"], q16.float(), d["query_mask"], d["length_mask"], d["moment_mask"])
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

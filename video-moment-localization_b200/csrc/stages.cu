@@ -158,7 +158,7 @@ int cast_pad(const float* src, void* dst, int64_t rows, int k, int k_pad, cudaSt
 // replayed CUDA graph.
 // =====================================================================================
 struct IngestArgs {
-  const float* src[2];   // video_features [rows0, k0], query_features [rows1, k1]
+  const void* src[2];    // video_features [rows0, k0], query_features [rows1, k1]: float, or bf16 when SRC16
   void* dst[2];          // bf16 [rows, kpad] or float [rows, k]; nullptr = skip
   int64_t rows[2];
   int k[2], kpad[2];
@@ -169,7 +169,7 @@ struct IngestArgs {
   const uint8_t* qmask; int32_t* qlen; int B, Nq;
 };
 
-template <bool BF16>
+template <bool BF16, bool SRC16>
 __global__ void __launch_bounds__(256)
 ingest_kernel(IngestArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -178,12 +178,20 @@ ingest_kernel(IngestArgs a) {
     if (!a.dst[s]) continue;
     const int k = a.k[s], kp4 = a.kpad[s] / 4;
     const int64_t total = a.rows[s] * kp4;
-    const float* src = a.src[s];
+    const float* src = reinterpret_cast<const float*>(a.src[s]);
+    const bf16* src16 = reinterpret_cast<const bf16*>(a.src[s]);
     for (int64_t e = tid; e < total; e += nth) {
       const int64_t r = e / kp4;
       const int c = (int)(e - r * kp4) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c + 3 < k) v = __ldg(reinterpret_cast<const float4*>(src + r * k + c));
+      if (SRC16) {                                     // half-width host features (k % 4 == 0: 8-byte aligned groups)
+        if (c + 3 < k) v = ld4(src16 + r * k + c);
+        else {
+          if (c < k) v.x = to_f(src16[r * k + c]);
+          if (c + 1 < k) v.y = to_f(src16[r * k + c + 1]);
+          if (c + 2 < k) v.z = to_f(src16[r * k + c + 2]);
+        }
+      } else if (c + 3 < k) v = __ldg(reinterpret_cast<const float4*>(src + r * k + c));
       else {
         if (c < k) v.x = src[r * k + c];
         if (c + 1 < k) v.y = src[r * k + c + 1];
@@ -208,7 +216,7 @@ ingest_kernel(IngestArgs a) {
     }
 }
 
-int ingest(const float* vf, const float* qf, const uint8_t* vmask, const uint8_t* qmask, const uint8_t* lmask,
+int ingest(const void* vf, const void* qf, int src_bf16, const uint8_t* vmask, const uint8_t* qmask, const uint8_t* lmask,
            const uint8_t* mmask, const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
            uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad,
            int q_kpad, int prec, cudaStream_t st) {
@@ -228,8 +236,13 @@ int ingest(const float* vf, const float* qf, const uint8_t* vmask, const uint8_t
   const int64_t total = (v_out ? a.rows[0] * (v_kpad / 4) : 0) + (q_out ? a.rows[1] * (q_kpad / 4) : 0) + a.mbytes[3];
   const int64_t want = ceil_div64(total, 256 * 4), cap = (int64_t)kNumSMs * 8;
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-  if (prec == VML_BF16) ingest_kernel<true><<<grid, 256, 0, st>>>(a);
-  else ingest_kernel<false><<<grid, 256, 0, st>>>(a);
+  if (prec == VML_BF16) {
+    if (src_bf16) ingest_kernel<true, true><<<grid, 256, 0, st>>>(a);
+    else ingest_kernel<true, false><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (src_bf16) ingest_kernel<false, true><<<grid, 256, 0, st>>>(a);
+    else ingest_kernel<false, false><<<grid, 256, 0, st>>>(a);
+  }
   VML_LAUNCHED(1);
   return VML_OK;
 }

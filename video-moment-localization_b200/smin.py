@@ -293,8 +293,10 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
     assert static or (b_off == 0 and Bt == B)
     T, Lm, d0, Nq = dims.T, dims.L, dims.d0, dims.Nq
     bf = prec == L_.BF16
-    vf = video_features.float().contiguous()
-    qf = query_features.float().contiguous()
+    # host-side bf16 features (half the H2D bytes) are taken as they are; anything else goes through float32
+    src16 = video_features.dtype == torch.bfloat16 and query_features.dtype == torch.bfloat16
+    vf = video_features.contiguous() if src16 else video_features.float().contiguous()
+    qf = query_features.contiguous() if src16 else query_features.float().contiguous()
     vmask, qmask = _mask_u8(video_mask, (B, T)), _mask_u8(query_mask, (B, Nq))
     lmask, mmask = _mask_u8(length_mask, (B, Lm)), _mask_u8(moment_mask, (B, Lm, Lm))
     vk = _round_up(d0, 8) if bf else d0
@@ -320,8 +322,11 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
 
     args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
             *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, stream_ptr())
-    call("vml_ingest", *args)
+    call("vml_ingest_bf16" if src16 else "vml_ingest", *args)
+    inp["_ingest_fn"] = "vml_ingest_bf16" if src16 else "vml_ingest"
     inp["_ingest_args"] = args          # ScoringPipeline re-issues this launch with new source pointers (its per-step fast path)
+    if v_out is None and src16:          # fp32 mode, eager call: the operands are the caller's tensors themselves
+        vf, qf = vf.float(), qf.float()
     inp.update(v=v_out if v_out is not None else vf, q=q_out if q_out is not None else qf, qlen=qlen,
                vmask=m_out[0] if static else vmask, qmask=m_out[1] if static else qmask,
                lmask=m_out[2] if static else lmask, mmask=m_out[3] if static else mmask,
