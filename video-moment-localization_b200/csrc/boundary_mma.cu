@@ -662,7 +662,7 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   VML_CHECK_ARG(g_scratch != nullptr && ab_scratch != nullptr);
   static bool reg = (register_kernel("boundary_gate_mma_kernel"), register_kernel("boundary_rows_mma_kernel"),
                      register_kernel("boundary_stream_kernel"), true); (void)reg;
-  int rc = VML_OK;
+  int rc = VML_OK, n_launched = 3;
   if (d.L <= BMM_ROWS) {
     // one row block per sample: gate + rows in one launch, G never leaves the SM
     static bool reg2 = (register_kernel("boundary_gate_rows_kernel"), true); (void)reg2;
@@ -675,7 +675,7 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
       VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<false>), (size_t)((int)smem_f)));
       boundary_gate_rows_kernel<false><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D);
     }
-    count_launches(-1);                                  // two launches in this branch (VML_LAUNCHED(3) below)
+    n_launched = 2;
   } else {
   dim3 grid(ceil_div(d.L, BMM_ROWS), B);
   const size_t smem_g = sizeof(float) * (size_t)(2 * d.Nq + BMM_ROWS) * (d.D + 4);
@@ -696,7 +696,7 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   else rc = ng <= 1 ? launch_stream<bf16, 1, false>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st)
                     : launch_stream<bf16, 2, false>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st);
   if (rc) return rc;
-  VML_LAUNCHED(3);
+  VML_LAUNCHED(n_launched);
   return VML_OK;
 }
 

@@ -15,6 +15,7 @@ whole split (the loop of main.py:168-189), with the host taken out of the steady
 """
 from __future__ import annotations
 
+from collections import deque
 from typing import Dict, List, Optional
 
 import torch
@@ -155,6 +156,7 @@ class ScoringPipeline:
         # per-step fast path: the ingest launch of (slot, position) re-issued with new source pointers -- ~20 us of host
         # work per submitted batch instead of ~180 us through the generic module path (measured; the device step is ~210 us)
         self._plans: Dict[tuple, "_Plan"] = {}
+        self._inflight = deque()               # (event, pinned host blob) of H2D copies that may still be running
         self._ingest_fn = getattr(L_.load(), "vml_ingest")
         self._h2d_fn = getattr(L_.load(), "vml_copy_h2d_async")
 
@@ -222,6 +224,8 @@ class ScoringPipeline:
             self._next_staging = (self._next_staging + 1) % len(self.staging)
             blob = batch.get("_blob")
             if stg.buf is None or (blob is not None and (stg.blob is None or stg.blob.numel() != blob.numel())):
+                if stg.buf is not None:                       # layout change mid-run (rare): let the old area drain first
+                    torch.cuda.synchronize(self.device)
                 if blob is not None:                          # one device blob mirroring the host blob: one copy per batch
                     stg.blob = torch.empty(blob.numel(), dtype=torch.uint8, device=self.device)
                     stg.buf = _blob_views(stg.blob, batch)
@@ -231,13 +235,21 @@ class ScoringPipeline:
             if stg.used:
                 self.copy_stream.wait_event(stg.free)         # the previous consumer's ingest has read it
             if blob is not None and stg.blob is not None:
+                # raw cudaMemcpyAsync: PyTorch's pinned-memory allocator does not see it, so the blob is kept alive
+                # (self._inflight) until its copy is known to have landed -- checked with event queries, never by blocking
                 L_.check(self._h2d_fn(stg.blob.data_ptr(), blob.data_ptr(), blob.numel(), self.copy_stream.cuda_stream),
                          "vml_copy_h2d_async")
+                stg.ready = torch.cuda.Event()
+                stg.ready.record(self.copy_stream)
+                self._inflight.append((stg.ready, blob))
+                while self._inflight and self._inflight[0][0].query():
+                    self._inflight.popleft()
             else:
                 with torch.cuda.stream(self.copy_stream):
                     for k in INPUT_KEYS:
                         stg.buf[k].copy_(batch[k], non_blocking=True)
-            stg.ready.record(self.copy_stream)
+            if blob is None or stg.blob is None:
+                stg.ready.record(self.copy_stream)
             slot.stream.wait_event(stg.ready)
             src = stg.buf
         else:
@@ -247,6 +259,8 @@ class ScoringPipeline:
                 plan.ev.record(torch.cuda.current_stream(self.device))
                 slot.stream.wait_event(plan.ev)               # the caller's tensors are ready
                 ptrs = tuple(batch[k].data_ptr() for k in _INGEST_ORDER)
+                for k in _INGEST_ORDER:                       # read on the slot's stream: no reuse of the memory before that
+                    batch[k].record_stream(slot.stream)
             else:
                 ptrs = stg.src_ptrs
             L_.check(plan.fn(*ptrs, *plan.tail), plan.fn_name)
@@ -260,6 +274,9 @@ class ScoringPipeline:
                 with torch.cuda.stream(slot.stream):
                     slot.inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True,
                                            b_off=slot.fill * B, b_total=self.coalesce * B)
+                if not from_host:
+                    for k in INPUT_KEYS:
+                        src[k].record_stream(slot.stream)
             if _canonical(src) is not None:
                 self._plans[(self._cur, slot.fill)] = _Plan(slot.inp, slot.stream.cuda_stream)
         if from_host:
@@ -300,6 +317,7 @@ class ScoringPipeline:
         self.flush()
         for s in self.slots:
             s.stream.synchronize()
+        self._inflight.clear()                 # every copy has landed: the host blobs may go
 
     def result(self, normalize: bool = True):
         """Recall table like main.py:163,189,209 (one D2H read)."""
