@@ -28,11 +28,16 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+CLEAN = False   # --clean-flush: after the 256 MiB memset, read a second 256 MiB buffer so that L2 ends up full of CLEAN lines
+
+
 def cold_time(fn, flush, reps=8):
     fn(); torch.cuda.synchronize()
     tot = 0.0
     for _ in range(reps):
         flush.zero_()
+        if CLEAN:
+            _flush_read.sum()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); e1.synchronize()
         tot += e0.elapsed_time(e1)
@@ -43,11 +48,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--clean-flush", action="store_true",
+                    help="memset flush followed by a 256 MiB read: the timed kernel then does not pay the write-back of the flush's dirty lines")
     args = ap.parse_args()
     L_.load()
     dev = torch.device("cuda")
     hbm, tf, src = peaks()
     flush = torch.empty(256 * 2**20, device=dev, dtype=torch.uint8)
+    global CLEAN, _flush_read
+    CLEAN = args.clean_flush
+    _flush_read = torch.zeros(64 * 2**20, device=dev, dtype=torch.float32)
     D, C = 512, 4
     rows = []
     Ns = (16, 64) if args.quick else (16, 32, 64, 128)
@@ -89,7 +99,7 @@ def main():
                 print(json.dumps(row), flush=True)
                 del op, mu, fm, fv
                 torch.cuda.empty_cache()
-    out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "timing": "CUDA events, L2 flushed (256 MiB memset) before every launch, mean of 8",
+    out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "timing": "CUDA events, L2 flushed (256 MiB memset" + (" + 256 MiB read: clean lines" if CLEAN else "") + ") before every launch, mean of 8",
            "rows": rows}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(out, open(args.out, "w"), indent=1)

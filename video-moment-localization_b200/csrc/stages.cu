@@ -2,6 +2,7 @@
 // content-word attention, boundary unit, moment-unit operand build, localization.
 // Each kernel is templated on the activation storage type (float = validation mode,
 // bf16 = fast mode); all arithmetic is fp32.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vml {
@@ -377,6 +378,10 @@ int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc,
   while (dslice % 16 == 0 && (dslice > 256 || (bytes(dslice) > 48 * 1024 && dslice > 64))) dslice /= 2;
   while (dslice % 16 == 0 && bytes(dslice) > 200 * 1024) dslice /= 2;
   while (dslice % 16 == 0 && dslice > 8 && (int64_t)B * (d.D / dslice) < 2 * kNumSMs) dslice /= 2;
+  if (const char* ov = getenv("VML_SPAN_DSLICE")) {     // tuning knob (tools/sweep.py): force the slice width
+    const int v = atoi(ov);
+    if (v >= 8 && v <= 256 && d.D % v == 0 && v % 8 == 0 && bytes(v) <= 200 * 1024) dslice = v;
+  }
   VML_CHECK_ARG(bytes(dslice) <= 200 * 1024 && d.D % dslice == 0 && dslice % 8 == 0 && dslice <= 256);
   const size_t smem = bytes(dslice);
   const int threads = smem > 75 * 1024 ? 512 : 256;
