@@ -129,3 +129,34 @@ def test_fp32_mode_accepts_bf16_host_features():
     b = model(v16.float(), d["video_mask"], q16.float(), d["query_mask"], d["length_mask"], d["moment_mask"])
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("from_host", [False, True])
+def test_pipeline_scores_a_ragged_tail_batch(from_host):
+    """len(split) % batch != 0 (the last batch of main.py:168-189): a batch of another size is scored eagerly into
+    the same counters, before and after full groups, with its own read-back."""
+    from vml_b200.pipeline import pack_host_batch
+    cfg = CONFIGS["charadessta"]
+    model = model_for(cfg, "bf16")
+    sizes = [8, 8, 8, 5, 8, 8, 3]
+    batches = [synth.make_batch(cfg, n, 700 + i) for i, n in enumerate(sizes)]
+    acc = RecallAccumulator(torch.device("cuda"))
+    per_batch = []
+    for b in batches:
+        d = {k: v.cuda() for k, v in b.items()}
+        out = model(*[d[k] for k in synth.MODEL_INPUT_KEYS])
+        one = RecallAccumulator(torch.device("cuda"))
+        one.update(out[0], out[1], out[2], d["moment_mask"], d["sm"])
+        acc.update(out[0], out[1], out[2], d["moment_mask"], d["sm"])
+        per_batch.append(one.counts.cpu())
+    pipe = ScoringPipeline(model, slots=2, coalesce=2)
+    rb = [torch.zeros(2, 4, dtype=torch.int64).pin_memory() for _ in sizes]
+    tickets = []
+    for i, b in enumerate(batches):
+        src = pack_host_batch(b) if from_host else {k: v.cuda() for k, v in b.items()}
+        tickets.append(pipe.submit(src, from_host=from_host, readback=rb[i]))
+    assert pipe.result() == acc.result() and pipe.num_samples == sum(sizes)
+    for t in tickets:
+        t.synchronize()
+    for got, want in zip(rb, per_batch):
+        assert torch.equal(got, want)

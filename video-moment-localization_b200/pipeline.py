@@ -206,8 +206,7 @@ class ScoringPipeline:
         if self._batch is None:
             self._batch = B
         if B != self._batch:
-            raise ValueError(f"ScoringPipeline is set up for batches of {self._batch} (got {B}); score a ragged tail batch "
-                             "with the module API or a second pipeline")
+            return self._submit_ragged(batch, from_host, readback)
         slot = self.slots[self._cur]
         if slot.fill == 0 or self._pk is None:       # parameters are looked at once per pass, not per batch
             with torch.no_grad():
@@ -291,6 +290,37 @@ class ScoringPipeline:
             self._launch(slot)
             self._cur = (self._cur + 1) % len(self.slots)
         return ticket
+
+    def _submit_ragged(self, batch, from_host, readback) -> Ticket:
+        """A batch of another size (the ragged tail of a split, main.py:168-189 with len(dataset) % batch != 0): the
+        pending group is launched and the batch is scored eagerly through the module on the caller's stream, its hits
+        added to the same device counters.  Once per split, so no graph and no staging ring."""
+        self.flush()
+        caller = torch.cuda.current_stream(self.device)
+        for s in self.slots:                      # the counters are shared: order after everything enqueued so far
+            ev = torch.cuda.Event()
+            ev.record(s.stream)
+            caller.wait_event(ev)
+        with torch.no_grad():
+            dev = {k: (batch[k].to(self.device, non_blocking=True) if not batch[k].is_cuda else batch[k]) for k in INPUT_KEYS}
+            from .synth import MODEL_INPUT_KEYS
+            out = self.model(*[dev[k] for k in MODEL_INPUT_KEYS], split_content=self.split_content)
+            step = torch.zeros(1, 2, 4, device=self.device, dtype=torch.int64)
+            top = score_topk_recall(out[0], out[1], out[2], dev["moment_mask"], dev["sm"], 5, self.nms_threshold, self.counts,
+                                    step_counts=step, step_group=out[0].shape[0])
+            if readback is not None:
+                readback.copy_(step[0], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(caller)
+        for s in self.slots:                      # later passes must not overtake the eager kernels' counter updates
+            s.stream.wait_event(done)
+        self.num_samples += out[0].shape[0]
+
+        class _Eager:                             # what Ticket.slot exposes: the outputs of this batch alone
+            outputs = (out, top)
+        t = Ticket(_Eager, 0)
+        t.event = done
+        return t
 
     def flush(self):
         """Launch a partially filled group (end of the split)."""
