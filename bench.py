@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=3, help="passes in flight (ScoringPipeline)")
-    ap.add_argument("--coalesce", type=int, default=3, help="submitted batches scored per pass (ScoringPipeline)")
+    ap.add_argument("--coalesce", type=int, default=4, help="submitted batches scored per pass (ScoringPipeline)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--split-content", action="store_true", help="content unit as two kernels (A/B against vml_content_unit)")
     args = ap.parse_args()
