@@ -396,6 +396,10 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         call("vml_lstm_layer_tc" if tc else "vml_lstm_layer", ptr(gin), ptr(pk["lstm_frag1" if tc else "lstm_whht1"]), ptr(qlen),
              ptr(fw), ptr(fwfs_h), ptr(fs), None if not bf else fwfs_h.data_ptr() + B * Nq * 2 * H * 2, B, Nq, H, st)
         mark("query_lstm")
+        ev_fs = None
+        if side is not main:                # span pooling only needs fs: it may start before the folded projection below
+            ev_fs = torch.cuda.Event()
+            ev_fs.record(side)
         # every query-side projection of every SMI layer in one GEMM (fw / fs do not change across layers)
         call("vml_linear", ptr(fwfs_h if bf else fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(qproj), B * Nq + B, ld, D, ld,
              None, 1, prec, 1, st)
@@ -409,7 +413,8 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     mark("clip_projection")
     call("vml_build_cells", ptr(mmask), B, Lm, cells, st)
     mark("build_cells")
-    join(side, main)
+    if ev_fs is not None:
+        main.wait_event(ev_fs)
 
     # ---- a3/a4 span pooling ----------------------------------------------------------------------------
     fc = [ws.get("fc_a", (cap, Cc, D), act), ws.get("fc_b", (cap, Cc, D), act)]
@@ -417,6 +422,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     fb = [ws.get("fb_a", (B, Lm, D), f32), ws.get("fb_b", (B, Lm, D), f32)]
     call("vml_span_pool_fuse", ptr(fv), ptr(fs), cells, ptr(fc[0]), ptr(fm[0]), ptr(fb[0]), B, dims, prec, st)
     mark("span_pool_fuse")
+    join(side, main)                        # qproj (boundary unit, content unit)
     if keep is not None:
         keep.update(fv=fv, fs=fs, fw=fw, cells=cells, fc0=fc[0].clone(), fm0=fm[0].clone(), fb0=fb[0].clone())
 
