@@ -290,14 +290,25 @@ content_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int q = 0; q < 8; ++q) a[e + q] = valid ? ch.v[q] * a[e + q] : 0.f;
         }
+        // Gram of the cell's 4 clips: the products with a partner row are computed once per pair -- the lane with the
+        // selector bit clear takes columns [0,16) of the chunk, its partner [16,32), then the two halves are exchanged
+        // and added (48 shuffles per chunk instead of 96; both lanes of a pair end with the same bits)
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        {
+          const bool h1 = (lane & 1) != 0, h2 = (lane & 2) != 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float gv = a[e];
-          g0 = fmaf(gv, gv, g0);
-          g1 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 1), g1);
-          g2 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 2), g2);
-          g3 = fmaf(gv, __shfl_xor_sync(0xffffffffu, gv, 3), g3);
+          for (int e = 0; e < 32; ++e) g0 = fmaf(a[e], a[e], g0);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float mine1 = h1 ? a[16 + i] : a[i], send1 = h1 ? a[i] : a[16 + i];      // partners r ^ 1 and r ^ 3 differ in bit 0
+            const float mine2 = h2 ? a[16 + i] : a[i], send2 = h2 ? a[i] : a[16 + i];      // partner r ^ 2 differs in bit 1
+            g1 = fmaf(mine1, __shfl_xor_sync(0xffffffffu, send1, 1), g1);
+            g2 = fmaf(mine2, __shfl_xor_sync(0xffffffffu, send2, 2), g2);
+            g3 = fmaf(mine1, __shfl_xor_sync(0xffffffffu, send1, 3), g3);
+          }
+          g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+          g2 += __shfl_xor_sync(0xffffffffu, g2, 2);
+          g3 += __shfl_xor_sync(0xffffffffu, g3, 3);
         }
         if (c < 64) { gg[0] += g0; gg[1] += g1; gg[2] += g2; gg[3] += g3; }
         else { gh[0] += g0; gh[1] += g1; gh[2] += g2; gh[3] += g3; }
