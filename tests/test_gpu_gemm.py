@@ -58,3 +58,22 @@ def test_linear_bf16_dynamic_row_count():
     call("vml_linear", ptr(af), ptr(wf), None, ptr(out32), M, N, K, N, ptr(n_dev), scale, L_.FP32, 1, stream_ptr())
     assert (out32[:rows].cpu().double() - ref[:rows]).abs().max().item() < 1e-4
     assert torch.all(out32[rows:] == -7.0)
+
+
+@pytest.mark.parametrize("name,B", [("charadessta", 200), ("tacos", 70)])
+def test_moment_gemm_cluster_multicast_is_bit_identical(name, B, monkeypatch):
+    """Opt-in variant of the moment GEMM (VML_GEMM_CLUSTER=1): 2-CTA clusters whose CTAs each load half of the weight tile
+    and multicast it to both (gemm_umma_kernel<256, ., 2>): same tiles, same MMA order -> the whole forward is
+    bit-identical to the single-CTA kernel, including an odd number of row tiles and the ragged last tile."""
+    from oracle import CONFIGS, init_params
+    from vml_b200 import synth
+    from gpu_util import model_for
+    cfg = CONFIGS[name]
+    model = model_for(cfg, "bf16", init_params(cfg, 43))
+    b = {k: v.cuda() for k, v in synth.make_batch(cfg, B, 31).items()}
+    want = [t.clone() for t in model(*[b[k] for k in synth.MODEL_INPUT_KEYS])]
+    monkeypatch.setenv("VML_GEMM_CLUSTER", "1")
+    got = model(*[b[k] for k in synth.MODEL_INPUT_KEYS])
+    for a, c in zip(got, want):
+        assert torch.equal(a, c)
+    assert float(got[0].abs().sum()) > 0

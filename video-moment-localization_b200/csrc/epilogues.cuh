@@ -142,6 +142,7 @@ struct EpiContentOutFused {
 // a8 tail  mu = (acc + (b_fb + b_fc)) + fm                (MomentUnit.forward, models.py:299-303)
 // bf16 variant with a prefetchable operand bundle (fm) for the tcgen05 GEMM
 struct EpiMomentOutPre {
+  static constexpr bool kCluster2 = true;   // K = 2D, BN = 256: L2 -> smem operand traffic is the roof
   const float* bias;  // [D] = b_fb + b_fc
   const bf16* fm;     // [n, D]
   bf16* out;          // [n, D]

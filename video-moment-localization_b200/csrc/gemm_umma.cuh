@@ -10,6 +10,7 @@
 // Pipelines: smem full/empty ring (STAGES), TMEM full/empty double buffer (2 accumulators),
 // so the epilogue of tile i overlaps the mainloop of tile i+1.
 #pragma once
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -31,6 +32,13 @@ struct epi_is_collective<E, std::enable_if_t<E::kWarpCollective>> : std::true_ty
 // The kernel then issues the loads of chunk c+1 (and of the next tile's first chunk, before it
 // waits for the MMA) while chunk c is being finished, hiding the L2/HBM latency that a single
 // epilogue warp per scheduler cannot hide by itself.
+// epilogues of GEMMs that are bound by L2 -> shared-memory operand traffic ask for 2-CTA clusters: the two CTAs of a
+// cluster work on vertically adjacent tiles and each loads HALF of the shared B (weight) tile, multicast to both
+template <typename E, typename = void>
+struct epi_wants_cluster : std::false_type {};
+template <typename E>
+struct epi_wants_cluster<E, std::enable_if_t<E::kCluster2>> : std::true_type {};
+
 template <typename E, typename = void>
 struct epi_has_pre : std::false_type {};
 template <typename E>
@@ -46,10 +54,11 @@ struct UmmaCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, typename Epi>
+template <int BN, typename Epi, int CL = 1>
 __global__ void __launch_bounds__(UG_GEMM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
+  static_assert(CL == 1 || CL == 2, "single CTA or 2-CTA cluster");
   using Cfg = UmmaCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
@@ -64,19 +73,25 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (m_dev) M = min(M, *m_dev * m_scale);
   const int tiles_m = (M + UG_BM - 1) / UG_BM, tiles_n = N / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (K + UG_BK - 1) / UG_BK;
+  // CL == 2: a cluster walks PAIRS of vertically adjacent tiles (same n); rank r takes m-tile 2*pair_m + r (a tile past
+  // the end still takes part in the B multicast and the barriers: its A rows are out of bounds = zero-filled)
+  const int crank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int num_tiles = CL == 2 ? ((tiles_m + 1) / 2) * tiles_n : tiles_m * tiles_n;     // tiles, or tile pairs
+  const int tile0 = CL == 2 ? (int)blockIdx.x / 2 : (int)blockIdx.x, tile_step = CL == 2 ? (int)gridDim.x / 2 : (int)gridDim.x;
+  auto tile_m0 = [&](int t) { return CL == 2 ? (2 * (t / tiles_n) + crank) * UG_BM : (t / tiles_n) * UG_BM; };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
-    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], CL); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], UG_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync_all();                    // the peer's barriers exist before anything is sent to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -84,14 +99,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * UG_BM, n0 = (tile % tiles_n) * BN;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m0 = tile_m0(tile), n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);      // CL == 2: both CTAs' MMAs have retired from this stage
           unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * UG_BK, m0);
-          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * UG_BK, n0);
+          if (CL == 2)                                       // my half of the B tile, to both CTAs of the cluster
+            ptx::tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * UG_BK,
+                                n0 + crank * (BN / 2), (uint16_t)3);
+          else
+            ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * UG_BK, n0);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -102,7 +121,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(UG_BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -115,7 +134,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < UG_BK / 16; ++k)  // +32 B per K=16 step inside the 128B swizzle atom
             ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty_bar[stage]);             // frees the smem stage when the MMAs retire
+          if (CL == 2) ptx::umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in BOTH CTAs: the stage is refilled by multicast
+          else ptx::umma_commit(&empty_bar[stage]);        // frees the smem stage when the MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
@@ -129,8 +149,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int c_lo = ((warp - 2) / 4) * HALF;              // (BN = 32: the second warp of a quadrant has no columns)
     const int c_hi = c_lo + HALF < BN ? c_lo + HALF : BN;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * UG_BM, n0 = (tile % tiles_n) * BN;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m0 = tile_m0(tile), n0 = (tile % tiles_n) * BN;
       const int row = m0 + quad * 32 + lane;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       if constexpr (epi_has_pre<Epi>::value) {
@@ -167,6 +187,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync_all();                    // no CTA leaves while its peer may still multicast into it
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
@@ -189,6 +210,33 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
     attr_done = true;
   }
   const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);
+  if constexpr (epi_wants_cluster<Epi>::value && BN == 256) {
+    // Opt-in (VML_GEMM_CLUSTER=1): measured on B200 it changes nothing (ActivityNet 285 vs 288 us, Charades 36 vs 35 us) --
+    // the 128 x 256 tile is bound by the 128 B/clk shared-memory READ port of the MMA (12 KB of operands per 64-clk
+    // instruction), not by L2 -> smem traffic; only cta_group::2 (each SM reads half of B) lifts that roof.
+    if (ceil_div(M, UG_BM) >= 2 && getenv("VML_GEMM_CLUSTER") != nullptr) {
+      // 2-CTA clusters: B tile loaded as two multicast halves (box of BN/2 rows), grid = an even number of CTAs
+      CUtensorMap tmBh;
+      rc = make_tmap_bf16_2d(&tmBh, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN / 2);
+      if (rc) return rc;
+      static bool attr2 = false;
+      if (!attr2) {
+        VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi, 2>), (size_t)(Cfg::SMEM_BYTES)));
+        attr2 = true;
+      }
+      const int64_t pairs = (int64_t)ceil_div(ceil_div(M, UG_BM), 2) * (N / BN);
+      const int clusters = (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(UG_GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      VML_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<BN, Epi, 2>, tmA, tmBh, M, N, K, m_dev, m_scale, epi));
+      VML_LAUNCHED(1);
+      return VML_OK;
+    }
+  }
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   gemm_umma_kernel<BN, Epi><<<grid, UG_GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
   VML_LAUNCHED(1);
