@@ -60,11 +60,14 @@ def test_linear_bf16_dynamic_row_count():
     assert torch.all(out32[rows:] == -7.0)
 
 
-@pytest.mark.parametrize("name,B", [("charadessta", 200), ("tacos", 70)])
-def test_moment_gemm_cluster_multicast_is_bit_identical(name, B, monkeypatch):
-    """Opt-in variant of the moment GEMM (VML_GEMM_CLUSTER=1): 2-CTA clusters whose CTAs each load half of the weight tile
-    and multicast it to both (gemm_umma_kernel<256, ., 2>): same tiles, same MMA order -> the whole forward is
-    bit-identical to the single-CTA kernel, including an odd number of row tiles and the ragged last tile."""
+@pytest.mark.parametrize("variant", ["pair", "multicast"])
+@pytest.mark.parametrize("name,B", [("charadessta", 200), ("tacos", 70), ("activitynet", 10)])
+def test_moment_gemm_cluster_variants_are_bit_identical(name, B, variant, monkeypatch):
+    """Two opt-in variants of the moment GEMM: an SM pair (VML_GEMM_PAIR=1: tcgen05.mma.cta_group::2, 256 x 256 tile, each
+    CTA loading its own A rows and half of the weight tile, the leader issuing one MMA for both) and 2-CTA clusters with
+    the weight tile loaded as two TMA-multicast halves (VML_GEMM_CLUSTER=1).  Both walk the same tiles with the same K
+    order as the default single-CTA kernel: the whole forward is bit-identical, including an odd number of row tiles
+    and the ragged last tile."""
     from oracle import CONFIGS, init_params
     from vml_b200 import synth
     from gpu_util import model_for
@@ -72,7 +75,7 @@ def test_moment_gemm_cluster_multicast_is_bit_identical(name, B, monkeypatch):
     model = model_for(cfg, "bf16", init_params(cfg, 43))
     b = {k: v.cuda() for k, v in synth.make_batch(cfg, B, 31).items()}
     want = [t.clone() for t in model(*[b[k] for k in synth.MODEL_INPUT_KEYS])]
-    monkeypatch.setenv("VML_GEMM_CLUSTER", "1")
+    monkeypatch.setenv("VML_GEMM_PAIR" if variant == "pair" else "VML_GEMM_CLUSTER", "1")
     got = model(*[b[k] for k in synth.MODEL_INPUT_KEYS])
     for a, c in zip(got, want):
         assert torch.equal(a, c)

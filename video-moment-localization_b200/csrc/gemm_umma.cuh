@@ -193,6 +193,139 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ---- host side ---------------------------------------------------------------------------
 // 2D bf16 tensor map, inner dimension = K (contiguous), 128B swizzle, box = {64, box_rows}.
+// ---- CTA-pair variant (tcgen05.mma.cta_group::2, UMMA_M = 256) ---------------------------------------------------
+// A cluster of two CTAs works on a 256 x BN tile: each CTA TMA-loads its own 128 A rows and its own HALF of the B tile
+// (BN/2 weight rows), the leader's single thread issues one MMA for both SMs, and each CTA's epilogue warps drain the
+// 128 accumulator rows that live in its own tensor memory.  Per MMA an SM now reads 4 KB of A + BN/2 rows of B from its
+// shared memory instead of 4 KB + BN rows: the 128 B/clk read port that capped the single-CTA 128 x 256 tile at 67 %
+// of the tensor pipe is no longer the limit.  Barriers: all TMA bytes of a stage count on the LEADER's full barrier;
+// the leader's commits arrive on the empty / accumulator-full barriers of BOTH CTAs; both CTAs' epilogue warps
+// arrive on the leader's accumulator-empty barrier.
+template <int BN>
+struct UmmaPairCfg {
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = UG_BM * UG_BK * 2;
+  static constexpr int BH_BYTES = (BN / 2) * UG_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "two accumulators of BN columns");
+};
+
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(UG_GEMM_THREADS, 1)
+gemm_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, int M, int N, int K,
+                      const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
+  using Cfg = UmmaPairCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (m_dev) M = min(M, *m_dev * m_scale);
+  const int tiles_m = (M + UG_BM - 1) / UG_BM, tiles_n = N / BN;
+  const int k_blocks = (K + UG_BK - 1) / UG_BK;
+  const int crank = (int)ptx::cluster_ctarank();
+  const bool leader = crank == 0;
+  const int num_pairs = ((tiles_m + 1) / 2) * tiles_n;
+  const int pair0 = (int)blockIdx.x / 2, pair_step = (int)gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmBh);
+    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * UG_EPI_WARPS); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();                                 // both CTAs' barriers and tensor memory exist
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                       // ===================== TMA producer (both CTAs) =====================
+      int stage = 0; uint32_t phase = 0;
+      for (int pair = pair0; pair < num_pairs; pair += pair_step) {
+        const int m0 = (2 * (pair / tiles_n) + crank) * UG_BM, n0 = (pair % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);    // the pair's MMAs have retired from this stage
+          unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);   // bytes of BOTH CTAs
+          ptx::tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * UG_BK, m0);
+          ptx::tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmBh, &full_bar[stage], kb * UG_BK, n0 + crank * (BN / 2));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {                             // ===================== MMA issuer (leader only) =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * UG_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int pair = pair0; pair < num_pairs; pair += pair_step) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // both CTAs' epilogues have drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
+          const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < UG_BK / 16; ++k)
+            ptx::umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          ptx::umma_commit_2sm(&empty_bar[stage], (uint16_t)3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_2sm(&tfull_bar[acc], (uint16_t)3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs: the 128 rows in their own tensor memory) =====================
+    const int quad = warp % 4;
+    constexpr int HALF = BN / 2;
+    const int c_lo = ((warp - 2) / 4) * HALF, c_hi = c_lo + HALF;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int pair = pair0; pair < num_pairs; pair += pair_step) {
+      const int m0 = (2 * (pair / tiles_n) + crank) * UG_BM, n0 = (pair % tiles_n) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      typename Epi::Pre pre = epi.load(row, n0 + c_lo, row < M);       // in flight while the MMA finishes
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 32) {
+        float v[32];
+        ptx::tmem_ld32(t_addr + (uint32_t)c, v);
+        typename Epi::Pre nxt = pre;
+        if (c + 32 < c_hi) nxt = epi.load(row, n0 + c + 32, row < M);
+        ptx::tmem_ld_wait();
+        epi.template apply_pre<32>(row, n0 + c, v, pre, row < M);
+        pre = nxt;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&tempty_bar[acc]);
+        else ptx::mbar_arrive_cluster(&tempty_bar[acc], 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();                                 // nobody leaves while the pair's MMAs / arrivals may still target it
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base); }
+}
+
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t k, uint64_t row_stride_elems, uint32_t box_rows);
 
 template <int BN, typename Epi>
@@ -210,6 +343,35 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
     attr_done = true;
   }
   const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);
+  if constexpr (epi_wants_cluster<Epi>::value && epi_has_pre<Epi>::value && BN == 256) {
+    // Opt-in (VML_GEMM_PAIR=1).  Validated bit-identical and measured neutral on B200 (ActivityNet 286 vs 288 us per layer,
+    // Charades 35.5 vs 34.7 us): with its register epilogue (16-byte accesses to 32 different rows per instruction) and
+    // ~1 GB of operand + residual + result traffic per ActivityNet layer, the moment GEMM sits at 53 % of BOTH the tensor
+    // and the HBM roof; the pair lifts the shared-memory read port, which is not what binds.  Kept for the round that
+    // moves the epilogue to TMA and fuses the bu_i*bu_j operand half into the producer.
+    if (ceil_div(M, UG_BM) >= 2 && getenv("VML_GEMM_PAIR") != nullptr) {
+      using PCfg = UmmaPairCfg<BN>;
+      CUtensorMap tmBh;
+      rc = make_tmap_bf16_2d(&tmBh, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN / 2);
+      if (rc) return rc;
+      static bool attrp = false;
+      if (!attrp) {
+        VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_pair_kernel<BN, Epi>), (size_t)(PCfg::SMEM_BYTES)));
+        attrp = true;
+      }
+      const int64_t pairs = (int64_t)ceil_div(ceil_div(M, UG_BM), 2) * (N / BN);
+      const int clusters = (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(UG_GEMM_THREADS); cfg.dynamicSmemBytes = PCfg::SMEM_BYTES; cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      VML_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_pair_kernel<BN, Epi>, tmA, tmBh, M, N, K, m_dev, m_scale, epi));
+      VML_LAUNCHED(1);
+      return VML_OK;
+    }
+  }
   if constexpr (epi_wants_cluster<Epi>::value && BN == 256) {
     // Opt-in (VML_GEMM_CLUSTER=1): measured on B200 it changes nothing (ActivityNet 285 vs 288 us, Charades 36 vs 35 us) --
     // the 128 x 256 tile is bound by the 128 B/clk shared-memory READ port of the MMA (12 KB of operands per 64-clk
