@@ -323,6 +323,9 @@ VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* b
   VML_PREC_OK(prec);
   // (K = 2D makes this stage tensor-bound: the register epilogue with 128 x 256 tiles measured faster than the
   //  shared-memory residual epilogue of gemm_res.cu, which is used for the byte-bound a6 tail)
+  if (prec == VML_BF16 && d.D % 128 == 0 && getenv("VML_MOMENT_RES") != nullptr)   // A/B knob: TMA-in / TMA-out residual epilogue, 128 x 128 tiles
+    return gemm_res(operand, Wcat, bias_sum, fm, nullptr, mu, nullptr, cells.capacity, d.D, 2 * d.D, 2 * d.D, 0, cells.n_cells, 1,
+                    ST(stream));
   if (prec == VML_BF16) {
     EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D};
     return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
