@@ -54,8 +54,11 @@ struct UmmaCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, typename Epi, int CL = 1>
-__global__ void __launch_bounds__(UG_GEMM_THREADS, 1)
+// EW epilogue warps (8 or 16): EW / 4 of them share a TMEM lane quadrant and split the tile's columns.  With 128 x 256
+// tiles 8 warps need ~2x the main loop's time for a residual epilogue (measured: the moment GEMM ran at 53 % of the
+// tensor pipe whatever fed its operands), hence 16 for BN = 256.
+template <int BN, typename Epi, int CL = 1, int EW = UG_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
   static_assert(CL == 1 || CL == 2, "single CTA or 2-CTA cluster");
@@ -85,7 +88,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], CL); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], UG_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], EW); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -145,7 +148,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp % 4;                             // TMEM lane quadrant this warp may access
-    constexpr int HALF = BN >= 64 ? BN / 2 : BN;           // columns handled by this warp: [c_lo, c_hi)
+    static_assert(EW == 8 || (EW == 16 && BN >= 128), "epilogue warps: 8, or 16 for wide tiles");
+    constexpr int HALF = EW == 16 ? BN / 4 : (BN >= 64 ? BN / 2 : BN);   // columns handled by this warp: [c_lo, c_hi)
     const int c_lo = ((warp - 2) / 4) * HALF;              // (BN = 32: the second warp of a quadrant has no columns)
     const int c_hi = c_lo + HALF < BN ? c_lo + HALF : BN;
     int acc = 0; uint32_t acc_phase = 0;
@@ -212,8 +216,10 @@ struct UmmaPairCfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "two accumulators of BN columns");
 };
 
+constexpr int UG_PAIR_EPI_WARPS = 16, UG_PAIR_THREADS = 64 + 32 * UG_PAIR_EPI_WARPS;
+
 template <int BN, typename Epi>
-__global__ void __launch_bounds__(UG_GEMM_THREADS, 1)
+__global__ void __launch_bounds__(UG_PAIR_THREADS, 1)
 gemm_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, int M, int N, int K,
                       const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
   using Cfg = UmmaPairCfg<BN>;
@@ -238,7 +244,7 @@ gemm_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmBh);
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * UG_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 2 * UG_PAIR_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
@@ -291,7 +297,7 @@ gemm_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else {
     // ===================== epilogue warps (both CTAs: the 128 rows in their own tensor memory) =====================
     const int quad = warp % 4;
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / (UG_PAIR_EPI_WARPS / 4);     // columns per warp: 4 warps share a TMEM lane quadrant
     const int c_lo = ((warp - 2) / 4) * HALF, c_hi = c_lo + HALF;
     int acc = 0; uint32_t acc_phase = 0;
     for (int pair = pair0; pair < num_pairs; pair += pair_step) {
@@ -362,7 +368,7 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
       const int64_t pairs = (int64_t)ceil_div(ceil_div(M, UG_BM), 2) * (N / BN);
       const int clusters = (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(UG_GEMM_THREADS); cfg.dynamicSmemBytes = PCfg::SMEM_BYTES; cfg.stream = stream;
+      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(UG_PAIR_THREADS); cfg.dynamicSmemBytes = PCfg::SMEM_BYTES; cfg.stream = stream;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -400,6 +406,18 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
     }
   }
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  if constexpr (BN == 256) {
+    if (getenv("VML_GEMM_EPI8") == nullptr) {               // (A/B knob) 16 epilogue warps for the wide tile
+      static bool attr16 = false;
+      if (!attr16) {
+        VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi, 1, 16>), (size_t)(Cfg::SMEM_BYTES)));
+        attr16 = true;
+      }
+      gemm_umma_kernel<BN, Epi, 1, 16><<<grid, 64 + 32 * 16, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+      VML_LAUNCHED(1);
+      return VML_OK;
+    }
+  }
   gemm_umma_kernel<BN, Epi><<<grid, UG_GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
   VML_LAUNCHED(1);
   return VML_OK;
