@@ -454,7 +454,8 @@ def main():
             seen += int(result_host[idx].sum())
         return seen
 
-    e2e_run(max(3, min(args.warmup, 10)))
+    # untimed: every staging area of the H2D ring allocated and every (slot, position) ingest launch recorded
+    e2e_run(max(args.warmup, len(pipe.staging) + 2 * args.coalesce))
     barrier()
     e0.record()
     e2e_run(args.steps)
