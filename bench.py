@@ -141,40 +141,93 @@ def ncu_traffic(stage, cfg_name, queries_in_pass):
     return tot if hit else None
 
 
+def reference_arm(cfg, device="cpu"):
+    """The baseline arm's step function: (step(batch) -> (outputs, metric dict), kind, description).
+
+    ``kind == "reference"``: the UNMODIFIED reference (baseline/_ref: models.SMIN.forward, models.py:367-377, +
+    utils.compute_ious, utils.py:10-31) with the bench's deterministic weights loaded through ``load_state_dict``.
+    ``kind == "port"``: only when baseline/_ref is absent -- the oracle's restatement of the same path."""
+    from vml_b200 import synth
+    from vml_b200.configs import init_params
+    params = init_params(cfg, 43)
+    dev = torch.device(device)
+    try:
+        from baseline import loader as bl
+        ref = bl.load_reference() if bl.available() else None
+    except Exception as exc:                                   # a broken copy must not take the bench down
+        print(f"[bench] baseline/_ref unusable ({exc!r}); falling back to the oracle port", file=sys.stderr)
+        ref = None
+    if ref is not None:
+        model = ref.models.SMIN(*cfg.ctor_args(), dev)
+        model.load_state_dict(params, strict=True)
+        model = model.to(dev).eval()
+
+        def step(batch):
+            with torch.no_grad():
+                out = model(*[batch[k] for k in synth.MODEL_INPUT_KEYS])
+            return out, dict(ref.utils.compute_ious(out[0], out[1], out[2], batch["moment_mask"], batch["sm"]))
+        return step, "reference", f"unmodified reference models.SMIN + utils.compute_ious from baseline/_ref, torch {torch.__version__} eager on {dev.type}"
+    if dev.type != "cpu":
+        raise RuntimeError("reference-on-GPU needs baseline/_ref (python -m baseline.install)")
+    from oracle import smin_forward as oracle_forward
+    from oracle import metrics_oracle as mo
+
+    def step(batch):
+        with torch.no_grad():
+            out = oracle_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS])
+        return out, mo.compute_ious(out[0], out[1], out[2], batch["moment_mask"], batch["sm"])
+    return step, "port", "oracle port of the reference path (baseline/_ref not installed), torch CPU"
+
+
 def run_reference(args, cfg, rank, world):
-    """CPU arm: the oracle port (the reference is pure Python and cannot travel; oracle/ is its
-    pinned restatement) on all host threads.  Rank 0 only."""
+    """Baseline arm, rank 0 only: the reference's own implementation of the path on the host cores (all threads), or with
+    ``--device cuda`` the same unmodified module in PyTorch eager on the GPU (the stronger baseline, recorded in profiles/)."""
     if rank != 0:
         return
-    from oracle import smin_forward as oracle_forward
-    from vml_b200.configs import init_params
-    from oracle import metrics_oracle as mo
     from vml_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = init_params(cfg, 43)
+    on_gpu = args.device == "cuda"
+    step, kind, what = reference_arm(cfg, "cuda:0" if on_gpu else "cpu")
     batch = synth.make_batch(cfg, BATCH, 1000)
+    h2d = 0
+    if on_gpu:
+        keys = synth.MODEL_INPUT_KEYS + ("sm",)
+        pinned = {k: batch[k].pin_memory() for k in keys}
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+        dev_batch = {k: pinned[k].cuda() for k in keys}
 
-    def step():
-        with torch.no_grad():
-            pm, ps, pe, pa = oracle_forward(params, cfg, *[batch[k] for k in synth.MODEL_INPUT_KEYS])
-        return mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"])
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    qps = BATCH * args.steps / dt
-    sample = f"{args.steps} step(s) of one {cfg.name} batch of {BATCH} queries (fp32, torch CPU, {torch.get_num_threads()} threads)"
+        def timed(fn, n):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 1e3
+        resident = lambda: step(dev_batch)                                             # compute_ious does its 8 .item() reads
+        e2e = lambda: step({k: pinned[k].to("cuda", non_blocking=True) for k in keys})      # main.py:118-133 + metric read-back
+        for _ in range(max(args.warmup, 3)):
+            resident()
+        dt = timed(resident, args.steps)
+        dt_e2e = timed(e2e, args.steps)
+    else:
+        for _ in range(args.warmup):
+            step(batch)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(batch)
+        dt = dt_e2e = time.perf_counter() - t0
+    qps, qps_e2e = BATCH * args.steps / dt, BATCH * args.steps / dt_e2e
+    sample = f"{args.steps} step(s) of one {cfg.name} batch of {BATCH} queries, fp32, {what}" + ("" if on_gpu else f", {torch.get_num_threads()} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg.name}: forward + R@n,IoU=m eval, batch {BATCH}, CPU oracle port of the reference path"},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "device": "cuda" if on_gpu else "cpu",
+        "config": {"workload": f"{cfg.name}: forward + R@n,IoU=m eval, batch {BATCH}, {what}"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64 if on_gpu else 0},
     }))
 
 
@@ -300,12 +353,68 @@ def run_train(args, cfg, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def parity_gate(cfg, model_bf16, dev_batch, host_batch, ref_out, ref_metrics, dev):
+    """CUDA path vs the baseline arm's outputs on the SAME batch of 64 (the bench's own batch shape): score tolerances of
+    north_star (1e-5 relative in fp32 mode, 1e-2 in bf16 mode), logits in bf16 mode (a sigmoid flattens errors), exact top-5
+    indices and R@n,IoU=m counts end to end in fp32 mode and kernel-isolated (our metric kernel on the baseline's scores)."""
+    from vml_b200 import synth
+    from vml_b200.configs import init_params
+    from vml_b200.evaluate import compute_ious, score_topk_recall
+    from vml_b200.smin import SMIN
+    B = host_batch["video_features"].shape[0]
+    args_dev = [dev_batch[k] for k in synth.MODEL_INPUT_KEYS]
+
+    def rel(o, r):
+        o, r = o.detach().cpu().double(), r.double()
+        return ((o - r).abs() / r.abs().clamp_min(1e-6)).max().item()
+
+    def logit_err(o, r):
+        o, r = o.detach().cpu().double(), r.double()
+        keep = r != 0
+        lo = torch.log(o[keep] / (1 - o[keep])) - torch.log(r[keep] / (1 - r[keep]))
+        return lo.abs().max().item()
+
+    m32 = SMIN(*cfg.ctor_args(), device=dev, precision="fp32")
+    m32.load_state_dict(init_params(cfg, 43))
+    m32 = m32.to(dev).eval()
+    with torch.no_grad():
+        o32 = m32(*args_dev)
+        o16 = model_bf16(*args_dev) if model_bf16.precision == "bf16" else o32
+    out = {"batch": B, "against": "the cpu_baseline arm's outputs on the same batch"}
+    out["fp32_rel"] = max(rel(o, r) for o, r in zip(o32, ref_out))
+    out["bf16_rel"] = max(rel(o, r) for o, r in zip(o16, ref_out))
+    out["bf16_logit_abs"] = max(logit_err(o, r) for o, r in zip(o16, ref_out))
+    out["masked_exact_zero"] = all(bool(torch.equal(o.cpu() == 0, r == 0)) for outs in (o32, o16) for o, r in zip(outs, ref_out))
+    # top-5: end to end in fp32 mode; the reference's own torch.topk order on its own scores is the expectation
+    pm, ps, pe, _ = ref_out
+    ref_score = (pm * torch.sqrt(ps.unsqueeze(2)) * torch.sqrt(pe.unsqueeze(1)) * host_batch["moment_mask"]).view(B, -1)
+    ref_top = ref_score.topk(k=5, dim=1)[1]
+    top32 = score_topk_recall(o32[0], o32[1], o32[2], dev_batch["moment_mask"], dev_batch["sm"])[0].cpu().long()
+    out["topk_exact_fp32"] = bool(torch.equal(top32, ref_top))
+    if not out["topk_exact_fp32"]:                   # near-ties may reorder: say how many samples differ
+        out["topk_samples_differing_fp32"] = int((top32 != ref_top).any(1).sum())
+    got32 = dict(compute_ious(o32[0], o32[1], o32[2], dev_batch["moment_mask"], dev_batch["sm"]))
+    out["recall_equal"] = got32 == dict(ref_metrics)
+    # kernel-isolated: the metric kernel on the baseline's own score tensors (bit-exact by construction of the op order)
+    g = lambda t: t.to(dev)
+    iso = score_topk_recall(g(pm), g(ps), g(pe), dev_batch["moment_mask"], dev_batch["sm"])
+    out["topk_exact_isolated"] = bool(torch.equal(iso[0].cpu().long(), ref_top))
+    out["recall_equal_isolated"] = dict(compute_ious(g(pm), g(ps), g(pe), dev_batch["moment_mask"], dev_batch["sm"])) == dict(ref_metrics)
+    out["recall_counts_reference"] = {k: v for k, v in sorted(dict(ref_metrics).items())}
+    out["tolerance"] = {"fp32_rel": 1e-5, "bf16_rel": 1e-2}
+    out["pass"] = bool(out["fp32_rel"] < 1e-5 and out["bf16_rel"] < 1e-2 and out["masked_exact_zero"] and out["recall_equal"]
+                       and out["topk_exact_isolated"] and out["recall_equal_isolated"])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (the contract's baseline arm) or cuda (reference in PyTorch eager on the GPU)")
     ap.add_argument("--mode", default="eval", choices=["eval", "train"],
                     help="eval: forward + R@n,IoU=m (the headline metric); train: the training step of BASELINE configs[3]")
     ap.add_argument("--config", default=None, choices=["charadessta", "tacos", "activitynet"])
@@ -573,29 +682,27 @@ def main():
         dist.all_reduce(total_counts)
         dist.all_reduce(nsamp)
 
-    # ---------------- CPU baseline (rank 0, N == 1) ------------------------------------------------------
-    cpu_baseline = None
+    # ---------------- CPU baseline + parity gate (rank 0, N == 1) ------------------------------------------
+    # The baseline arm's outputs on host[0] are not thrown away: the CUDA path scores the same batch in both arithmetic
+    # modes and the line carries the comparison ("parity gates in the same job").
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import smin_forward as oracle_forward
-        from oracle import metrics_oracle as mo
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        params = init_params(cfg, 43)
+        ref_step, kind, what = reference_arm(cfg, "cpu")
         b = host[0]
-
-        def cpu_step():
-            with torch.no_grad():
-                o = oracle_forward(params, cfg, *[b[k] for k in synth.MODEL_INPUT_KEYS])
-            return mo.compute_ious(o[0], o[1], o[2], b["moment_mask"], b["sm"])
-        cpu_step()
+        ref_out, ref_metrics = ref_step(b)
         n_cpu, t0 = 0, time.perf_counter()
         while n_cpu < 12 and (time.perf_counter() - t0 < 10.0 or n_cpu < 3):     # bounded sample: ~10 s of host work
-            cpu_step()
+            ref_step(b)
             n_cpu += 1
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": BATCH * n_cpu / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-                        "sample": f"{n_cpu} x one {cfg.name} batch of {BATCH} queries after 1 warm-up, fp32 torch CPU oracle port, "
+        cpu_baseline = {"value": BATCH * n_cpu / dt, "unit": "queries/s", "cores": cores, "kind": kind,
+                        "sample": f"{n_cpu} x one {cfg.name} batch of {BATCH} queries after 1 warm-up, fp32, {what}, "
                                   f"{torch.get_num_threads()} threads"}
+        parity = parity_gate(cfg, model, resident[0], b, ref_out, ref_metrics, dev)
+        if not parity["pass"]:
+            print(f"[bench] PARITY GATE FAILED: {parity}", file=sys.stderr)
 
     if rank == 0:
         out = {
@@ -620,6 +727,7 @@ def main():
             "roofline": roofline,
             "stages": stages,
             "cpu_baseline": cpu_baseline,
+            "parity": parity,
             "recall_counts": total_counts.cpu().tolist(), "num_samples": int(nsamp.item()),
             "kernels": lib.kernel_names(),
         }

@@ -277,6 +277,13 @@ VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float*
                           const float* sm, int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx,
                           float* top_score, float* top_iou, int64_t* counts, int64_t* step_counts, int step_group,
                           void* stream);
+/* The same with the caller's own lists, as utils.py:10 allows (`n`, `m` are arbitrary Python lists there): ns[n_n]
+ * (n_n <= 8, each >= 1) and ms[n_m] (n_m <= 8) are HOST arrays; k = max(ns) <= 32 is the reference's topk(max(n));
+ * counts / step_counts are laid out [n_n][n_m] (step group stride n_n*n_m). */
+VML_API int vml_score_topk_recall_nm(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask,
+                          const float* sm, int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx,
+                          float* top_score, float* top_iou, int64_t* counts, int64_t* step_counts, int step_group,
+                          const int32_t* ns, int n_n, const float* ms, int n_m, void* stream);
 
 /* ---- backward / training path (fp32): adjoints behind loss.backward() (main.py:150) -----------------------
  * All tensors float.  Outputs documented "+=" accumulate (the caller zeroes gradient buffers once per step);

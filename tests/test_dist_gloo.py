@@ -87,7 +87,7 @@ def _grad_worker(rank, world, port, n_total, out):
     """Data-parallel training math (trainer.allreduce_mean_): every rank back-propagates the loss of its own slice
     (autograd of the CPU oracle stands in for the CUDA backward), flattens the gradients in parameter order like
     FusedAdam.flat_grad, and one all-reduce yields the global-batch gradient."""
-    from vml_b200.trainer import allreduce_mean_
+    from vml_b200.trainer import allreduce_mean_, shard_weight
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     vdist.init_from_env(backend="gloo")
     cfg = CONFIGS["tiny"]
@@ -99,6 +99,12 @@ def _grad_worker(rank, world, port, n_total, out):
                       mine["ya"], mine["length_mask"])
     loss.backward()
     flat = torch.cat([p.grad.reshape(-1) for p in params.values()])
+    # B_local / B_global weighting (uneven shards): global size summed over ranks == global size given
+    nb = mine["video_features"].shape[0]
+    w = float(shard_weight(nb, None, flat.device))
+    assert abs(w - shard_weight(nb, n_total, flat.device)) < 1e-12
+    assert (w == 1.0) == (n_total % world == 0)
+    flat.mul_(float(w))
     assert allreduce_mean_(flat) == 1.0
     if rank == 0:
         torch.save(flat, out)
@@ -106,9 +112,9 @@ def _grad_worker(rank, world, port, n_total, out):
     dist.destroy_process_group()
 
 
-def test_data_parallel_gradient_equals_global_batch_gradient(tmp_path):
+@pytest.mark.parametrize("n_total", [6, 7])             # 6: equal slices; 7: ragged last batch (4 + 3), weighted by B_r / B
+def test_data_parallel_gradient_equals_global_batch_gradient(tmp_path, n_total):
     out = str(tmp_path / "g.pt")
-    n_total = 6                                        # equal slices: mean of local means == global mean (main.py:106)
     mp.spawn(_grad_worker, args=(2, _free_port(), n_total, out), nprocs=2, join=True)
     got = torch.load(out)
     cfg = CONFIGS["tiny"]

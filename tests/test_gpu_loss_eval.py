@@ -175,3 +175,18 @@ def test_bf16_kernel_isolated_indices_exact():
     assert torch.equal(top_idx.cpu().long(), mo.topk_lowest_index(scores, 5))
     got = compute_ious(pm, ps, pe, batch["moment_mask"].cuda(), batch["sm"].cuda())
     assert dict(got) == mo.compute_ious(pm.cpu(), ps.cpu(), pe.cpu(), batch["moment_mask"], batch["sm"])
+
+
+@pytest.mark.parametrize("n,m", [([1, 5], [0.1, 0.3, 0.5, 0.7]), ([1, 3, 10], [0.25, 0.5]), ([2], [0.05, 0.15, 0.35, 0.55, 0.75, 0.9]),
+                                 ([1, 2, 3, 4, 5, 6, 7, 8], [0.5]), ([32], [0.3, 0.7])])
+def test_compute_ious_arbitrary_n_and_m_lists(n, m):
+    """utils.py:10 takes arbitrary ``n`` / ``m`` lists: keys (the caller's own values in the f-string) and counts exact."""
+    cfg = CONFIGS["charadessta"]
+    batch, pm, ps, pe, _ = _scores(cfg, 12, 41)
+    g = lambda t: t.cuda()
+    got = compute_ious(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]), n, m)
+    ref = mo.compute_ious(pm, ps, pe, batch["moment_mask"], batch["sm"], n, m)
+    assert dict(got) == ref
+    assert any(v not in (0.0, 12.0) for v in ref.values()) or len(m) == 1        # the case discriminates
+    with pytest.raises(ValueError):
+        compute_ious(g(pm), g(ps), g(pe), g(batch["moment_mask"]), g(batch["sm"]), [33], m)

@@ -41,7 +41,8 @@ def test_gemm_strided_matches_torch():
     assert ((C2 - ref2).abs() / ref2.abs().clamp_min(1.0)).max() < 1e-4
 
 
-@pytest.mark.parametrize("name,B,seed", [("tiny", 5, 21), ("tiny_r2", 4, 22), ("charadessta", 3, 23), ("activitynet", 2, 24)])
+@pytest.mark.parametrize("name,B,seed", [("tiny", 5, 21), ("tiny_r2", 4, 22), ("charadessta", 3, 23), ("activitynet", 2, 24),
+                                         ("tacos", 3, 25)])          # tacos: the shape of BASELINE configs[3]
 def test_backward_matches_oracle_autograd(name, B, seed):
     cfg = CONFIGS[name]
     params = init_params(cfg, 43)
@@ -118,3 +119,58 @@ def test_fused_adam_checkpoint_round_trips_with_torch_adam():
         ours.step(); ref.step(); stock.step(); mine.step()
     for a, b, c, d in zip(ps, ref_ps, ps2, ps3):
         assert (a - b).abs().max() < 1e-6 and (c - b).abs().max() < 1e-6 and (d - b).abs().max() < 1e-6
+
+
+def test_fused_adam_steps_refresh_packed_weights():
+    """Regression (round-1 advisor finding): ``FusedAdam.step`` writes the parameters from a kernel, so SMIN's packed-weight
+    cache must be invalidated explicitly.  Three ``train_step``s of SMIN + FusedAdam must track SMIN + torch.optim.Adam on the
+    same batches (losses and parameters), and an eval forward must move after a step."""
+    from vml_b200.optim import FusedAdam
+    from vml_b200.trainer import train_step
+    cfg = CONFIGS["tiny"]
+    params = init_params(cfg, 43)
+    ours, ref = model_for(cfg, "fp32", params), model_for(cfg, "fp32", params)
+    ours.train(); ref.train()
+    opt, ref_opt = FusedAdam(ours.parameters(), lr=1e-2), torch.optim.Adam(ref.parameters(), lr=1e-2)
+    batches = [{k: v.cuda() for k, v in synth.make_batch(cfg, 4, 300 + i).items()} for i in range(2)]
+    probe = batches[0]
+
+    def eval_scores(m):
+        m.eval()
+        with torch.no_grad():
+            out = m(*[probe[k] for k in synth.MODEL_INPUT_KEYS])[0].clone()
+        m.train()
+        return out
+
+    before = eval_scores(ours)
+    losses, ref_losses = [], []
+    for step in range(3):
+        d = batches[step % 2]                      # batch 0 is repeated at step 2: its loss must have moved
+        losses.append(train_step(ours, opt, d).item())
+        ref_opt.zero_grad()
+        out = ref(*[d[k] for k in synth.MODEL_INPUT_KEYS])
+        loss = loss_fn(out[0], d["ym"], d["sm"], d["moment_mask"], out[1], d["ys"], d["ss"], out[2], d["ye"], d["se"], out[3], d["ya"],
+                       d["length_mask"])
+        loss.backward()
+        ref_opt.step()
+        ref_losses.append(loss.item())
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 1e-5 * abs(b), (losses, ref_losses)
+    assert abs(losses[2] - losses[0]) > 1e-4 * abs(losses[0]), "the loss on the repeated batch did not move: frozen weights"
+    for (n, p), (_, r) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert (p - r).abs().max() <= 1e-5 * max(r.abs().max().item(), 1e-3), n
+    after = eval_scores(ours)
+    assert (after - before).abs().max() > 1e-4, "eval forward unchanged after three optimizer steps: stale packed weights"
+    assert (after - eval_scores(ref)).abs().max() < 1e-4
+
+
+def test_fused_adam_refuses_rebound_parameters():
+    from vml_b200 import lib
+    from vml_b200.optim import FusedAdam
+    ps = [torch.randn(10, 3, device="cuda", requires_grad=True)]
+    opt = FusedAdam(ps, lr=1e-3)
+    ps[0].grad = torch.ones_like(ps[0])
+    opt.step()
+    ps[0].data = ps[0].data.clone()                # what model.to() / flatten_parameters would do
+    with pytest.raises(lib.VmlError):
+        opt.step()

@@ -128,7 +128,7 @@ int scaled_iou_bce(const float*, const uint8_t*, const float*, const uint8_t*, c
                    const float*, const uint8_t*, const float*, const float*, const uint8_t*, const uint8_t*, int, int,
                    float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
 int score_topk_recall(const float*, const float*, const float*, const uint8_t*, const float*, int, int, int, int, int,
-                      int32_t*, float*, float*, int64_t*, int64_t*, int, cudaStream_t);
+                      int32_t*, float*, float*, int64_t*, int64_t*, int, const int*, int, const float*, int, cudaStream_t);
 
 // generic dispatch: fp32 -> CUDA-core GEMM, bf16 -> tcgen05 GEMM
 template <typename Epi>
@@ -353,7 +353,16 @@ VML_API int vml_score_topk_recall(const float* pm, const float* ps, const float*
                           int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score,
                           float* top_iou, int64_t* counts, int64_t* step_counts, int step_group, void* stream) {
   return score_topk_recall(pm, ps, pe, moment_mask, sm, B, L, k, nms_num, nms_den, top_idx, top_score, top_iou, counts,
-                           step_counts, step_group, ST(stream));
+                           step_counts, step_group, nullptr, 0, nullptr, 0, ST(stream));
+}
+
+VML_API int vml_score_topk_recall_nm(const float* pm, const float* ps, const float* pe, const uint8_t* moment_mask, const float* sm,
+                          int B, int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score,
+                          float* top_iou, int64_t* counts, int64_t* step_counts, int step_group, const int32_t* ns, int n_n,
+                          const float* ms, int n_m, void* stream) {
+  VML_CHECK_ARG(ns != nullptr && ms != nullptr);
+  return score_topk_recall(pm, ps, pe, moment_mask, sm, B, L, k, nms_num, nms_den, top_idx, top_score, top_iou, counts,
+                           step_counts, step_group, ns, n_n, ms, n_m, ST(stream));
 }
 
 // ---- backward / training path (fp32) ---------------------------------------------------------------------

@@ -473,16 +473,21 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long)hi << 32) | lo;
 }
 
+// n in `ns` (top-n prefixes), m in `ms` (strict IoU thresholds): the reference's arbitrary lists (utils.py:10,24-29)
+struct RecallSpec { int ns[8]; float ms[8]; int n_n, n_m; };
+constexpr int kMaxTopK = 32;
+
 __global__ void __launch_bounds__(256)
 score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ pe,
                   const uint8_t* __restrict__ mmask, const float* __restrict__ sm, int L, int k, int nms_num, int nms_den,
                   int32_t* __restrict__ top_idx, float* __restrict__ top_score, float* __restrict__ top_iou,
-                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ counts2, int group) {
+                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ counts2, int group,
+                  const RecallSpec spec) {
   extern __shared__ __align__(8) unsigned char smem_raw[];
   float* sc = reinterpret_cast<float*>(smem_raw);                       // [L*L] scores; < 0 marks taken/suppressed
   __shared__ unsigned long long wbest[8];
-  __shared__ int picked[8];
-  __shared__ float picked_iou[8];
+  __shared__ int picked[kMaxTopK];
+  __shared__ float picked_iou[kMaxTopK];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
   const int n = L * L;
   const size_t mo = (size_t)b * n;
@@ -542,30 +547,39 @@ score_topk_kernel(const float* __restrict__ pm, const float* __restrict__ ps, co
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    const float thr[4] = {0.1f, 0.3f, 0.5f, 0.7f};
-    const int ns[2] = {1, 5};
-    for (int a = 0; a < 2; ++a)
-      for (int t = 0; t < 4; ++t) {
-        bool hit = false;
-        for (int r = 0; r < min(ns[a], k); ++r) hit = hit || (picked[r] >= 0 && picked_iou[r] > thr[t]);
-        if (hit) {
-          atomicAdd(&counts[a * 4 + t], 1ull);
-          if (counts2) atomicAdd(&counts2[(b / group) * 8 + a * 4 + t], 1ull);
-        }
-      }
+  if (tid < spec.n_n * spec.n_m) {
+    const int a = tid / spec.n_m, t = tid % spec.n_m, per = spec.n_n * spec.n_m;
+    bool hit = false;
+    for (int r = 0; r < min(spec.ns[a], k); ++r) hit = hit || (picked[r] >= 0 && picked_iou[r] > spec.ms[t]);
+    if (hit) {
+      atomicAdd(&counts[tid], 1ull);
+      if (counts2) atomicAdd(&counts2[(b / group) * per + tid], 1ull);
+    }
   }
 }
 
 int score_topk_recall(const float* pm, const float* ps, const float* pe, const uint8_t* mmask, const float* sm, int B,
                       int L, int k, int nms_num, int nms_den, int32_t* top_idx, float* top_score, float* top_iou,
-                      int64_t* counts, int64_t* counts2, int group, cudaStream_t st) {
-  VML_CHECK_ARG(B > 0 && L > 0 && k >= 1 && k <= 8 && nms_den > 0 && (size_t)L * L * 4 <= 200 * 1024);
+                      int64_t* counts, int64_t* counts2, int group, const int* ns, int n_n, const float* ms, int n_m,
+                      cudaStream_t st) {
+  VML_CHECK_ARG(B > 0 && L > 0 && k >= 1 && k <= kMaxTopK && k <= L * L && nms_den > 0 && (size_t)L * L * 4 <= 200 * 1024);
+  RecallSpec spec{};
+  if (ns == nullptr || ms == nullptr) {        // the reference's defaults (utils.py:10)
+    spec.n_n = 2; spec.n_m = 4;
+    spec.ns[0] = 1; spec.ns[1] = 5;
+    spec.ms[0] = 0.1f; spec.ms[1] = 0.3f; spec.ms[2] = 0.5f; spec.ms[3] = 0.7f;
+  } else {
+    VML_CHECK_ARG(n_n >= 1 && n_n <= 8 && n_m >= 1 && n_m <= 8);
+    spec.n_n = n_n; spec.n_m = n_m;
+    for (int a = 0; a < n_n; ++a) { VML_CHECK_ARG(ns[a] >= 1); spec.ns[a] = ns[a]; }
+    for (int t = 0; t < n_m; ++t) spec.ms[t] = ms[t];
+  }
   static bool reg = (register_kernel("score_topk_kernel"), true); (void)reg;
   const size_t smem = sizeof(float) * L * L;
   VML_CUDA(ensure_dyn_smem((const void*)(score_topk_kernel), (size_t)((int)smem)));
   score_topk_kernel<<<B, 256, smem, st>>>(pm, ps, pe, mmask, sm, L, k, nms_num, nms_den, top_idx, top_score, top_iou,
-                                          (unsigned long long*)counts, (unsigned long long*)counts2, group > 0 ? group : B);
+                                          (unsigned long long*)counts, (unsigned long long*)counts2, group > 0 ? group : B,
+                                          spec);
   VML_LAUNCHED(1);
   return VML_OK;
 }

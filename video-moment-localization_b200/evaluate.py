@@ -7,6 +7,7 @@ Temporal NMS is OFF by default, like the reference (utils.py:14 "NMS NOT IMPLEME
 """
 from __future__ import annotations
 
+import ctypes
 from collections import defaultdict
 from fractions import Fraction
 
@@ -24,16 +25,26 @@ def _as_u8(t):
 
 
 def score_topk_recall(pm, ps, pe, moment_mask, sm, k: int = 5, nms_threshold: float = 1.0, counts=None, step_counts=None,
-                      step_group: int = 0):
-    """One launch: scores, top-k indices/scores/IoUs per sample, and the 8 hit counters
-    (int64 [2,4], accumulated in place when ``counts`` is given; ``step_counts``, optional, is a
-    second accumulator for per-step read-back).  Everything stays on the device."""
+                      step_group: int = 0, n=None, m=None):
+    """One launch: scores, top-k indices/scores/IoUs per sample, and the hit counters
+    (int64 [len(n), len(m)] -- [2,4] for the reference defaults --, accumulated in place when ``counts`` is given;
+    ``step_counts``, optional, is a second accumulator for per-step read-back).  Everything stays on the device.
+    ``n`` / ``m``: the caller's own lists (utils.py:10); ``None`` = the reference defaults."""
     if not pm.is_cuda:
         raise L_.VmlError("vml_b200.evaluate runs on CUDA only; there is no CPU path")
     B, L = pm.shape[0], pm.shape[1]
     dev = pm.device
+    default_nm = n is None and m is None
+    ns = list(_NS) if n is None else [int(x) for x in n]
+    ms = list(_MS) if m is None else [float(x) for x in m]
+    if not default_nm:
+        if not (1 <= len(ns) <= 8 and 1 <= len(ms) <= 8) or min(ns) < 1:
+            raise ValueError("compute_ious: 1..8 values of n (each >= 1) and 1..8 values of m")
+        k = max(ns)                      # the reference takes topk(max(n)) (utils.py:23)
+    if k > min(32, L * L):
+        raise ValueError("compute_ious: max(n) must be <= min(32, L*L)")
     if counts is None:
-        counts = torch.zeros(2, 4, device=dev, dtype=torch.int64)
+        counts = torch.zeros(len(ns), len(ms), device=dev, dtype=torch.int64)
     top_idx = torch.empty(B, k, device=dev, dtype=torch.int32)
     top_score = torch.empty(B, k, device=dev, dtype=torch.float32)
     top_iou = torch.empty(B, k, device=dev, dtype=torch.float32)
@@ -41,21 +52,26 @@ def score_topk_recall(pm, ps, pe, moment_mask, sm, k: int = 5, nms_threshold: fl
     # keep every converted operand referenced until the launch is enqueued
     pm_, ps_, pe_, sm_ = (t.float().contiguous() for t in (pm, ps, pe, sm))
     mask_ = _as_u8(moment_mask)
-    call("vml_score_topk_recall", ptr(pm_), ptr(ps_), ptr(pe_), ptr(mask_), ptr(sm_), B, L, k, fr.numerator, fr.denominator,
-         ptr(top_idx), ptr(top_score), ptr(top_iou), ptr(counts), ptr(step_counts), step_group, stream_ptr())
+    if default_nm:
+        call("vml_score_topk_recall", ptr(pm_), ptr(ps_), ptr(pe_), ptr(mask_), ptr(sm_), B, L, k, fr.numerator, fr.denominator,
+             ptr(top_idx), ptr(top_score), ptr(top_iou), ptr(counts), ptr(step_counts), step_group, stream_ptr())
+    else:
+        ns_c, ms_c = (ctypes.c_int32 * len(ns))(*ns), (ctypes.c_float * len(ms))(*ms)      # host arrays, read at enqueue time
+        call("vml_score_topk_recall_nm", ptr(pm_), ptr(ps_), ptr(pe_), ptr(mask_), ptr(sm_), B, L, k, fr.numerator, fr.denominator,
+             ptr(top_idx), ptr(top_score), ptr(top_iou), ptr(counts), ptr(step_counts), step_group,
+             ctypes.cast(ns_c, ctypes.c_void_p), len(ns), ctypes.cast(ms_c, ctypes.c_void_p), len(ms), stream_ptr())
     return top_idx, top_score, top_iou, counts
 
 
 def compute_ious(pm, ps, pe, moment_mask, sm, n=[1, 5], m=[0.1, 0.3, 0.5, 0.7], nms_threshold: float = 1.0):
     """Same signature and return value as the reference: dict 'R@{n}, IoU={m}' -> float count
     (the caller divides by num_samples, main.py:163,189,209).  One D2H copy of 8 counters."""
-    if list(n) != list(_NS) or [float(x) for x in m] != list(_MS):
-        raise ValueError("the fused kernel evaluates n in {1,5} and m in {0.1,0.3,0.5,0.7} (the reference defaults)")
-    _, _, _, counts = score_topk_recall(pm, ps, pe, moment_mask, sm, k=max(n), nms_threshold=nms_threshold)
+    n, m = list(n), list(m)
+    _, _, _, counts = score_topk_recall(pm, ps, pe, moment_mask, sm, k=max(n), nms_threshold=nms_threshold, n=n, m=m)
     host = counts.cpu()
     metrics = defaultdict(lambda: 0.0)
-    for a, n_ in enumerate(_NS):
-        for t, m_ in enumerate(_MS):
+    for a, n_ in enumerate(n):                     # key text = the caller's own values, like the f-string of utils.py:29
+        for t, m_ in enumerate(m):
             metrics[f"R@{n_}, IoU={m_}"] += float(host[a, t].item())
     return metrics
 

@@ -80,6 +80,7 @@ _SIGS = {
     "vml_localize": [_P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_scaled_iou_bce": [_P] * 13 + [_I, _I] + [_P] * 7 + [_P],
     "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
+    "vml_score_topk_recall_nm": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _P],
 }
 _RET = {"vml_last_error": C.c_char_p, "vml_kernel_names": C.c_char_p, "vml_launch_count": C.c_int64}
 

@@ -42,8 +42,9 @@ class _ScaledIouBce(torch.autograd.Function):
         out, grads = _launch(pm, ym, sm, moment_mask, ps, ys, ss, pe, ye, se, pa, ya, length_mask, need)
         if need:
             ctx.save_for_backward(*grads)
-        ctx.mark_non_differentiable(out[1:])
-        return out[0], out[1:]
+        parts = out[1:]                      # ONE view object: the one marked is the one returned
+        ctx.mark_non_differentiable(parts)
+        return out[0], parts
 
     @staticmethod
     def backward(ctx, g_loss, _g_parts):

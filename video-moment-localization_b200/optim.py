@@ -18,6 +18,7 @@ class FusedAdam:
             raise L_.VmlError("FusedAdam needs fp32 CUDA parameters; there is no CPU path")
         L_.load()
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.generation = 0                 # number of steps applied to the flat buffer (diagnostics / tests)
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
@@ -30,6 +31,23 @@ class FusedAdam:
                 self.flat[o:o + k].copy_(p.reshape(-1))
                 p.data = self.flat[o:o + k].view(p.shape)            # the parameter now lives inside the flat buffer
                 o += k
+        self._offsets = self._param_offsets()
+
+    def _param_offsets(self):
+        out, o = [], 0
+        for p in self.params:
+            out.append(o)
+            o += p.numel()
+        return out
+
+    def _check_homed(self):
+        """A later ``model.to()`` / ``.float()`` / ``nn.LSTM.flatten_parameters`` rebinds ``p.data`` and would leave the
+        optimizer updating a dead buffer: refuse to step instead."""
+        base = self.flat.data_ptr()
+        for p, o in zip(self.params, self._offsets):
+            if p.data_ptr() != base + 4 * o:
+                raise L_.VmlError("FusedAdam: a parameter no longer lives in the optimizer's flat buffer (it was re-bound by "
+                                  ".to()/.float()/flatten_parameters after the optimizer was built); rebuild the optimizer")
 
     # -- checkpoint compatibility (main.py:270-274 saves {"epoch", "model", "optimizer": optimizer.state_dict()}) -----
     @property
@@ -92,9 +110,14 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0, gathered: bool = False):
+        self._check_homed()
         if not gathered:
             self.gather_grads()
         self.t += 1
         call("vml_adam_step", ptr(self.flat), ptr(self.flat_grad), ptr(self.m), ptr(self.v), self.flat.numel(), self.lr,
              self.betas[0], self.betas[1], self.eps, self.t, grad_scale, stream_ptr())
-        self.flat.add_(0)     # in-place torch op: bumps the version counter the parameter views share (drives SMIN's packed-weight cache)
+        # The kernel wrote the parameters behind autograd's back.  Each Parameter re-homed with ``p.data = view`` keeps its
+        # OWN version counter (it does not share ``flat``'s), so bump every one explicitly: SMIN's packed-weight cache is
+        # keyed on (data_ptr, _version) and must see the step.
+        torch.autograd.graph.increment_version(self.params)
+        self.generation += 1

@@ -13,6 +13,7 @@ tcgen05 path, ``precision='fp32'`` the CUDA-core validation path (1e-5 parity).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -519,7 +520,7 @@ class SMIN(nn.Module):
     """B200-native SMIN.  Interface of the reference ``models.SMIN`` (models.py:348,367)."""
 
     def __init__(self, T, L, C, D, dl, num_smi_layers, input_video_dim, max_query_length, lstm_hidden_size,
-                 device="cpu", precision: str = "bf16"):
+                 device="cpu", precision: Optional[str] = None):
         super().__init__()
         if D != 2 * lstm_hidden_size:
             raise ValueError("D must equal 2*lstm_hidden_size (models.py:81 multiplies fv[B,T,D] by fs[B,2H])")
@@ -528,7 +529,11 @@ class SMIN(nn.Module):
         self.T, self.L, self.C, self.D, self.dl = T, L, C, D, dl
         self.num_smi_layers, self.input_video_dim = num_smi_layers, input_video_dim
         self.max_query_length, self.lstm_hidden_size, self.device = max_query_length, lstm_hidden_size, device
-        self.precision = precision
+        # main.get_model (main.py:71) passes the ten positional arguments only: the arithmetic mode of a drop-in run is
+        # then chosen with VML_PRECISION=bf16|fp32 (default bf16: tcgen05 path; fp32: 1e-5 validation path)
+        self.precision = precision if precision is not None else os.environ.get("VML_PRECISION", "bf16")
+        if self.precision not in L_.PREC:
+            raise ValueError(f"precision must be one of {sorted(L_.PREC)}, got {self.precision!r}")
         # construction order mirrors the reference so the RNG stream yields the same init
         self.backbone = _Backbone(T, D, input_video_dim, lstm_hidden_size)
         self.pgm = _Holder()
