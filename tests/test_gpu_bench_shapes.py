@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 from gpu_util import dims_of, model_for, rel_err, scaled_err, unpack  # noqa: E402
 
 FP32_TOL, BF16_TOL = 1e-5, 1e-2          # north_star
-BF16_LOGIT_TOL = 1.5e-2                  # |logit - logit_ref|: ~2.7x tighter than what 1e-2 relative on p ~ 0.5 allows (4e-2)
+BF16_LOGIT_TOL = 5e-3                    # |logit - logit_ref|: 8x tighter than what 1e-2 relative on p ~ 0.5 allows (4e-2); measured 1e-3
 GOLDEN = [("charadessta_b64", "charadessta"), ("tacos_b64", "tacos"), ("activitynet_b16", "activitynet"), ("activitynet_b4", "activitynet")]
 
 

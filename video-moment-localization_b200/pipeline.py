@@ -132,9 +132,10 @@ def _canonical(batch: Dict[str, torch.Tensor]):
 
 class ScoringPipeline:
     def __init__(self, model: SMIN, slots: int = 3, coalesce: int = 1, use_graph: bool = True, nms_threshold: float = 1.0,
-                 split_content: bool = False):
+                 split_content: bool = False, timing_events: bool = False):
         L_.load()
         self.split_content = split_content
+        self.timing_events = timing_events     # pass-completion events carry timestamps (bench: steady-state window)
         self.model = model
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
@@ -190,7 +191,7 @@ class ScoringPipeline:
             for i, rb in enumerate(slot.readbacks):
                 if rb is not None:
                     rb.copy_(slot.step_counts[i], non_blocking=True)
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=self.timing_events)
             done.record(slot.stream)
         for t in slot.tickets:
             t.event = done
