@@ -178,6 +178,17 @@ VML_API int vml_make_labels(const double* times, const double* duration, const i
                             float* sm, uint8_t* ym, float* ss, uint8_t* ys, float* se, uint8_t* ye, uint8_t* ya,
                             uint8_t* length_mask, uint8_t* moment_mask, uint8_t* video_mask, void* stream);
 
+/* Fixed-length clip sampling on the device (dataset.py:40-74 get_fixed_length_features): raw [sum nfeats, d0] holds the
+ * videos' own clip features back to back, offsets [B+1] their row ranges.  frame_idx = round-half-even(spos + i*stride),
+ * stride = 1 (nfeats <= T) or nfeats/T, cut to T; video_features [B,T,d0] rows >= min(nfeats, T) are zero-filled,
+ * video_mask [B,T] (optional) marks the live rows, nfeats [B] = min(nfeats, T); start_index / end_index [B] are the
+ * sampled-clip indices of the normalised ground-truth positions (dataset.py:57-62).  spos [B] (optional; NULL = 0, the
+ * non-training splits) is the caller's random start offset (dataset.py:44-49).  status (device int32, OR-ed): bit 1 = a
+ * sample whose index list fits neither nfeats nor T -- where the reference raises its AssertionError. */
+VML_API int vml_sample_clips(const float* raw, const int64_t* offsets, const int32_t* spos, const double* start_pos,
+                             const double* end_pos, int B, int T, int d0, float* video_features, uint8_t* video_mask,
+                             int64_t* nfeats, int32_t* start_index, int32_t* end_index, int32_t* status, void* stream);
+
 /* ---- a5+a6: ContentUnit (models.py:207-226,242-276) ----------------------------------------- */
 
 /* middle of the unit: c_hat act [n*C, dl] -> cc_hat act [n*C, dl]
@@ -225,13 +236,16 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
  * Scratch: g_scratch float [B,L,D] (the gated rows G), ab_scratch float [B,L,L] (the attention rows A_b).
  * bu float [B,L,D] = f_bb + f_b + f_bm.
  * fbar (optional, act [n, D]) receives sigmoid(fm*fs)*fm per cell (models.py:191 == :272-274),
- * which the fused content-out epilogue reuses instead of recomputing it per clip.
+ * which the fused content-out epilogue reuses instead of recomputing it per clip.  fbar_bias (optional, float [D]) is
+ * added to the STORED fbar before its rounding (not to f_bm): the content unit's output bias b_c then travels with the gate
+ * term, and vml_content_unit called with bc == NULL adds fbar only (its residual add runs on the tensor cores).
  * Three launches: gate and rows (warp-level TF32 mma; 3xTF32 split in VML_FP32), then a streaming pass over
  * the map cells (one CTA per map row). */
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask,
                       const uint8_t* length_mask, vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu,
-                      void* fbar, float* prob_out, float* u_out, int B, vml_dims_t d, int prec, void* stream);
+                      void* fbar, const float* fbar_bias, float* prob_out, float* u_out, int B, vml_dims_t d, int prec,
+                      void* stream);
 /* prob_out (optional, float [B,L,Nq]) and u_out (optional, float [B,L,D] = Aq*lmask + fs) are the saved
  * activations the backward pass needs (training path only). */
 

@@ -87,8 +87,8 @@ int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*,
 int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
                       void*, int, vml_dims_t, int, cudaStream_t);
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
-                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, float*, float*, int, vml_dims_t, int,
-                  cudaStream_t);
+                  const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, const float*, float*, float*, int,
+                  vml_dims_t, int, cudaStream_t);
 // backward.cu
 int colsum(const float*, int64_t, int64_t, float*, int64_t, int, int, int, const int32_t*, int, float, cudaStream_t);
 int localize_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
@@ -114,8 +114,10 @@ int gemm_res(const void*, const void*, const float*, const void*, const void*, v
 int content_tc(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
                vml_cells_t, void*, int, vml_dims_t, cudaStream_t);
 int content_unit(const void*, const void*, const float*, const float*, int, int, int, int, const float*, int, const uint8_t*,
-                 vml_cells_t, const void*, const float*, const void*, void*, void*, int, int, vml_dims_t, int, cudaStream_t);
+                 vml_cells_t, const void*, const float*, const void*, void*, void*, int, int, vml_dims_t, int, int, cudaStream_t);
 bool content_unit_supported(vml_dims_t);
+int sample_clips(const float*, const int64_t*, const int32_t*, const double*, const double*, int, int, int, float*, uint8_t*,
+                 int64_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int make_labels(const double*, const double*, const int64_t*, int, int, int, float*, uint8_t*, float*, uint8_t*, float*, uint8_t*,
                 uint8_t*, uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
 int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, int, cudaStream_t);
@@ -262,6 +264,13 @@ VML_API int vml_copy_h2d_async(void* dst, const void* src_pinned, int64_t bytes,
   return VML_OK;
 }
 
+VML_API int vml_sample_clips(const float* raw, const int64_t* offsets, const int32_t* spos, const double* start_pos,
+                             const double* end_pos, int B, int T, int d0, float* video_features, uint8_t* video_mask,
+                             int64_t* nfeats, int32_t* start_index, int32_t* end_index, int32_t* status, void* stream) {
+  return sample_clips(raw, offsets, spos, start_pos, end_pos, B, T, d0, video_features, video_mask, nfeats, start_index,
+                      end_index, status, ST(stream));
+}
+
 VML_API int vml_make_labels(const double* times, const double* duration, const int64_t* nfeats, int B, int T, int L, float* sm,
                     uint8_t* ym, float* ss, uint8_t* ys, float* se, uint8_t* ye, uint8_t* ya, uint8_t* length_mask,
                     uint8_t* moment_mask, uint8_t* video_mask, void* stream) {
@@ -275,8 +284,10 @@ VML_API int vml_content_unit(const void* fc, const void* W_chat, const float* b_
                      const void* Wc, const float* bc, const void* fbar, void* cu, void* mu_operand, int B, vml_dims_t d,
                      int store_cu, void* stream) {
   VML_CHECK_ARG(fc && W_chat && Wc && fbar && cu && mu_operand);
+  // bc == NULL: the output bias is already inside fbar (vml_boundary_unit's fbar_bias) -> the kernel variant whose residual
+  // add runs on the tensor cores and whose epilogue only adds fbar
   return content_unit(fc, W_chat, b_chat, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, query_mask, cells, Wc, bc, fbar, cu,
-                      (bf16*)mu_operand + d.D, 2 * d.D, B, d, store_cu, ST(stream));
+                      (bf16*)mu_operand + d.D, 2 * d.D, B, d, store_cu, bc == nullptr ? 1 : 0, ST(stream));
 }
 
 VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc, const void* fc, const void* fm, const float* fs,
@@ -301,11 +312,11 @@ VML_API int vml_content_out(const void* cc_hat, const void* Wc, const float* bc,
 
 VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                       const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
-                      vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar, float* prob_out, float* u_out,
-                      int B, vml_dims_t d, int prec, void* stream) {
+                      vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar, const float* fbar_bias,
+                      float* prob_out, float* u_out, int B, vml_dims_t d, int prec, void* stream) {
   VML_PREC_OK(prec);
   return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, ab_scratch, bu,
-                       fbar, prob_out, u_out, B, d, prec, ST(stream));
+                       fbar, fbar_bias, prob_out, u_out, B, d, prec, ST(stream));
 }
 
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {

@@ -569,7 +569,7 @@ template <typename ActT, int NG, bool PRECISE>
 __global__ void __launch_bounds__(128)
 boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const ActT* __restrict__ fm,
                        const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
-                       ActT* __restrict__ fbar, int n_rows, int L, int D, int capacity) {
+                       ActT* __restrict__ fbar, const float* __restrict__ fbar_bias, int n_rows, int L, int D, int capacity) {
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int grow = blockIdx.x * 4 + warp;              // b * L + i
   if (grow >= n_rows) return;
@@ -577,12 +577,16 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
   const int n_lo = row_start[grow], n_hi = min(row_start[grow + 1], capacity);
   if (n_lo >= n_hi) return;                            // empty row: bu stays f_bb + f_b (A_b row is all zero there)
   const float* arow = ab + (size_t)grow * L;
-  f8 s8[NG], bm[NG];
+  // fbar_bias (optional): added to the STORED fbar only (before its rounding) -- the consumer's output bias travels with it
+  f8 s8[NG], bm[NG], fb8[NG];
 #pragma unroll
   for (int q = 0; q < NG; ++q) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s8[q].v[e] = 0.f; bm[q].v[e] = 0.f; }
-    if (q * 256 + lane * 8 < D) s8[q] = ld8(fs + (size_t)b * D + q * 256 + lane * 8);
+    for (int e = 0; e < 8; ++e) { s8[q].v[e] = 0.f; bm[q].v[e] = 0.f; fb8[q].v[e] = 0.f; }
+    if (q * 256 + lane * 8 < D) {
+      s8[q] = ld8(fs + (size_t)b * D + q * 256 + lane * 8);
+      if (fbar_bias) fb8[q] = ld8(fbar_bias + q * 256 + lane * 8);
+    }
   }
   constexpr int CB = 4;
   for (int seg = n_lo; seg < n_hi; seg += 32) {        // 32 cells of the row per segment
@@ -614,7 +618,11 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
                 gv.v[e] = PRECISE ? sigmoidf_(z) * x : __fdividef(x, 1.0f + __expf(-z));
                 bm[q].v[e] = fmaf(a, gv.v[e], bm[q].v[e]);
               }
-              if (fbar) st8(fbar + (size_t)(seg + c0 + u) * D + q * 256 + lane * 8, gv);
+              if (fbar) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gv.v[e] += fb8[q].v[e];
+                st8(fbar + (size_t)(seg + c0 + u) * D + q * 256 + lane * 8, gv);
+              }
             }
         }
       }
@@ -647,17 +655,17 @@ static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, fl
 }
 
 template <typename ActT, int NG, bool PRECISE>
-static int launch_stream(const float* ab, const float* fs, const void* fm, vml_cells_t cells, float* bu, void* fbar, int B,
-                         vml_dims_t d, cudaStream_t st) {
+static int launch_stream(const float* ab, const float* fs, const void* fm, vml_cells_t cells, float* bu, void* fbar,
+                         const float* fbar_bias, int B, vml_dims_t d, cudaStream_t st) {
   boundary_stream_kernel<ActT, NG, PRECISE><<<ceil_div(B * d.L, 4), 128, 0, st>>>(
-      ab, fs, (const ActT*)fm, cells.code, cells.row_start, bu, (ActT*)fbar, B * d.L, d.L, d.D, cells.capacity);
+      ab, fs, (const ActT*)fm, cells.code, cells.row_start, bu, (ActT*)fbar, fbar_bias, B * d.L, d.L, d.D, cells.capacity);
   return VML_OK;
 }
 
 int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                   const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
-                  float* g_scratch, float* ab_scratch, float* bu, void* fbar, float* prob_out, float* u_out, int B, vml_dims_t d,
-                  int prec, cudaStream_t st) {
+                  float* g_scratch, float* ab_scratch, float* bu, void* fbar, const float* fbar_bias, float* prob_out, float* u_out,
+                  int B, vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.Nq <= BMM_MAXQ && d.D % 64 == 0 && d.D <= 64 * BMM_MAXD64 && d.L <= 248 && ld % 4 == 0 && off_kbt % 4 == 0);
   VML_CHECK_ARG(g_scratch != nullptr && ab_scratch != nullptr);
   static bool reg = (register_kernel("boundary_gate_mma_kernel"), register_kernel("boundary_rows_mma_kernel"),
@@ -691,10 +699,10 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   if (rc) return rc;
   }
   const int ng = ceil_div(d.D, 256);
-  if (prec == VML_FP32) rc = ng <= 1 ? launch_stream<float, 1, true>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st)
-                                     : launch_stream<float, 2, true>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st);
-  else rc = ng <= 1 ? launch_stream<bf16, 1, false>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st)
-                    : launch_stream<bf16, 2, false>(ab_scratch, fs, fm, cells, bu, fbar, B, d, st);
+  if (prec == VML_FP32) rc = ng <= 1 ? launch_stream<float, 1, true>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st)
+                                     : launch_stream<float, 2, true>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st);
+  else rc = ng <= 1 ? launch_stream<bf16, 1, false>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st)
+                    : launch_stream<bf16, 2, false>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st);
   if (rc) return rc;
   VML_LAUNCHED(n_launched);
   return VML_OK;

@@ -28,6 +28,8 @@
 // TMEM columns: [0,128) c_hat accumulator; [128,256) A, later Y (even column blocks); [256,256+NW) S,
 // [256,384) later Y (odd column blocks) -- the aliases are phase-exclusive (Y MMAs are issued only after
 // every attention thread has finished reading S and A; the next tile's S/A only after Y was drained).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_umma.cuh"
 #include "sm100.cuh"
@@ -50,6 +52,10 @@ constexpr int CU_DL = 128, CU_WST = 2, CU_MAXKB = 8;
 #define VML_CU_ROW_WARPS 16
 #endif
 constexpr int CU_ROW_WARPS = VML_CU_ROW_WARPS, CU_ROW_THREADS = 32 * CU_ROW_WARPS, CU_THREADS = 64 + CU_ROW_THREADS + 32;   // + store warp
+// V2: + an unused filler warp + the mean_c drain warp (a warp reads TMEM lanes 32*(warp % 4)..+31: the drain needs lanes 0..31)
+constexpr int CU_DRAIN_WARP = (2 + CU_ROW_WARPS + 1 + 3) / 4 * 4, CU_THREADS_V2 = 32 * (CU_DRAIN_WARP + 1);
+constexpr int CU_TMEM_SIDE = 384;                    // V2: mean_c accumulator, lanes 0..31 x 128 columns
+constexpr int CU_M4_ROWS = 252, CU_M4_BYTES = 2 * CU_M4_ROWS * 16;   // V2: master pattern of the mean_c operand (see kernel)
 constexpr int CU_SPLIT = CU_ROW_WARPS / 4;           // threads per tile row (one per TMEM-lane-sharing warp)
 constexpr int CU_COLS = 128 / CU_SPLIT;              // columns of a 128-column block each of them owns
 static_assert(CU_ROW_WARPS == 8 || CU_ROW_WARPS == 16, "2 or 4 row warps per TMEM lane quadrant");
@@ -58,7 +64,14 @@ constexpr int CU_BOX = UG_BM * UG_BK * 2;            // one 128 x 64 bf16 box (1
 constexpr int CU_CS_BYTES = UG_BM * CU_DL * 2;       // c_hat / cc_hat tile
 constexpr int CU_TMEM_A = 128, CU_TMEM_S = 256, CU_TMEM_Y0 = 128, CU_TMEM_Y1 = 256;
 
-template <int NQP, int GS>
+// V = 1: round-1 epilogue (bias, residual and fbar added in registers, mean_c by a shuffle reduce-scatter).
+// V = 3: V2 with mean_c on the tensor cores as well (side = M4 . out, out read back as an MN-major operand straight from the
+//        finished tile; a dedicated warp drains the 32 x 128 result) -- the row warps only add fbar, round and store.
+// V = 2: the output bias arrives folded into fbar (the boundary unit adds it before rounding), the residual X is added by
+//        the tensor cores (Y += X_box . I_16, one M=128,N=16,K=16 MMA per 16 columns: exact products, fp32 accumulation) and
+//        mean_c is read back from the finished bf16 tile in shared memory by one lane per (cell, 8-column piece) -- no
+//        shuffles, ~2.3x fewer instructions per output element in the phase that bounds the kernel.
+template <int NQP, int GS, int V = 3>
 struct CuCfg {
   static constexpr int NW = GS * NQP;                // word slots of a GS-sample group
   static constexpr int KG = NW / 8;
@@ -68,7 +81,7 @@ struct CuCfg {
   static constexpr int GG_BYTES = CU_SPLIT * UG_BM * 16;   // partial Grams (float4 per row thread), aliased onto Ps
   static constexpr int U_RAW = KS_BYTES + WT_BYTES + (PS_BYTES > GG_BYTES ? PS_BYTES : GG_BYTES);
   static constexpr int U_BYTES = (U_RAW + 1023) / 1024 * 1024;
-  static constexpr int SIDE_FLOATS = 2 * NW + CU_DL + CU_MAXKB * 64;   // beta | mask | b1 | b2
+  static constexpr int SIDE_FLOATS = 2 * NW + CU_DL + (V == 1 ? CU_MAXKB * 64 : 128 + (V == 3 ? CU_M4_BYTES / 4 : 0));   // beta | mask | b1 | b2 (V1) or I_16 + M4 (V2)
   static constexpr int X_BYTES = CU_MAXKB * CU_BOX;
   static constexpr int SMEM = X_BYTES + CU_CS_BYTES + U_BYTES + CU_WST * CU_BOX + SIDE_FLOATS * 4 + 1024 + 256;
 };
@@ -80,8 +93,8 @@ __device__ __forceinline__ uint4 cu_pack8(const float* v) {
   return u;
 }
 
-template <int NQP, int GS>
-__global__ void __launch_bounds__(CU_THREADS, 1)
+template <int NQP, int GS, int V>
+__global__ void __launch_bounds__(V == 3 ? CU_THREADS_V2 : CU_THREADS, 1)
 content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, int D,
                     const bf16* __restrict__ fbar, bf16* __restrict__ side, int ld_side,
@@ -89,7 +102,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     int off_what, int off_ktil, int off_beta, const float* __restrict__ s_hat, int s_ld,
                     const uint8_t* __restrict__ qmask, const int32_t* __restrict__ code, const int32_t* __restrict__ n_cells,
                     int Nq, int B, int store_cu) {
-  using Cfg = CuCfg<NQP, GS>;
+  using Cfg = CuCfg<NQP, GS, V>;
   constexpr int NW = Cfg::NW, KG = Cfg::KG;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
@@ -105,8 +118,14 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   float* s_beta = reinterpret_cast<float*>(Wr + CU_WST * CU_BOX);   // [NW]
   float* s_mask = s_beta + NW;                                      // [NW]
   float* s_b1 = s_mask + NW;                                        // [128]
-  float* s_b2 = s_b1 + CU_DL;                                       // [D]
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(s_b2 + CU_MAXKB * 64);
+  float* s_b2 = s_b1 + CU_DL;                                       // V1: [D] output bias;  V2: I_16 (bf16 16x16 identity, 512 B)
+  unsigned char* I16 = reinterpret_cast<unsigned char*>(s_b2);
+  // V2: mean over a cell's 4 clips on the tensor cores, side[c, n] = sum_r M4[c, r] out[r, n] with M4[c, r] = 0.25 [r / 4 == c].
+  // Per K step s (tile rows 16s..16s+15) the A operand is A_s[m, k] = 0.25 [m == 4s + k / 4] = P[m - 4s, k]: ONE master
+  // pattern P[m', k] = 0.25 [m' == k / 4], m' in [-124, 127], stored K-major with its rows 16 bytes apart (sbo 128) and its two
+  // 8-column groups CU_M4_ROWS * 16 bytes apart; the descriptor of step s just starts 4s rows earlier.
+  unsigned char* M4 = I16 + 512;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(s_b2 + (V == 1 ? CU_MAXKB * 64 : 128 + (V == 3 ? CU_M4_BYTES / 4 : 0)));
   uint64_t* xfree = xfull + CU_MAXKB;      // [4] per column block
   uint64_t* wfull = xfree + 4;
   uint64_t* wempty = wfull + CU_WST;
@@ -117,7 +136,10 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* yfull = afull_bar + 1;         // [2]
   uint64_t* yempty = yfull + 2;            // [2]
   uint64_t* sready = yempty + 2;           // [2] column block finished in shared memory -> store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sready + 2);
+  uint64_t* cs_free = sready + 2;          // V2: the last column block's output (staged in Cs) has been stored
+  uint64_t* side_full = cs_free + 1;       // V2: mean_c MMAs of a column block have completed
+  uint64_t* side_empty = side_full + 1;    // V2: the drain warp has read the mean_c accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int M = *n_cells * 4;
@@ -142,6 +164,9 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       ptx::mbar_init(&yfull[i], 1); ptx::mbar_init(&yempty[i], CU_ROW_WARPS);
       ptx::mbar_init(&sready[i], CU_ROW_THREADS);
     }
+    ptx::mbar_init(cs_free, 1);
+    ptx::mbar_init(side_full, 1);
+    ptx::mbar_init(side_empty, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -157,7 +182,10 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const uint32_t ph = it & 1;
         const int m0 = tile * UG_BM;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kq = 0; kq < KB; ++kq) {
+          // V2: the last column block's boxes are released first (by the tensor cores, see the MMA issuer), so the next
+          // tile's main loop starts with them; the in-place blocks follow in the order their stores complete
+          const int kb = V >= 2 ? (kq + KB - 2) % KB : kq;
           if ((kb & 1) == 0) ptx::mbar_wait(&xfree[kb >> 1], ph ^ 1);      // previous tile's column block has been stored
           ptx::mbar_arrive_expect_tx(&xfull[kb], CU_BOX);
           ptx::tma_load_2d(Xs + kb * CU_BOX, &tmX, &xfull[kb], kb * UG_BK, m0);
@@ -184,7 +212,8 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       uint32_t yi = 0, it = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const uint32_t ph = it & 1;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kq = 0; kq < KB; ++kq) {
+          const int kb = V >= 2 ? (kq + KB - 2) % KB : kq;       // same order as the producer
           ptx::mbar_wait(&xfull[kb], ph);
           ptx::mbar_wait(&wfull[wst], wph);
           ptx::tc_fence_after();
@@ -192,7 +221,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(Wr + wst * CU_BOX));
 #pragma unroll
           for (int k = 0; k < UG_BK / 16; ++k)
-            ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kq | k) != 0);
           ptx::umma_commit(&wempty[wst]);
           if (++wst == CU_WST) { wst = 0; wph ^= 1; }
         }
@@ -218,6 +247,21 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             ptx::umma_commit(&wempty[wst]);
             if (++wst == CU_WST) { wst = 0; wph ^= 1; }
           }
+          if (V >= 2) {
+            // residual on the tensor cores: Y[:, 64j + 16s ..+16) += X_box(2nb + j)[:, 16s ..+16) . I_16^T
+            constexpr uint32_t idesc_r = ptx::umma_idesc_bf16(UG_BM, 16);
+            const uint64_t idn = ptx::umma_desc_nosw(ptx::smem_u32(I16), 128, 256);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t xdesc = ptx::umma_desc_sw128(ptx::smem_u32(Xs + (2 * nb + j) * CU_BOX));
+#pragma unroll
+              for (int k = 0; k < UG_BK / 16; ++k)
+                ptx::umma_bf16(d_tmem + (uint32_t)(64 * j + 16 * k), xdesc + (uint64_t)(k * 2), idn, idesc_r, true);
+            }
+            // The LAST column block's output is staged in Cs (dead once these MMAs have read cc_hat), not in place: its X
+            // boxes are free for the next tile's loads as soon as the tensor cores have consumed them
+            if (nb == NB - 1) ptx::umma_commit(&xfree[nb]);
+          }
           ptx::umma_commit(&yfull[yb]);
           CU_TX(20 + 3 * nb);
         }
@@ -227,29 +271,88 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (lane == 0) {                                    // ===================== store warp =====================
       // Waiting for a TMA store to finish READING shared memory takes ~1 us; done here, off the row warps' path.
       uint32_t yi = 0;
+      // V3: mean over the cell's 4 clips of the finished block: 8 K steps (16 tile rows) x 2 boxes, M = 128 (32 rows used),
+      // N = 64, A = the shifted master pattern, B = the box itself read MN-major.  Block counter c: phase of side_full / side_empty.
+      auto side_mma = [&](const unsigned char* boxes, uint32_t c) {
+        ptx::mbar_wait(side_empty, (c & 1) ^ 1);               // the drain warp has read the previous block's result
+        ptx::tc_fence_after();
+        constexpr uint32_t idesc_m = ptx::umma_idesc_bf16_bmn(UG_BM, 64);
+        const uint32_t m4 = ptx::smem_u32(M4);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t b0 = ptx::smem_u32(boxes + j * CU_BOX);
+#pragma unroll
+          for (int ks = 0; ks < UG_BM / 16; ++ks)
+            ptx::umma_bf16(tmem_base + CU_TMEM_SIDE + (uint32_t)(64 * j),
+                           ptx::umma_desc_nosw(m4 + (uint32_t)((124 - 4 * ks) * 16), CU_M4_ROWS * 16, 128),
+                           ptx::umma_desc_sw128_mn(b0 + (uint32_t)(ks * 2048)), idesc_m, ks != 0);
+        }
+        ptx::umma_commit(side_full);
+      };
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int m0 = tile * UG_BM;
         for (int nb = 0; nb < NB; ++nb, ++yi) {
           const uint32_t yb = yi & 1;
           ptx::mbar_wait(&sready[yb], (yi >> 1) & 1);
+          const bool in_cs = V >= 2 && nb == NB - 1;             // V2: the last block was staged in Cs
+          const unsigned char* src = in_cs ? Cs : Xs + (2 * nb) * CU_BOX;
           if (store_cu) {
-            ptx::tma_store_2d(&tmOut, Xs + (2 * nb) * CU_BOX, nb * 128, m0);
-            ptx::tma_store_2d(&tmOut, Xs + (2 * nb + 1) * CU_BOX, nb * 128 + 64, m0);
+            ptx::tma_store_2d(&tmOut, src, nb * 128, m0);
+            ptx::tma_store_2d(&tmOut, src + CU_BOX, nb * 128 + 64, m0);
             ptx::bulk_commit();
-            if (nb > 0) {                                      // the previous column block has left shared memory
-              ptx::bulk_wait_read<1>();
-              ptx::mbar_arrive(&xfree[nb - 1]);
-            }
-            if (nb == NB - 1) {
+            if (V >= 2) {
+              // this warp has nothing else to do until the next block is ready (>= 1 us away): wait for its own store to
+              // have read shared memory and hand the boxes back at once (V1 released a block one block late)
+              if (V == 3) side_mma(src, yi);
               ptx::bulk_wait_read<0>();
-              ptx::mbar_arrive(&xfree[nb]);
+              if (V == 3) ptx::mbar_wait(side_full, yi & 1);     // ... and the mean_c MMAs to have read them too
+              ptx::mbar_arrive(in_cs ? cs_free : &xfree[nb]);
+            } else {
+              if (nb > 0) {                                    // the previous column block has left shared memory
+                ptx::bulk_wait_read<1>();
+                ptx::mbar_arrive(&xfree[nb - 1]);
+              }
+              if (nb == NB - 1) {
+                ptx::bulk_wait_read<0>();
+                ptx::mbar_arrive(&xfree[nb]);
+              }
             }
           } else {
-            ptx::mbar_arrive(&xfree[nb]);                      // nothing to store: the boxes are free at once
+            if (V == 3) { side_mma(src, yi); ptx::mbar_wait(side_full, yi & 1); }
+            ptx::mbar_arrive(in_cs ? cs_free : &xfree[nb]);    // nothing to store: the boxes are free at once
           }
         }
       }
     }
+  } else if (V == 3 && warp == CU_DRAIN_WARP) {
+    // ===================== mean_c drain warp (V3): TMEM lanes 0..31 = the tile's 32 cells, 128 columns per block =====================
+    uint32_t c = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int cell = tile * (UG_BM / 4) + lane;
+      const bool live = cell * 4 < M;
+      for (int nb = 0; nb < NB; ++nb, ++c) {
+        ptx::mbar_wait(side_full, c & 1);
+        ptx::tc_fence_after();
+        uint4* dst = reinterpret_cast<uint4*>(side + (size_t)cell * ld_side + nb * 128);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {                          // 32 columns at a time (register budget of the whole CTA)
+          float v[32];
+          ptx::tmem_ld32(tmem_base + CU_TMEM_SIDE + (uint32_t)(32 * q), v);
+          ptx::tmem_ld_wait();
+          if (q == 3) {                                        // accumulator drained: the next block's MMAs may overwrite it
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(side_empty);
+          }
+          if (live) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[4 * q + e] = cu_pack8(v + 8 * e);
+          }
+        }
+      }
+    }
+  } else if (warp >= 2 + CU_ROW_WARPS) {
+    // (V3: the filler warp between the store warp and the drain warp has no work)
   } else {
     // ===================== row warps (8): thread pair == tile row == (cell, clip) =====================
     // warp w serves TMEM lane quadrant w % 4; the two warps of a quadrant (grp 0 / 1) split every per-row loop by
@@ -265,7 +368,21 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const float inv_sqrt_dl = 1.0f / sqrtf((float)CU_DL);
     float4* s_gg = reinterpret_cast<float4*>(Ps);         // partial Grams, exchanged between a row's two threads (Ps is dead by then)
     if (at < CU_DL) s_b1[at] = bias1[at];
-    for (int e = at; e < D; e += CU_ROW_THREADS) s_b2[e] = bias2[e];
+    if (V == 1) {
+      for (int e = at; e < D; e += CU_ROW_THREADS) s_b2[e] = bias2[e];
+    } else if (at < 256) {        // I_16, K-major core-matrix layout (lbo 128, sbo 256): element (n, k) = (n == k)
+      const int n = at >> 4, k = at & 15;
+      *reinterpret_cast<uint16_t*>(I16 + (n & 7) * 16 + (n >> 3) * 256 + (k >> 3) * 128 + (k & 7) * 2) = n == k ? (uint16_t)0x3F80 : (uint16_t)0;
+    }
+    if (V == 3) {
+      for (int e = at; e < CU_M4_BYTES / 4; e += CU_ROW_THREADS) reinterpret_cast<uint32_t*>(M4)[e] = 0u;
+      CU_ROW_BAR();
+      if (at < 16) {                                         // P[m', k] = 0.25 for k / 4 == m' (m' = 0..3), row index m' + 124
+        const int mp = at >> 2, k = at;
+        *reinterpret_cast<uint16_t*>(M4 + (mp + 124) * 16 + (k >> 3) * (CU_M4_ROWS * 16) + (k & 7) * 2) = (uint16_t)0x3E80;
+      }
+    }
+    if (V >= 2) ptx::fence_proxy_async();     // I_16, M4 -> visible to the MMAs (ordered before the first cc_ready / sready arrive)
     uint32_t s_phase = 0, a_phase = 0, yi = 0, it = 0;
     int staged_bg = -1;                                   // sample group whose query operands sit in Ks / Wt / s_beta / s_mask
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
@@ -320,6 +437,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (g == 0) {
           // ---- c_hat row out of TMEM: + bias, round to bf16 (what the unfused path stores), park in Cs ----
           ptx::mbar_wait(chat_full, ph);
+          if (V >= 2) ptx::mbar_wait(cs_free, ph ^ 1);        // the previous tile's last column block has left Cs
           CU_T(2);
           ptx::tc_fence_after();
           const uint32_t t_addr = tmem_base + lane_base;
@@ -519,16 +637,17 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int i = 0; i < NP; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
       for (int nb = 0; nb < NB; ++nb, ++yi) {
         const uint32_t yb = yi & 1, yph = (yi >> 1) & 1;
-        unsigned char* xb = Xs + (2 * nb + box_of) * CU_BOX;
+        unsigned char* xb = (V >= 2 && nb == NB - 1) ? Cs + box_of * CU_BOX : Xs + (2 * nb + box_of) * CU_BOX;
         ptx::mbar_wait_relaxed(&yfull[yb], yph);              // TMEM data: ordered by the tcgen05 fence below
         CU_T(9 + 2 * nb);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + lane_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0) + (uint32_t)(grp * CU_COLS);
-        const float* bcol = s_b2 + nb * 128 + grp * CU_COLS;
         float acc[CU_COLS];
         ptx::tmem_ld32(t_addr, acc);
         if (CU_COLS == 64) ptx::tmem_ld32(t_addr + 32u, acc + (CU_COLS - 32));
         ptx::tmem_ld_wait();
+        if constexpr (V == 1) {
+        const float* bcol = s_b2 + nb * 128 + grp * CU_COLS;
 #pragma unroll
         for (int pc = 0; pc < NP; ++pc) {
           const f8 xv = unpack8(*reinterpret_cast<const uint4*>(xb + ptx::sw128_off(r, pc0 + pc)));
@@ -571,6 +690,42 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               *reinterpret_cast<__nv_bfloat162*>(srow + nb * 128 + pc * 8 + (hi1 ? 4 : 0) + (hi2 ? 2 : 0)) = __floats2bfloat162_rn(m0, m1);
           }
         }
+        } else {
+          // V2: the accumulator already holds cc_hat.W2^T + X (tensor cores); fbar carries the output bias.
+#pragma unroll
+          for (int pc = 0; pc < NP; ++pc) {
+            const f8 fv = unpack8(fq[pc]);
+            float* a = acc + pc * 8;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) ptx::add2(a[q], a[q + 1], fv.v[q], fv.v[q + 1]);
+            *reinterpret_cast<uint4*>(xb + ptx::sw128_off(r, pc0 + pc)) = cu_pack8(a);      // result in place of the residual
+          }
+          if constexpr (V == 2) {
+          __syncwarp();                                        // the warp's 32 rows x CU_COLS columns are in shared memory
+          // mean over a cell's 4 clips from the finished bf16 tile: one lane per (cell, 8-column piece); the four 16-byte
+          // reads of a quarter warp hit 8 distinct bank groups of the 128B swizzle (conflict-free), no shuffles
+#pragma unroll
+          for (int item = lane; item < 8 * NP; item += 32) {
+            const int c = item / NP, p = item % NP;            // cell within this warp's 8, piece within its CU_COLS columns
+            const int r0 = quad * 32 + 4 * c;
+            f8 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = unpack8(*reinterpret_cast<const uint4*>(xb + ptx::sw128_off(r0 + q, pc0 + p)));
+            float o[8];
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+              float a0 = v[0].v[q], a1 = v[0].v[q + 1], b0 = v[2].v[q], b1 = v[2].v[q + 1];
+              ptx::add2(a0, a1, v[1].v[q], v[1].v[q + 1]);                         // (r0 + r1)
+              ptx::add2(b0, b1, v[3].v[q], v[3].v[q + 1]);                         // (r2 + r3)
+              ptx::add2(a0, a1, b0, b1);
+              ptx::mul2(a0, a1, 0.25f, 0.25f);
+              o[q] = a0; o[q + 1] = a1;
+            }
+            if (m0 + r0 < M)
+              *reinterpret_cast<uint4*>(side + (size_t)((m0 + r0) >> 2) * ld_side + nb * 128 + grp * CU_COLS + p * 8) = cu_pack8(o);
+          }
+          }
+        }
         CU_T(38 + nb);
         if (nb + 1 < NB) {
 #pragma unroll
@@ -593,14 +748,14 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
 }
 
-template <int NQP, int GS>
+template <int NQP, int GS, int V>
 static int launch_content_unit(const CUtensorMap* tm, int grid, const bf16* fbar, bf16* side, int ld_side, const float* b1, const float* b2, const float* qproj, int ld,
                                int off_what, int off_ktil, int off_beta, const float* s_hat, int s_ld, const uint8_t* qmask,
                                vml_cells_t cells, int B, vml_dims_t d, int store_cu, cudaStream_t st) {
-  using Cfg = CuCfg<NQP, GS>;
+  using Cfg = CuCfg<NQP, GS, V>;
   static_assert(Cfg::SMEM <= 232448, "content_unit_kernel exceeds the 227 KB shared-memory limit");
-  VML_CUDA(ensure_dyn_smem((const void*)(content_unit_kernel<NQP, GS>), (size_t)(Cfg::SMEM)));
-  content_unit_kernel<NQP, GS><<<grid, CU_THREADS, Cfg::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], d.D, fbar, side, ld_side, b1, b2, qproj, ld,
+  VML_CUDA(ensure_dyn_smem((const void*)(content_unit_kernel<NQP, GS, V>), (size_t)(Cfg::SMEM)));
+  content_unit_kernel<NQP, GS, V><<<grid, V == 3 ? CU_THREADS_V2 : CU_THREADS, Cfg::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], d.D, fbar, side, ld_side, b1, b2, qproj, ld,
                                                                     off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells.code,
                                                                     cells.n_cells, d.Nq, B, store_cu);
   VML_LAUNCHED(1);
@@ -616,7 +771,7 @@ bool content_unit_supported(vml_dims_t d) {
 int content_unit(const void* fc, const void* W1, const float* b1, const float* qproj, int ld, int off_what, int off_ktil,
                  int off_beta, const float* s_hat, int s_ld, const uint8_t* qmask, vml_cells_t cells, const void* W2,
                  const float* b2, const void* fbar, void* cu, void* side, int ld_side, int B, vml_dims_t d, int store_cu,
-                 cudaStream_t st) {
+                 int bias_in_fbar, cudaStream_t st) {
   VML_CHECK_ARG(content_unit_supported(d) && ld % 4 == 0 && off_what % 4 == 0 && off_ktil % 4 == 0 && s_ld % 4 == 0 &&
                 ld_side % 8 == 0 && cells.capacity > 0);
   static bool reg = (register_kernel("content_unit_kernel"), true); (void)reg;
@@ -630,10 +785,21 @@ int content_unit(const void* fc, const void* W1, const float* b1, const float* q
   VML_CHECK_ARG((reinterpret_cast<uintptr_t>(fbar) & 15) == 0 && (reinterpret_cast<uintptr_t>(side) & 15) == 0);
   const int tiles = ceil_div((int)M, UG_BM);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-#define VML_CU(NQP, GS) return launch_content_unit<NQP, GS>(tm, grid, (const bf16*)fbar, (bf16*)side, ld_side, b1, b2, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, B, d, store_cu, st)
-  if (d.Nq + 1 <= 8) VML_CU(8, 2);
-  if (d.Nq + 1 <= 16) VML_CU(16, 2);
-  VML_CU(32, 1);
+#define VML_CU(NQP, GS, V) return launch_content_unit<NQP, GS, V>(tm, grid, (const bf16*)fbar, (bf16*)side, ld_side, b1, b2, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, B, d, store_cu, st)
+  if (bias_in_fbar) {            // V2 / V3: output bias folded into fbar by the boundary unit, residual on the tensor cores
+    const bool v2 = getenv("VML_CU_VARIANT") != nullptr && atoi(getenv("VML_CU_VARIANT")) == 2;   // (A/B knob) mean_c read back by the row warps
+    if (v2) {
+      if (d.Nq + 1 <= 8) VML_CU(8, 2, 2);
+      if (d.Nq + 1 <= 16) VML_CU(16, 2, 2);
+      VML_CU(32, 1, 2);
+    }
+    if (d.Nq + 1 <= 8) VML_CU(8, 2, 3);
+    if (d.Nq + 1 <= 16) VML_CU(16, 2, 3);
+    VML_CU(32, 1, 3);
+  }
+  if (d.Nq + 1 <= 8) VML_CU(8, 2, 1);
+  if (d.Nq + 1 <= 16) VML_CU(16, 2, 1);
+  VML_CU(32, 1, 1);
 #undef VML_CU
 }
 

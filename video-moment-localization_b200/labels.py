@@ -31,3 +31,31 @@ def make_labels(times: torch.Tensor, duration: torch.Tensor, nfeats: torch.Tenso
     for k in ("ym", "ys", "ye", "ya", "length_mask", "moment_mask"):
         o[k] = o[k].view(torch.bool)
     return o
+
+
+def sample_clips(raw: torch.Tensor, offsets: torch.Tensor, T: int, start_pos=None, end_pos=None, spos=None) -> Dict[str, torch.Tensor]:
+    """Fixed-length clip sampling of a whole batch on the device (``get_fixed_length_features``, dataset.py:40-74).
+
+    ``raw`` [sum nfeats, d0] float32: every video's own clip features back to back; ``offsets`` [B+1] int64 row ranges.
+    ``start_pos`` / ``end_pos`` [B]: normalised ground-truth positions (dataset.py:133-134); ``spos`` [B] int32: the random
+    start offsets of the training split (dataset.py:44-49; None = 0 as for val / test).  Returns video_features [B,T,d0],
+    video_mask [B,T,1] u8, nfeats [B] int64, start_index / end_index [B] int32 -- the values ``__getitem__`` collates."""
+    if not raw.is_cuda:
+        raise L_.VmlError("sample_clips runs on CUDA (sm_100a) only; there is no CPU path")
+    L_.load()
+    dev = raw.device
+    B, d0 = offsets.numel() - 1, raw.shape[1]
+    raw = raw.float().contiguous()
+    off = offsets.to(device=dev, dtype=torch.int64).contiguous()
+    f64 = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float64).to(dev).contiguous()
+    sp, ep = f64(start_pos), f64(end_pos)
+    so = None if spos is None else torch.as_tensor(spos, dtype=torch.int32).to(dev).contiguous()
+    out = {"video_features": torch.empty(B, T, d0, device=dev, dtype=torch.float32),
+           "video_mask": torch.empty(B, T, 1, device=dev, dtype=torch.uint8),
+           "nfeats": torch.empty(B, device=dev, dtype=torch.int64),
+           "start_index": torch.empty(B, device=dev, dtype=torch.int32), "end_index": torch.empty(B, device=dev, dtype=torch.int32)}
+    status = torch.zeros(1, device=dev, dtype=torch.int32)
+    call("vml_sample_clips", ptr(raw), ptr(off), ptr(so), ptr(sp), ptr(ep), B, T, d0, ptr(out["video_features"]), ptr(out["video_mask"]),
+         ptr(out["nfeats"]), ptr(out["start_index"]), ptr(out["end_index"]), ptr(status), stream_ptr())
+    out["status"] = status                  # bit 1: a sample on which the reference would raise its AssertionError
+    return out

@@ -57,10 +57,11 @@ _SIGS = {
     "vml_content_in_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _I, Dims, _P],
     "vml_copy_h2d_async": [_P, _P, _I64, _P],
     "vml_make_labels": [_P, _P, _P, _I, _I, _I] + [_P] * 10 + [_P],
+    "vml_sample_clips": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "vml_content_unit": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_content_unit_supported": [Dims],
     "vml_content_out": [_P, _P, _P, _P, _P, _P, _P, _P, Cells, _P, Dims, _I, _P],
-    "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_colsum": [_P, _I64, _I64, _P, _I64, _I, _I, _I, _P, _I, C.c_float, _P],
     "vml_localize_bwd": [_P] * 12 + [Cells, _P, _P, _P, _P, _I, Dims, _P],
     "vml_pair_bwd": [_P, _I, _P, Cells, _P, _I, Dims, _P],

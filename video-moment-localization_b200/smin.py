@@ -233,6 +233,7 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: Dims, prec: int, device) -> 
         pk[f"mu_b{k}"] = f32(sd[mu + "conv_layer_fb.bias"]) + f32(sd[mu + "conv_layer_fc.bias"])
     pk["qcat_w"], pk["qcat_b"] = gemm_weight(qw), qb.to(torch.float32).contiguous()
     lo = "localization.conv_layer_"
+    pk["zero_d"] = torch.zeros(D, device=device, dtype=torch.float32)
     pk["loc_w"] = torch.stack([f32(sd[lo + n + ".weight"]).reshape(D) for n in ("pm", "ps", "pe", "pa")], 0).contiguous()
     pk["loc_b"] = torch.cat([f32(sd[lo + n + ".bias"]).reshape(1) for n in ("pm", "ps", "pe", "pa")], 0).contiguous()
     return pk
@@ -436,6 +437,9 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     fbar = ws.get("fbar", (cap, D), act) if fused else None
     # whole content unit in one kernel (fc tile resident in shared memory: read once, written once per layer)
     one_kernel_cu = fused and dl == 128 and Nq <= 31 and D % 128 == 0 and D <= 512 and not split_content
+    # fast mode: the content unit's output bias b_c rides inside fbar (added by the boundary unit before the rounding), so the
+    # one-kernel content unit (bc = NULL: residual on the tensor cores) only adds fbar; VML_CU_V1=1 selects the round-1 kernel
+    bias_in_fbar = fused and os.environ.get("VML_CU_V1") is None
     n_dev = cells.n_cells
     two_chains = fused and side is not main
     cside = side if two_chains else main
@@ -447,7 +451,8 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         o = k * lay["blk"]
         # a7 boundary unit (main)
         call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
-             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar), None, None, B, dims, prec, st)
+             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar),
+             ptr(pk[f"cout_b{k}"]) if bias_in_fbar else None, None, None, B, dims, prec, st)
         mark("boundary_unit")
         ev_bu = None
         if two_chains:
@@ -462,8 +467,8 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
                 # the last layer's cu is consumed only through mean_c cu (the moment operand): skip its store
                 store_cu = 1 if (k + 1 < layers or keep is not None) else 0
                 call("vml_content_unit", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o, o + dl,
-                     o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]),
-                     ptr(fbar), ptr(fc[nxt]), ptr(mu_op), B, dims, store_cu, sst)
+                     o + 2 * dl + D, s_hat_base + k * dl * 4, ld, ptr(qmask), cells, ptr(pk[f"cout_w{k}"]),
+                     None if bias_in_fbar else ptr(pk[f"cout_b{k}"]), ptr(fbar), ptr(fc[nxt]), ptr(mu_op), B, dims, store_cu, sst)
                 mark("content_unit")
             elif fused and dl == 128 and Nq <= 31:
                 call("vml_content_in_attention", ptr(fc[cur]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(qproj), ld, o,
@@ -478,8 +483,8 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
                 mark("content_attention")
                 if ev_bu is not None:
                     cside.wait_event(ev_bu)         # fbar of this layer
-                call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(fc[cur]), ptr(fm[cur]),
-                     ptr(fs), ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
+                call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk["zero_d" if bias_in_fbar else f"cout_b{k}"]),
+                     ptr(fc[cur]), ptr(fm[cur]), ptr(fs), ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
                 mark("content_out_gemm")
         # a8 moment unit (main)
         if fused:

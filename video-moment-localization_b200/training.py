@@ -84,7 +84,7 @@ def train_forward(pk: Dict[str, torch.Tensor], dims: Dims, inp: dict) -> tuple:
         G, Ab, bu = E(B, Lm, D), E(B, Lm, Lm), E(B, Lm, D)
         Pw, U = torch.zeros(B, Lm, Nq, device=dev, dtype=F32), E(B, Lm, D)
         call("vml_boundary_unit", ptr(tp.qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(tp.fb[k]), ptr(tp.fm[k]),
-             ptr(qmask), ptr(lmask), cells, ptr(G), ptr(Ab), ptr(bu), None, ptr(Pw), ptr(U), B, dims, P, st)
+             ptr(qmask), ptr(lmask), cells, ptr(G), ptr(Ab), ptr(bu), None, None, ptr(Pw), ptr(U), B, dims, P, st)
         c_hat, cc_hat, cu = E(cap * Cc, dl), E(cap * Cc, dl), E(cap, Cc, D)
         call("vml_linear", ptr(tp.fc[k]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl,
              cells.n_cells, Cc, P, 0, st)
