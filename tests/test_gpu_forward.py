@@ -151,14 +151,14 @@ def test_cpu_input_raises():
         m(*[batch[k] for k in synth.MODEL_INPUT_KEYS])
 
 
-@pytest.mark.parametrize("variant", ["v1", "v2", "v3"])
+@pytest.mark.parametrize("variant", ["v1", "v2", "v3", "v4"])
 @pytest.mark.parametrize("name,B,rng", [("charadessta", 48, None), ("charadessta", 24, (1, 12)), ("tacos", 9, None),
                                         ("tacos", 16, (4, 20)), ("activitynet", 5, None), ("activitynet", 12, (2, 9))])
 def test_one_kernel_content_unit_against_split(name, B, rng, variant, monkeypatch):
     """vml_content_unit (fc tile resident in shared memory, one kernel per layer) against vml_content_in_attention +
     vml_content_out, over full tiles, ragged last tiles, multi-sample tiles and the skipped last-layer cu store.
     v1 (VML_CU_V1=1, the round-1 kernel) performs the same arithmetic in the same order: every layer's cu / fm / fb and
-    the final scores are BIT-IDENTICAL.  v2 / v3 (v3 = default) add the residual on the tensor cores (fp32 accumulation
+    the final scores are BIT-IDENTICAL.  v2 / v3 / v4 (v4 = default: streamed tile) add the residual on the tensor cores (fp32 accumulation
     inside the MMA instead of an FADD) and take mean_c from the rounded bf16 tile (v2: read back by the row warps, v3: by
     the tensor cores): cu within 1 bf16 ulp of the split path, the maps that follow within the drift that implies (all
     variants are separately held to the oracle at 1e-2 elsewhere)."""
@@ -167,8 +167,8 @@ def test_one_kernel_content_unit_against_split(name, B, rng, variant, monkeypatc
     monkeypatch.delenv("VML_CU_VARIANT", raising=False)
     if variant == "v1":
         monkeypatch.setenv("VML_CU_V1", "1")
-    elif variant == "v2":
-        monkeypatch.setenv("VML_CU_VARIANT", "2")
+    elif variant in ("v2", "v3"):
+        monkeypatch.setenv("VML_CU_VARIANT", variant[1])
     cfg = CONFIGS[name]
     params = init_params(cfg, 43)
     batch = synth.make_batch(cfg, B, 1300 + B, **({"nfeats_range": rng} if rng else {}))

@@ -80,3 +80,61 @@ def test_moment_gemm_cluster_variants_are_bit_identical(name, B, variant, monkey
     for a, c in zip(got, want):
         assert torch.equal(a, c)
     assert float(got[0].abs().sum()) > 0
+
+
+def _tf32_ref(A, B):
+    """fp64 product of the fp32 operands (what every variant approximates)."""
+    return (A.double() @ B.double().t()).float()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 520), (260, 132, 4100), (128, 128, 8192)])
+def test_gemm_tf32_all_operand_layouts(a_mn, b_mn, M, N, K):
+    """gemm_tf32_kernel (tcgen05 kind::tf32, operands straight from fp32 tensors by TMA): K-major and MN-major operands in all
+    four combinations, ragged M / N / K, plain store, accumulate and split-K (few output tiles).  Tolerance: TF32 inputs
+    (10-bit mantissa, rounded) with fp32 accumulation -> 2e-3 of the result's scale."""
+    from vml_b200 import lib
+    from vml_b200.training import _gemm
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    ref = _tf32_ref(A, B)
+    At, Bt = A.t().contiguous(), B.t().contiguous()                 # [K, M], [K, N]: the MN-major storage
+    a_args = (At.data_ptr(), 1, M, 0) if a_mn else (A.data_ptr(), K, 1, 0)
+    b_args = (Bt.data_ptr(), 1, N, 0) if b_mn else (B.data_ptr(), K, 1, 0)
+    ldc = N + 4
+    C = torch.full((M, ldc), 7.0, device="cuda")
+    _gemm(*a_args, *b_args, C.data_ptr(), ldc, 1, 0, M, N, K)
+    assert "gemm_tf32_kernel" in lib.kernel_names(), "the product did not take the tensor-core path"
+    scale = ref.abs().max().item()
+    assert (C[:, :N] - ref).abs().max().item() <= 2e-3 * scale
+    assert bool((C[:, N:] == 7.0).all()), "columns beyond N were touched"
+    # accumulate on top of existing values, with alpha
+    _gemm(*a_args, *b_args, C.data_ptr(), ldc, 1, 0, M, N, K, alpha=0.5, acc=1)
+    assert (C[:, :N] - 1.5 * ref).abs().max().item() <= 3e-3 * scale
+
+
+def test_gemm_tf32_device_limited_rows_and_contraction():
+    """Live row counts read from device memory: M (dX-type product) and K (dW-type product, both operands MN-major); rows
+    beyond the live count hold NaN and must influence nothing."""
+    from vml_b200.training import _gemm
+    torch.manual_seed(3)
+    cap, live, D1, D2 = 6000, 4321, 256, 384
+    n_dev = torch.tensor([live], device="cuda", dtype=torch.int32)
+    X = torch.randn(cap, D1, device="cuda")
+    Y = torch.randn(cap, D2, device="cuda")
+    X[live:] = float("nan")
+    Y[live:] = float("nan")
+    W = torch.randn(D2, D1, device="cuda")                        # Y ~ X.W^T
+    # dW[D2, D1] = sum_m Y[m, :]^T X[m, :]   (both MN-major, K = live rows)
+    dW = torch.zeros(D2, D1, device="cuda")
+    _gemm(Y.data_ptr(), 1, D2, 0, X.data_ptr(), 1, D1, 0, dW.data_ptr(), D1, 1, 0, D2, D1, cap, acc=1, splits=2, k_dev=n_dev.data_ptr())
+    ref = (Y[:live].double().t() @ X[:live].double()).float()
+    assert torch.isfinite(dW).all()
+    assert (dW - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    # dX[cap, D1] = Y . W   (A K-major with device-limited M, B MN-major)
+    dX = torch.zeros(cap, D1, device="cuda")
+    _gemm(Y.data_ptr(), D2, 1, 0, W.data_ptr(), 1, D1, 0, dX.data_ptr(), D1, 1, 0, cap, D1, D2, m_dev=n_dev.data_ptr())
+    ref = (Y[:live].double() @ W.double()).float()
+    assert (dX[:live] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert bool((dX[live:] == 0).all()), "rows beyond the live count were written"

@@ -160,3 +160,37 @@ def test_pipeline_scores_a_ragged_tail_batch(from_host):
         t.synchronize()
     for got, want in zip(rb, per_batch):
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("from_host", [True, False])
+def test_compact_batches_with_device_built_labels_equal_full_batches(from_host):
+    """SURVEY 8(f)-3 wired into the pipeline: a batch that carries only features, the word mask and (times, duration, nfeats)
+    -- masks and the IoU map built by vml_make_labels on the device -- scores bit-identically to the full 7-tensor batch, and
+    moves fewer bytes over PCIe (incl. a ragged tail batch)."""
+    from vml_b200.pipeline import COMPACT_KEYS, pack_host_batch
+    cfg = CONFIGS["charadessta"]
+    model = model_for(cfg, "bf16")
+    batches = [synth.make_batch(cfg, 8, 700 + i) for i in range(5)] + [synth.make_batch(cfg, 3, 799)]
+    ref = ScoringPipeline(model, slots=2, coalesce=2)
+    for b in batches:
+        ref.submit({k: b[k].cuda() for k in INPUT_KEYS})
+    want = ref.result(normalize=False)
+    pipe = ScoringPipeline(model, slots=2, coalesce=2)
+    tickets = []
+    for b in batches:
+        if from_host:
+            full, compact = pack_host_batch(b), pack_host_batch(b, compact=True)
+            assert compact["_blob"].numel() < full["_blob"].numel()
+            tickets.append(pipe.submit(compact, from_host=True))
+        else:
+            tickets.append(pipe.submit({k: b[k].cuda() for k in COMPACT_KEYS}))
+    assert pipe.result(normalize=False) == want
+    assert torch.equal(pipe.counts, ref.counts)
+    # the first group's scores, bit for bit
+    a = ScoringPipeline(model, slots=1, coalesce=1)
+    b_ = ScoringPipeline(model, slots=1, coalesce=1)
+    t1 = a.submit({k: batches[0][k].cuda() for k in INPUT_KEYS}); a.flush(); t1.synchronize()
+    src = pack_host_batch(batches[0], compact=True) if from_host else {k: batches[0][k].cuda() for k in COMPACT_KEYS}
+    t2 = b_.submit(src, from_host=from_host); b_.flush(); t2.synchronize()
+    for x, y in zip(t1.slot.outputs[0], t2.slot.outputs[0]):
+        assert torch.equal(x, y)

@@ -76,6 +76,31 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   return VML_OK;
 }
 
+// generic 2D map with 128B swizzle: dtype 0 = bf16, 1 = fp32 rounded to TF32 by the copy engine (plain fp32 if the driver
+// refuses that type); inner = contiguous dimension
+int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle = 3) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VML_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)outer_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType types[3] = {CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32};
+  CUresult r = CUDA_ERROR_UNKNOWN;
+  for (int t = dtype; t < (dtype == 1 ? 3 : dtype + 1); ++t) {
+    r = enc(map, types[t], 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) break;
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu stride=%llu B)", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)outer_stride_bytes);
+    return VML_ERR_CUDA; }
+  return VML_OK;
+}
+int launch_gemm_tf32(const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*, int64_t, int64_t, int, int, int, float, int,
+                     const int32_t*, int, const int32_t*, int, cudaStream_t);
+
 // stage launchers implemented in stages.cu / query_loss_eval.cu
 int build_cells(const uint8_t*, int, int, vml_cells_t, cudaStream_t);
 int unpack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
@@ -198,6 +223,12 @@ VML_API int vml_gemm_strided(const float* A, int64_t sam, int64_t sak, int64_t s
                              int64_t sbb, float* C, int64_t scm, int64_t scn, int64_t scb, int M, int N, int K, int batch,
                              float alpha, int accumulate, int splits, const int32_t* m_dev, int m_scale,
                              const int32_t* k_dev, int k_scale, void* stream) {
+  if (batch == 1) {
+    // large products: tcgen05 kind::tf32 straight from the caller's fp32 tensors (gemm_tf32.cu); 1 = not eligible
+    const int rc = launch_gemm_tf32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, alpha, accumulate, m_dev, m_scale, k_dev, k_scale,
+                                    ST(stream));
+    if (rc <= 0) return rc;
+  }
   SGemm g{A, sam, sak, sab, B, sbn, sbk, sbb, C, scm, scn, scb, M, N, K, batch, alpha, accumulate, splits, m_dev, m_scale, k_dev, k_scale};
   return launch_gemm_strided(g, ST(stream));
 }

@@ -63,8 +63,15 @@ static_assert(CU_ROW_WARPS == 8 || CU_ROW_WARPS == 16, "2 or 4 row warps per TME
 constexpr int CU_BOX = UG_BM * UG_BK * 2;            // one 128 x 64 bf16 box (16 KB)
 constexpr int CU_CS_BYTES = UG_BM * CU_DL * 2;       // c_hat / cc_hat tile
 constexpr int CU_TMEM_A = 128, CU_TMEM_S = 256, CU_TMEM_Y0 = 128, CU_TMEM_Y1 = 256;
+constexpr int CU_BAR_BYTES = 512;                    // mbarriers + the TMEM slot
 
 // V = 1: round-1 epilogue (bias, residual and fbar added in registers, mean_c by a shuffle reduce-scatter).
+// V = 4: V3's epilogue, but NO resident tile: the 128 KB it occupied become a ring of ~10 boxes through which the tile's X and
+//        W1 blocks stream for the first contraction and -- per output column block -- the W2 boxes plus the SAME X boxes
+//        again (an L2 hit: the SM read them microseconds ago) for the residual MMA; the finished block is written in place of
+//        those re-read boxes and stored from there.  With only two 16 KB weight stages in flight (all that fit beside a
+//        resident tile) the kernel was bound by the weight stream: 16 box round trips of ~1 us per tile, serialised with the
+//        row warps' work.  The deeper ring also lets tile t+1's first contraction run under tile t's attention phase.
 // V = 3: V2 with mean_c on the tensor cores as well (side = M4 . out, out read back as an MN-major operand straight from the
 //        finished tile; a dedicated warp drains the 32 x 128 result) -- the row warps only add fbar, round and store.
 // V = 2: the output bias arrives folded into fbar (the boundary unit adds it before rounding), the residual X is added by
@@ -81,9 +88,12 @@ struct CuCfg {
   static constexpr int GG_BYTES = CU_SPLIT * UG_BM * 16;   // partial Grams (float4 per row thread), aliased onto Ps
   static constexpr int U_RAW = KS_BYTES + WT_BYTES + (PS_BYTES > GG_BYTES ? PS_BYTES : GG_BYTES);
   static constexpr int U_BYTES = (U_RAW + 1023) / 1024 * 1024;
-  static constexpr int SIDE_FLOATS = 2 * NW + CU_DL + (V == 1 ? CU_MAXKB * 64 : 128 + (V == 3 ? CU_M4_BYTES / 4 : 0));   // beta | mask | b1 | b2 (V1) or I_16 + M4 (V2)
-  static constexpr int X_BYTES = CU_MAXKB * CU_BOX;
-  static constexpr int SMEM = X_BYTES + CU_CS_BYTES + U_BYTES + CU_WST * CU_BOX + SIDE_FLOATS * 4 + 1024 + 256;
+  static constexpr int SIDE_FLOATS = 2 * NW + CU_DL + (V == 1 ? CU_MAXKB * 64 : 128 + (V >= 3 ? CU_M4_BYTES / 4 : 0));   // beta | mask | b1 | b2 (V1) or I_16 + M4 (V2)
+  static constexpr int FIXED = CU_CS_BYTES + U_BYTES + SIDE_FLOATS * 4 + 1024 + CU_BAR_BYTES;
+  // V4: no resident tile -- ONE ring of 16 KB boxes (as many as fit) carries X, W1, W2 and the re-read X of the residual
+  static constexpr int RB = (232448 - FIXED) / CU_BOX;
+  static constexpr int X_BYTES = V == 4 ? RB * CU_BOX : CU_MAXKB * CU_BOX;
+  static constexpr int SMEM = X_BYTES + FIXED + (V == 4 ? 0 : CU_WST * CU_BOX);
 };
 
 __device__ __forceinline__ uint4 cu_pack8(const float* v) {
@@ -94,7 +104,7 @@ __device__ __forceinline__ uint4 cu_pack8(const float* v) {
 }
 
 template <int NQP, int GS, int V>
-__global__ void __launch_bounds__(V == 3 ? CU_THREADS_V2 : CU_THREADS, 1)
+__global__ void __launch_bounds__(V >= 3 ? CU_THREADS_V2 : CU_THREADS, 1)
 content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, int D,
                     const bf16* __restrict__ fbar, bf16* __restrict__ side, int ld_side,
@@ -115,7 +125,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   unsigned char* Wt = Ks + Cfg::KS_BYTES;
   unsigned char* Ps = Wt + Cfg::WT_BYTES;
   unsigned char* Wr = U + Cfg::U_BYTES;                        // weight ring
-  float* s_beta = reinterpret_cast<float*>(Wr + CU_WST * CU_BOX);   // [NW]
+  float* s_beta = reinterpret_cast<float*>(Wr + (V == 4 ? 0 : CU_WST * CU_BOX));   // [NW]  (V4 has no separate weight ring)
   float* s_mask = s_beta + NW;                                      // [NW]
   float* s_b1 = s_mask + NW;                                        // [128]
   float* s_b2 = s_b1 + CU_DL;                                       // V1: [D] output bias;  V2: I_16 (bf16 16x16 identity, 512 B)
@@ -125,7 +135,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   // pattern P[m', k] = 0.25 [m' == k / 4], m' in [-124, 127], stored K-major with its rows 16 bytes apart (sbo 128) and its two
   // 8-column groups CU_M4_ROWS * 16 bytes apart; the descriptor of step s just starts 4s rows earlier.
   unsigned char* M4 = I16 + 512;
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(s_b2 + (V == 1 ? CU_MAXKB * 64 : 128 + (V == 3 ? CU_M4_BYTES / 4 : 0)));
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(s_b2 + (V == 1 ? CU_MAXKB * 64 : 128 + (V >= 3 ? CU_M4_BYTES / 4 : 0)));
   uint64_t* xfree = xfull + CU_MAXKB;      // [4] per column block
   uint64_t* wfull = xfree + 4;
   uint64_t* wempty = wfull + CU_WST;
@@ -139,7 +149,13 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* cs_free = sready + 2;          // V2: the last column block's output (staged in Cs) has been stored
   uint64_t* side_full = cs_free + 1;       // V2: mean_c MMAs of a column block have completed
   uint64_t* side_empty = side_full + 1;    // V2: the drain warp has read the mean_c accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + 1);
+  uint64_t* chat_free = side_empty + 1;    // V4: the row warps have parked c_hat -> the next tile's first contraction may start
+  uint64_t* bfull = chat_free + 1;         // V4: [RB] box landed
+  uint64_t* bempty = bfull + 12;           // V4: [RB] box consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 12);
+  static_assert(Cfg::RB <= 12 && (24 + 12 + 12 + 12) * 8 + 8 <= CU_BAR_BYTES, "barrier block");
+  unsigned char* Ring = smem;              // V4: RB boxes (V < 4: this is Xs)
+  constexpr int RB = Cfg::RB;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int M = *n_cells * 4;
@@ -167,6 +183,8 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     ptx::mbar_init(cs_free, 1);
     ptx::mbar_init(side_full, 1);
     ptx::mbar_init(side_empty, 1);
+    ptx::mbar_init(chat_free, CU_ROW_THREADS);
+    for (int i = 0; i < 12; ++i) { ptx::mbar_init(&bfull[i], 1); ptx::mbar_init(&bempty[i], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -175,7 +193,142 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // V4: program order of the ring's boxes.  PER = 2 * KB boxes per phase (main: X(kb), W1(kb);  tail: per column block
+  // W2(nb, 0), W2(nb, 1), X(2nb), X(2nb + 1)); a CTA's sequence is main(0), then for t = 0..n-1: main(t + 1) (if any), tail(t)
+  const int n_my = tile_end - tile_begin, PER = 2 * KB;
+  auto base_main = [&](int t) { return t == 0 ? 0 : PER + 2 * PER * (t - 1); };
+  auto base_tail = [&](int t) { return PER + 2 * PER * t + (t + 1 < n_my ? PER : 0); };
+
+  if (V == 4 && warp == 0) {
+    if (lane == 0) {                                    // ===================== TMA producer (V4) =====================
+      auto load = [&](int bi, const CUtensorMap* tm, int c0, int c1) {
+        const int slot = bi % RB;
+        ptx::mbar_wait(&bempty[slot], ((bi / RB) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bfull[slot], CU_BOX);
+        ptx::tma_load_2d(Ring + slot * CU_BOX, tm, &bfull[slot], c0, c1);
+      };
+      auto do_main = [&](int t) {
+        const int base = base_main(t), m0 = (tile_begin + t) * UG_BM;
+        for (int kb = 0; kb < KB; ++kb) { load(base + 2 * kb, &tmX, kb * UG_BK, m0); load(base + 2 * kb + 1, &tmW1, kb * UG_BK, 0); }
+      };
+      auto do_tail = [&](int t) {
+        const int base = base_tail(t), m0 = (tile_begin + t) * UG_BM;
+        for (int nb = 0; nb < NB; ++nb) {
+          load(base + 4 * nb, &tmW2, 0, nb * 128);
+          load(base + 4 * nb + 1, &tmW2, UG_BK, nb * 128);
+          load(base + 4 * nb + 2, &tmX, (2 * nb) * UG_BK, m0);
+          load(base + 4 * nb + 3, &tmX, (2 * nb + 1) * UG_BK, m0);
+        }
+      };
+      if (n_my > 0) do_main(0);
+      for (int t = 0; t < n_my; ++t) {
+        if (t + 1 < n_my) do_main(t + 1);
+        do_tail(t);
+      }
+    }
+  } else if (V == 4 && warp == 1) {
+    if (lane == 0) {                                    // ===================== MMA issuer (V4): (1) and (4) =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(UG_BM, CU_DL);
+      constexpr uint32_t idesc_r = ptx::umma_idesc_bf16(UG_BM, 16);
+      const uint64_t idn = ptx::umma_desc_nosw(ptx::smem_u32(I16), 128, 256);
+      auto wait_box = [&](int bi) {
+        const int slot = bi % RB;
+        ptx::mbar_wait(&bfull[slot], (bi / RB) & 1);
+        return slot;
+      };
+      uint32_t yi = 0;
+      auto do_main = [&](int t) {
+        if (t > 0) ptx::mbar_wait(chat_free, (uint32_t)(t - 1) & 1);     // c_hat(t - 1) has left the accumulator
+        ptx::tc_fence_after();
+        const int base = base_main(t);
+        for (int kb = 0; kb < KB; ++kb) {
+          const int sx = wait_box(base + 2 * kb), sw = wait_box(base + 2 * kb + 1);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(Ring + sx * CU_BOX));
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(Ring + sw * CU_BOX));
+#pragma unroll
+          for (int k = 0; k < UG_BK / 16; ++k)
+            ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          ptx::umma_commit(&bempty[sx]);
+          ptx::umma_commit(&bempty[sw]);
+        }
+        ptx::umma_commit(chat_full);
+      };
+      auto do_tail = [&](int t) {
+        ptx::mbar_wait(cc_ready, (uint32_t)t & 1);       // cc_hat is in Cs; S and A have been read out of TMEM
+        ptx::tc_fence_after();
+        const uint32_t c0 = ptx::smem_u32(Cs);
+        const int base = base_tail(t);
+        for (int nb = 0; nb < NB; ++nb, ++yi) {
+          const uint32_t yb = yi & 1;
+          ptx::mbar_wait(&yempty[yb], ((yi >> 1) & 1) ^ 1);
+          const uint32_t d_tmem = tmem_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0);
+          int sw[2], sx[2];
+          for (int j = 0; j < 2; ++j) sw[j] = wait_box(base + 4 * nb + j);
+          for (int j = 0; j < 2; ++j) sx[j] = wait_box(base + 4 * nb + 2 + j);
+          ptx::tc_fence_after();
+          for (int kh = 0; kh < 2; ++kh) {
+            const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(Ring + sw[kh] * CU_BOX));
+#pragma unroll
+            for (int k = 0; k < UG_BK / 16; ++k)
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_nosw(c0 + (uint32_t)((kh * 4 + k) * 256), 128, 2048), bdesc + (uint64_t)(k * 2),
+                             idesc, (kh | k) != 0);
+            ptx::umma_commit(&bempty[sw[kh]]);
+          }
+          for (int j = 0; j < 2; ++j) {                  // residual: Y[:, 64j + 16k ..+16) += X_box(2nb + j)[:, 16k ..+16) . I_16^T
+            const uint64_t xdesc = ptx::umma_desc_sw128(ptx::smem_u32(Ring + sx[j] * CU_BOX));
+#pragma unroll
+            for (int k = 0; k < UG_BK / 16; ++k)
+              ptx::umma_bf16(d_tmem + (uint32_t)(64 * j + 16 * k), xdesc + (uint64_t)(k * 2), idn, idesc_r, true);
+          }
+          ptx::umma_commit(&yfull[yb]);
+        }
+      };
+      if (n_my > 0) do_main(0);
+      for (int t = 0; t < n_my; ++t) {
+        if (t + 1 < n_my) do_main(t + 1);
+        do_tail(t);
+      }
+    }
+  } else if (V == 4 && warp == 2 + CU_ROW_WARPS) {
+    if (lane == 0) {                                    // ===================== store warp (V4) =====================
+      uint32_t yi = 0;
+      for (int t = 0; t < n_my; ++t) {
+        const int m0 = (tile_begin + t) * UG_BM, base = base_tail(t);
+        for (int nb = 0; nb < NB; ++nb, ++yi) {
+          const uint32_t yb = yi & 1;
+          ptx::mbar_wait(&sready[yb], (yi >> 1) & 1);
+          const int sx0 = (base + 4 * nb + 2) % RB, sx1 = (base + 4 * nb + 3) % RB;
+          const unsigned char* b0 = Ring + sx0 * CU_BOX;
+          const unsigned char* b1 = Ring + sx1 * CU_BOX;
+          if (store_cu) {
+            ptx::tma_store_2d(&tmOut, b0, nb * 128, m0);
+            ptx::tma_store_2d(&tmOut, b1, nb * 128 + 64, m0);
+            ptx::bulk_commit();
+          }
+          // mean over the cell's 4 clips of the finished block on the tensor cores (see V3)
+          ptx::mbar_wait(side_empty, (yi & 1) ^ 1);
+          ptx::tc_fence_after();
+          constexpr uint32_t idesc_m = ptx::umma_idesc_bf16_bmn(UG_BM, 64);
+          const uint32_t m4 = ptx::smem_u32(M4);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t bb = ptx::smem_u32(j ? b1 : b0);
+#pragma unroll
+            for (int ks = 0; ks < UG_BM / 16; ++ks)
+              ptx::umma_bf16(tmem_base + CU_TMEM_SIDE + (uint32_t)(64 * j),
+                             ptx::umma_desc_nosw(m4 + (uint32_t)((124 - 4 * ks) * 16), CU_M4_ROWS * 16, 128),
+                             ptx::umma_desc_sw128_mn(bb + (uint32_t)(ks * 2048)), idesc_m, ks != 0);
+          }
+          ptx::umma_commit(side_full);
+          if (store_cu) ptx::bulk_wait_read<0>();
+          ptx::mbar_wait(side_full, yi & 1);             // the MMAs have read the boxes too
+          ptx::mbar_arrive(&bempty[sx0]);
+          ptx::mbar_arrive(&bempty[sx1]);
+        }
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {                                    // ===================== TMA producer =====================
       int wst = 0; uint32_t wph = 0;
       uint32_t it = 0;
@@ -324,7 +477,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
       }
     }
-  } else if (V == 3 && warp == CU_DRAIN_WARP) {
+  } else if (V >= 3 && warp == CU_DRAIN_WARP) {
     // ===================== mean_c drain warp (V3): TMEM lanes 0..31 = the tile's 32 cells, 128 columns per block =====================
     uint32_t c = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -374,7 +527,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int n = at >> 4, k = at & 15;
       *reinterpret_cast<uint16_t*>(I16 + (n & 7) * 16 + (n >> 3) * 256 + (k >> 3) * 128 + (k & 7) * 2) = n == k ? (uint16_t)0x3F80 : (uint16_t)0;
     }
-    if (V == 3) {
+    if (V >= 3) {
       for (int e = at; e < CU_M4_BYTES / 4; e += CU_ROW_THREADS) reinterpret_cast<uint32_t*>(M4)[e] = 0u;
       CU_ROW_BAR();
       if (at < 16) {                                         // P[m', k] = 0.25 for k / 4 == m' (m' = 0..3), row index m' + 124
@@ -437,7 +590,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (g == 0) {
           // ---- c_hat row out of TMEM: + bias, round to bf16 (what the unfused path stores), park in Cs ----
           ptx::mbar_wait(chat_full, ph);
-          if (V >= 2) ptx::mbar_wait(cs_free, ph ^ 1);        // the previous tile's last column block has left Cs
+          if (V == 2 || V == 3) ptx::mbar_wait(cs_free, ph ^ 1);        // the previous tile's last column block has left Cs
           CU_T(2);
           ptx::tc_fence_after();
           const uint32_t t_addr = tmem_base + lane_base;
@@ -456,6 +609,10 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               }
               *reinterpret_cast<uint4*>(Cs + row_off + ((c + e) >> 3) * 128) = cu_pack8(t);
             }
+          }
+          if (V == 4) {                                        // accumulator read: the next tile's first contraction may overwrite it
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(chat_free);
           }
         }
         ptx::fence_proxy_async();
@@ -637,7 +794,8 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int i = 0; i < NP; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
       for (int nb = 0; nb < NB; ++nb, ++yi) {
         const uint32_t yb = yi & 1, yph = (yi >> 1) & 1;
-        unsigned char* xb = (V >= 2 && nb == NB - 1) ? Cs + box_of * CU_BOX : Xs + (2 * nb + box_of) * CU_BOX;
+        unsigned char* xb = V == 4 ? Ring + ((base_tail((int)it) + 4 * nb + 2 + box_of) % RB) * CU_BOX
+                            : (V >= 2 && nb == NB - 1) ? Cs + box_of * CU_BOX : Xs + (2 * nb + box_of) * CU_BOX;
         ptx::mbar_wait_relaxed(&yfull[yb], yph);              // TMEM data: ordered by the tcgen05 fence below
         CU_T(9 + 2 * nb);
         ptx::tc_fence_after();
@@ -692,6 +850,10 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         } else {
           // V2: the accumulator already holds cc_hat.W2^T + X (tensor cores); fbar carries the output bias.
+          if (V >= 3 && !valid) {            // rows past the live count feed the mean_c MMA (0 x NaN = NaN): keep them finite
+#pragma unroll
+            for (int e = 0; e < CU_COLS; ++e) acc[e] = 0.f;
+          }
 #pragma unroll
           for (int pc = 0; pc < NP; ++pc) {
             const f8 fv = unpack8(fq[pc]);
@@ -755,7 +917,7 @@ static int launch_content_unit(const CUtensorMap* tm, int grid, const bf16* fbar
   using Cfg = CuCfg<NQP, GS, V>;
   static_assert(Cfg::SMEM <= 232448, "content_unit_kernel exceeds the 227 KB shared-memory limit");
   VML_CUDA(ensure_dyn_smem((const void*)(content_unit_kernel<NQP, GS, V>), (size_t)(Cfg::SMEM)));
-  content_unit_kernel<NQP, GS, V><<<grid, V == 3 ? CU_THREADS_V2 : CU_THREADS, Cfg::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], d.D, fbar, side, ld_side, b1, b2, qproj, ld,
+  content_unit_kernel<NQP, GS, V><<<grid, V >= 3 ? CU_THREADS_V2 : CU_THREADS, Cfg::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], d.D, fbar, side, ld_side, b1, b2, qproj, ld,
                                                                     off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells.code,
                                                                     cells.n_cells, d.Nq, B, store_cu);
   VML_LAUNCHED(1);
@@ -787,15 +949,20 @@ int content_unit(const void* fc, const void* W1, const float* b1, const float* q
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
 #define VML_CU(NQP, GS, V) return launch_content_unit<NQP, GS, V>(tm, grid, (const bf16*)fbar, (bf16*)side, ld_side, b1, b2, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, B, d, store_cu, st)
   if (bias_in_fbar) {            // V2 / V3: output bias folded into fbar by the boundary unit, residual on the tensor cores
-    const bool v2 = getenv("VML_CU_VARIANT") != nullptr && atoi(getenv("VML_CU_VARIANT")) == 2;   // (A/B knob) mean_c read back by the row warps
-    if (v2) {
+    const int variant = getenv("VML_CU_VARIANT") != nullptr ? atoi(getenv("VML_CU_VARIANT")) : 4;   // (A/B knob)
+    if (variant == 2) {            // mean_c read back by the row warps
       if (d.Nq + 1 <= 8) VML_CU(8, 2, 2);
       if (d.Nq + 1 <= 16) VML_CU(16, 2, 2);
       VML_CU(32, 1, 2);
     }
-    if (d.Nq + 1 <= 8) VML_CU(8, 2, 3);
-    if (d.Nq + 1 <= 16) VML_CU(16, 2, 3);
-    VML_CU(32, 1, 3);
+    if (variant == 3) {            // resident tile, residual + mean_c on the tensor cores
+      if (d.Nq + 1 <= 8) VML_CU(8, 2, 3);
+      if (d.Nq + 1 <= 16) VML_CU(16, 2, 3);
+      VML_CU(32, 1, 3);
+    }
+    if (d.Nq + 1 <= 8) VML_CU(8, 2, 4);          // streamed tile (box ring), the default
+    if (d.Nq + 1 <= 16) VML_CU(16, 2, 4);
+    VML_CU(32, 1, 4);
   }
   if (d.Nq + 1 <= 8) VML_CU(8, 2, 1);
   if (d.Nq + 1 <= 16) VML_CU(16, 2, 1);

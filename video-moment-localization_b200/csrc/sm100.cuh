@@ -175,13 +175,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // MN-major, 128-byte-swizzled operand tile: rows = K index (128 B = 64 bf16 MN-elements each), 8-row groups 1024 B apart
 // (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).  A TMA box of [rows x 64 bf16] with 128B swizzle read as the
 // B (or A) operand whose contraction index runs over the box ROWS; one MMA (K = 16) consumes two 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
+// 32-bit element types (TF32) read MN-major need layout type 1 = SWIZZLE_128B_BASE32B instead: 32-byte pieces of a 128-byte row
+// XOR-ed with (row % 4), K groups of FOUR rows (512 B) -- what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes = 16, uint32_t sbo_bytes = 1024,
+                                                       uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;         // stride between 64-element MN atoms (unused for a single atom)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride between 8-row K groups
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 128-byte MN atoms (unused for a single atom)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride between K groups (8 rows; 4 rows for BASE32B)
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  d |= (uint64_t)(layout_type & 7) << 61;        // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Un-swizzled ("interleaved") operand tile made of 8-row x 16-byte core matrices (128 contiguous bytes each):

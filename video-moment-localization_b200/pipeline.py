@@ -25,25 +25,45 @@ from .evaluate import score_topk_recall
 from .smin import SMIN, Workspace, smin_core, smin_ingest
 
 INPUT_KEYS = ("video_features", "video_mask", "query_features", "query_mask", "length_mask", "moment_mask", "sm")
+# compact batches: the masks and the IoU map are generated on the device (vml_make_labels, dataset.py:95-110,139-149) from
+# the annotation scalars -- only the features, the word mask and three scalars per sample cross PCIe
+COMPACT_KEYS = ("video_features", "query_features", "query_mask", "times", "duration", "nfeats")
 
 
-def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torch.dtype] = None) -> Dict[str, torch.Tensor]:
+def _is_compact(batch) -> bool:
+    return "times" in batch and "sm" not in batch
+
+
+def _keys_of(batch):
+    return COMPACT_KEYS if _is_compact(batch) else INPUT_KEYS
+
+
+def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torch.dtype] = None,
+                    compact: bool = False) -> Dict[str, torch.Tensor]:
     """Re-lay one batch (dict with INPUT_KEYS) as views into ONE pinned host blob (key ``"_blob"``), so that
     ``ScoringPipeline.submit(..., from_host=True)`` moves it with a single H2D copy.  (A collate function
     can write straight into such a blob; the layout is the INPUT_KEYS order, each tensor 256-byte aligned.)
     ``feature_dtype=torch.bfloat16`` stores the clip features and word vectors as bf16 (half the bytes over PCIe;
-    in bf16 precision the scores are bit-identical, the rounding just happens before the copy instead of after)."""
+    in bf16 precision the scores are bit-identical, the rounding just happens before the copy instead of after).
+    ``compact=True`` keeps only COMPACT_KEYS (``times`` [B,2] / ``duration`` [B] as float64, ``nfeats`` [B] int64, as
+    ``synth.make_batch`` and the dataset's annotations provide them): ``ScoringPipeline`` then builds the video / length /
+    moment masks and the IoU map ``sm`` on the device, bit-identical to the host-built ones (GPU test)."""
+    keys = COMPACT_KEYS if compact else INPUT_KEYS
+    if compact:
+        batch = {"video_features": batch["video_features"], "query_features": batch["query_features"],
+                 "query_mask": batch["query_mask"], "times": batch["times"].to(torch.float64),
+                 "duration": batch["duration"].to(torch.float64), "nfeats": batch["nfeats"].to(torch.int64)}
     if feature_dtype is not None:
         batch = dict(batch)
         for k in ("video_features", "query_features"):
             batch[k] = batch[k].to(feature_dtype)
     offs, total = {}, 0
-    for k in INPUT_KEYS:
+    for k in keys:
         offs[k] = total
         total += (batch[k].numel() * batch[k].element_size() + 255) // 256 * 256
     blob = torch.empty(total, dtype=torch.uint8).pin_memory()
     out = {"_blob": blob}
-    for k in INPUT_KEYS:
+    for k in keys:
         t = batch[k].contiguous()
         nbytes = t.numel() * t.element_size()
         view = blob[offs[k]: offs[k] + nbytes].view(t.dtype).view(t.shape)
@@ -54,7 +74,7 @@ def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torc
 
 def _blob_views(blob: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     out, total = {}, 0
-    for k in INPUT_KEYS:
+    for k in _keys_of(like):
         t = like[k]
         nbytes = t.numel() * t.element_size()
         out[k] = blob[total: total + nbytes].view(t.dtype).view(t.shape)
@@ -98,6 +118,8 @@ class _Staging:
         self.free = torch.cuda.Event()         # re-recorded by every consumer
         self.used = False
         self.src_ptrs = None                   # device pointers of the 7 views, in vml_ingest argument order
+        self.labels: Optional[Dict[str, torch.Tensor]] = None     # compact batches: device-built masks + sm of this area
+        self.label_args = None
 
 
 # canonical dtypes of a collated batch (dataset.py:165-176); anything else takes the generic (converting) path
@@ -123,6 +145,8 @@ def _canonical(batch: Dict[str, torch.Tensor]):
     """None if the batch needs the generic (converting) path, else the ingest entry point its dtypes select."""
     f16 = batch["video_features"].dtype is torch.bfloat16
     for k, dt in _CANON.items():
+        if k not in batch:                      # compact batch: the masks / sm are built on the device in canonical form
+            continue
         t = batch[k]
         want = torch.bfloat16 if (f16 and k in ("video_features", "query_features")) else dt
         if t.dtype is not want or not t.is_contiguous():
@@ -160,6 +184,22 @@ class ScoringPipeline:
         self._inflight = deque()               # (event, pinned host blob) of H2D copies that may still be running
         self._ingest_fn = getattr(L_.load(), "vml_ingest")
         self._h2d_fn = getattr(L_.load(), "vml_copy_h2d_async")
+        self._labels_fn = getattr(L_.load(), "vml_make_labels")
+
+    def _attach_label_buffers(self, stg: "_Staging", B: int):
+        """Device outputs of ``vml_make_labels`` for a staging area that receives compact batches; afterwards ``stg.buf``
+        offers all INPUT_KEYS, so everything downstream (ingest launch, fast path) is unchanged."""
+        T, Lm, dev = self.dims.T, self.dims.L, self.device
+        lab = {"sm": torch.empty(B, Lm, Lm, device=dev, dtype=torch.float32),
+               "length_mask": torch.empty(B, Lm, device=dev, dtype=torch.uint8).view(torch.bool),
+               "moment_mask": torch.empty(B, Lm, Lm, device=dev, dtype=torch.uint8).view(torch.bool),
+               "video_mask": torch.empty(B, T, 1, device=dev, dtype=torch.uint8)}
+        stg.labels = lab
+        stg.buf.update(lab)
+        p = lambda k: lab[k].data_ptr()
+        # (times, duration, nfeats, B, T, L, sm, ym, ss, ys, se, ye, ya, length_mask, moment_mask, video_mask, stream)
+        stg.label_args = (stg.buf["times"].data_ptr(), stg.buf["duration"].data_ptr(), stg.buf["nfeats"].data_ptr(), B, T, Lm,
+                          p("sm"), None, None, None, None, None, None, p("length_mask"), p("moment_mask"), p("video_mask"))
 
     # -- one pass on a slot ------------------------------------------------------------------------------
     def _core_and_eval(self, slot: _Slot, pk, inp, group):
@@ -204,6 +244,11 @@ class ScoringPipeline:
         ``ticket.synchronize()``, ``ticket.slot.outputs`` holds the pass's (pm, ps, pe, pa) and top-k
         records (rows ``ticket.index * B ...`` belong to this batch) until the slot is reused."""
         B = batch["video_features"].shape[0]
+        if _is_compact(batch) and not from_host:      # device-resident compact batch: build the masks + sm, then as usual
+            from .labels import make_labels
+            lab = make_labels(batch["times"], batch["duration"], batch["nfeats"], self.dims.T, self.dims.L)
+            batch = {**{k: batch[k] for k in ("video_features", "query_features", "query_mask")},
+                     **{k: lab[k] for k in ("video_mask", "length_mask", "moment_mask", "sm")}}
         if self._batch is None:
             self._batch = B
         if B != self._batch:
@@ -230,7 +275,9 @@ class ScoringPipeline:
                     stg.blob = torch.empty(blob.numel(), dtype=torch.uint8, device=self.device)
                     stg.buf = _blob_views(stg.blob, batch)
                 else:
-                    stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in INPUT_KEYS}
+                    stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in _keys_of(batch)}
+                if _is_compact(batch):
+                    self._attach_label_buffers(stg, B)
                 stg.src_ptrs = tuple(stg.buf[k].data_ptr() for k in _INGEST_ORDER)
             if stg.used:
                 self.copy_stream.wait_event(stg.free)         # the previous consumer's ingest has read it
@@ -246,11 +293,13 @@ class ScoringPipeline:
                     self._inflight.popleft()
             else:
                 with torch.cuda.stream(self.copy_stream):
-                    for k in INPUT_KEYS:
+                    for k in _keys_of(batch):
                         stg.buf[k].copy_(batch[k], non_blocking=True)
             if blob is None or stg.blob is None:
                 stg.ready.record(self.copy_stream)
             slot.stream.wait_event(stg.ready)
+            if stg.label_args is not None:                    # compact batch: masks + sm built on the device, on the slot's stream
+                L_.check(self._labels_fn(*stg.label_args, slot.stream.cuda_stream), "vml_make_labels")
             src = stg.buf
         else:
             src = batch
@@ -303,7 +352,10 @@ class ScoringPipeline:
             ev.record(s.stream)
             caller.wait_event(ev)
         with torch.no_grad():
-            dev = {k: (batch[k].to(self.device, non_blocking=True) if not batch[k].is_cuda else batch[k]) for k in INPUT_KEYS}
+            dev = {k: (batch[k].to(self.device, non_blocking=True) if not batch[k].is_cuda else batch[k]) for k in _keys_of(batch)}
+            if _is_compact(batch):
+                from .labels import make_labels
+                dev.update(make_labels(dev["times"], dev["duration"], dev["nfeats"], self.dims.T, self.dims.L))
             from .synth import MODEL_INPUT_KEYS
             out = self.model(*[dev[k] for k in MODEL_INPUT_KEYS], split_content=self.split_content)
             step = torch.zeros(1, 2, 4, device=self.device, dtype=torch.int64)
