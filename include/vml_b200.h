@@ -41,6 +41,10 @@ extern "C" {
 
 #define VML_FP32 0
 #define VML_BF16 1
+/* fp32 tensors, dense products on the tensor cores as TF32 (10-bit mantissa inputs, fp32 accumulation): accepted by the
+ * GEMM-backed entry points (vml_linear, vml_clip_projection, vml_content_out, vml_moment_out) for the TRAINING forward;
+ * everything else treats it as VML_FP32. */
+#define VML_TF32 2
 
 #define VML_OK 0
 #define VML_ERR_ARG (-1)

@@ -1,5 +1,7 @@
 """Training path: the hand-written backward (csrc/backward.cu + vml_gemm_strided) against autograd of the
 CPU oracle, parameter by parameter, and one Adam step against torch.optim.Adam."""
+import os
+
 import pytest
 import torch
 
@@ -54,7 +56,9 @@ def test_backward_matches_oracle_autograd(name, B, seed):
     out = model(*[d[k] for k in synth.MODEL_INPUT_KEYS])
     loss = loss_fn(out[0], d["ym"], d["sm"], d["moment_mask"], out[1], d["ys"], d["ss"], out[2], d["ye"], d["se"], out[3], d["ya"],
                    d["length_mask"])
-    assert abs(loss.item() - ref_loss) < 1e-5 * abs(ref_loss)
+    # the training path runs its dense products as TF32 on the tensor cores (forward and backward): loss within 2e-4
+    # (1e-5 with VML_TRAIN_FP32=1, the CUDA-core validation arithmetic), gradients within 2e-3 of their scale
+    assert abs(loss.item() - ref_loss) < (1e-5 if os.environ.get("VML_TRAIN_FP32") else 2e-4) * abs(ref_loss)
     loss.backward()
     bad = []
     for n, p in model.named_parameters():

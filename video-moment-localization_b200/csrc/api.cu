@@ -79,7 +79,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
 // generic 2D map with 128B swizzle: dtype 0 = bf16, 1 = fp32 rounded to TF32 by the copy engine (plain fp32 if the driver
 // refuses that type); inner = contiguous dimension
 int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
-                 uint32_t box_inner, uint32_t box_outer, int swizzle = 3) {
+                 uint32_t box_inner, uint32_t box_outer, int swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VML_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -162,6 +162,10 @@ template <typename Epi>
 static int gemm_dispatch(const void* A, const void* W, int M, int N, int K, int lda, const int32_t* m_dev, int m_scale,
                          const Epi& epi, int prec, cudaStream_t st) {
   if (prec == VML_BF16) return launch_gemm_umma(A, W, M, N, K, lda, K, m_dev, m_scale, epi, st);
+  // VML_TF32 (training forward): fp32 tensors as they are, tcgen05 kind::tf32; small or oddly strided products stay on CUDA cores
+  if (prec == VML_TF32 && lda % 4 == 0 && K % 4 == 0 && N % 32 == 0 && (double)M * N * K >= 5.0e7 &&
+      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0)
+    return launch_gemm_umma_tf32(A, W, M, N, K, lda, K, m_dev, m_scale, epi, st);
   VML_CHECK_ARG(lda == K);
   return launch_gemm_simt((const float*)A, (const float*)W, M, N, K, m_dev, m_scale, epi, st);
 }
@@ -170,7 +174,7 @@ static int gemm_dispatch(const void* A, const void* W, int M, int N, int K, int 
 
 using namespace vml;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
-#define VML_PREC_OK(p) VML_CHECK_ARG((p) == VML_FP32 || (p) == VML_BF16)
+#define VML_PREC_OK(p) VML_CHECK_ARG((p) == VML_FP32 || (p) == VML_BF16 || (p) == VML_TF32)
 
 extern "C" {
 
@@ -254,7 +258,7 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
     return launch_gemm_umma(v, W, M, d.D, k_pad, k_pad, k_pad, nullptr, 1, e, ST(stream));
   }
   EpiClip<float> e{bias, pe, video_mask, d.T, (float*)fv, d.D};
-  return launch_gemm_simt((const float*)v, (const float*)W, M, d.D, d.d0, nullptr, 1, e, ST(stream));
+  return gemm_dispatch(v, W, M, d.D, d.d0, d.d0, nullptr, 1, e, prec, ST(stream));
 }
 
 VML_API int vml_lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y_bf16, float* fs,

@@ -11,6 +11,8 @@
 // validation mode, so both modes share this code.  One CTA (8 warps) per (sample, 16 map rows):
 // contractions over D are split across the warps along K and reduced through shared memory,
 // contractions producing D columns are split across the warps along N.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vml {
@@ -348,16 +350,41 @@ boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
   const int dq = D / 4;
-  for (int e = tid; e < Nq * dq; e += BMM_THREADS) {
-    const int k = e / dq, c4 = (e - k * dq) * 4;
-    *reinterpret_cast<float4*>(Ks + (size_t)k * DS + c4) = __ldg(reinterpret_cast<const float4*>(qproj + ((size_t)b * Nq + k) * ld + off_kbt + c4));
-    *reinterpret_cast<float4*>(Ws + (size_t)k * DS + c4) = __ldg(reinterpret_cast<const float4*>(fw + ((size_t)b * Nq + k) * D + c4));
-  }
-  for (int e = tid; e < BMM_ROWS * dq; e += BMM_THREADS) {
-    const int rr = e / dq, c4 = (e - rr * dq) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rr < L) v = __ldg(reinterpret_cast<const float4*>(fb + ((size_t)b * L + rr) * D + c4));
-    *reinterpret_cast<float4*>(Xs + (size_t)rr * DS + c4) = v;
+  // staging: 12 independent 16-byte loads in flight per thread before the first shared-memory store (the unit is
+  // latency-bound: one load per iteration meant ~20 dependent trips to L2 / HBM per CTA)
+  {
+    constexpr int UB = 4;
+    const int nkw = Nq * dq, nx = BMM_ROWS * dq;
+    for (int e0 = tid; e0 < max(nkw, nx); e0 += UB * BMM_THREADS) {
+      float4 kv[UB], wv[UB], xv[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int e = e0 + u * BMM_THREADS;
+        kv[u] = wv[u] = xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < nkw) {
+          const int k = e / dq, c4 = (e - k * dq) * 4;
+          kv[u] = __ldg(reinterpret_cast<const float4*>(qproj + ((size_t)b * Nq + k) * ld + off_kbt + c4));
+          wv[u] = __ldg(reinterpret_cast<const float4*>(fw + ((size_t)b * Nq + k) * D + c4));
+        }
+        if (e < nx) {
+          const int rr = e / dq, c4 = (e - rr * dq) * 4;
+          if (rr < L) xv[u] = __ldg(reinterpret_cast<const float4*>(fb + ((size_t)b * L + rr) * D + c4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int e = e0 + u * BMM_THREADS;
+        if (e < nkw) {
+          const int k = e / dq, c4 = (e - k * dq) * 4;
+          *reinterpret_cast<float4*>(Ks + (size_t)k * DS + c4) = kv[u];
+          *reinterpret_cast<float4*>(Ws + (size_t)k * DS + c4) = wv[u];
+        }
+        if (e < nx) {
+          const int rr = e / dq, c4 = (e - rr * dq) * 4;
+          *reinterpret_cast<float4*>(Xs + (size_t)rr * DS + c4) = xv[u];
+        }
+      }
+    }
   }
   __syncthreads();
   const int rA = g, rB = g + 8;
@@ -577,14 +604,22 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
   const int n_lo = row_start[grow], n_hi = min(row_start[grow + 1], capacity);
   if (n_lo >= n_hi) return;                            // empty row: bu stays f_bb + f_b (A_b row is all zero there)
   const float* arow = ab + (size_t)grow * L;
+  // blockIdx.y: 256-column group (fast mode launches NG = 1 with D / 256 groups in grid.y: half the registers per thread,
+  // 5 resident CTAs per SM instead of 3 -- the kernel is latency-bound, resident warps are what it needs)
+  const int col_shift = (int)blockIdx.y * 256;
+  fs += col_shift; fm += col_shift; bu += col_shift;
+  if (fbar) fbar += col_shift;
+  if (fbar_bias) fbar_bias += col_shift;
+  const int ldD = D;                                   // row stride of fs / fm / fbar / bu
+  const int Dc = min(D - col_shift, NG * 256);         // columns this CTA covers
   // fbar_bias (optional): added to the STORED fbar only (before its rounding) -- the consumer's output bias travels with it
   f8 s8[NG], bm[NG], fb8[NG];
 #pragma unroll
   for (int q = 0; q < NG; ++q) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s8[q].v[e] = 0.f; bm[q].v[e] = 0.f; fb8[q].v[e] = 0.f; }
-    if (q * 256 + lane * 8 < D) {
-      s8[q] = ld8(fs + (size_t)b * D + q * 256 + lane * 8);
+    if (q * 256 + lane * 8 < Dc) {
+      s8[q] = ld8(fs + (size_t)b * ldD + q * 256 + lane * 8);
       if (fbar_bias) fb8[q] = ld8(fbar_bias + q * 256 + lane * 8);
     }
   }
@@ -601,7 +636,7 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
         for (int q = 0; q < NG; ++q) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) m[u][q].v[e] = 0.f;
-          if (q * 256 + lane * 8 < D) m[u][q] = ld8(fm + (size_t)n * D + q * 256 + lane * 8);
+          if (q * 256 + lane * 8 < Dc) m[u][q] = ld8(fm + (size_t)n * ldD + q * 256 + lane * 8);
         }
       }
 #pragma unroll
@@ -610,7 +645,7 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
         if (c0 + u < seg_n) {                          // warp-uniform
 #pragma unroll
           for (int q = 0; q < NG; ++q)
-            if (q * 256 + lane * 8 < D) {
+            if (q * 256 + lane * 8 < Dc) {
               f8 gv;
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -621,7 +656,7 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
               if (fbar) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) gv.v[e] += fb8[q].v[e];
-                st8(fbar + (size_t)(seg + c0 + u) * D + q * 256 + lane * 8, gv);
+                st8(fbar + (size_t)(seg + c0 + u) * ldD + q * 256 + lane * 8, gv);
               }
             }
         }
@@ -630,8 +665,8 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
   }
 #pragma unroll
   for (int q = 0; q < NG; ++q)
-    if (q * 256 + lane * 8 < D) {
-      float* o = bu + (size_t)grow * D + q * 256 + lane * 8;
+    if (q * 256 + lane * 8 < Dc) {
+      float* o = bu + (size_t)grow * ldD + q * 256 + lane * 8;
       f8 tot = ld8(o);
 #pragma unroll
       for (int e = 0; e < 8; ++e) tot.v[e] = tot.v[e] + bm[q].v[e];
@@ -657,7 +692,9 @@ static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, fl
 template <typename ActT, int NG, bool PRECISE>
 static int launch_stream(const float* ab, const float* fs, const void* fm, vml_cells_t cells, float* bu, void* fbar,
                          const float* fbar_bias, int B, vml_dims_t d, cudaStream_t st) {
-  boundary_stream_kernel<ActT, NG, PRECISE><<<ceil_div(B * d.L, 4), 128, 0, st>>>(
+  // NG column groups per warp; when NG * 256 < D the remaining groups run as separate CTAs (grid.y)
+  dim3 grid(ceil_div(B * d.L, 4), ceil_div(d.D, NG * 256));
+  boundary_stream_kernel<ActT, NG, PRECISE><<<grid, 128, 0, st>>>(
       ab, fs, (const ActT*)fm, cells.code, cells.row_start, bu, (ActT*)fbar, fbar_bias, B * d.L, d.L, d.D, cells.capacity);
   return VML_OK;
 }
@@ -701,8 +738,9 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   const int ng = ceil_div(d.D, 256);
   if (prec == VML_FP32) rc = ng <= 1 ? launch_stream<float, 1, true>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st)
                                      : launch_stream<float, 2, true>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st);
-  else rc = ng <= 1 ? launch_stream<bf16, 1, false>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st)
-                    : launch_stream<bf16, 2, false>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st);
+  else rc = (ng <= 1 || getenv("VML_STREAM_NG2") == nullptr)        // fast mode: one 256-column group per warp (A/B knob: both in one)
+                ? launch_stream<bf16, 1, false>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st)
+                : launch_stream<bf16, 2, false>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st);
   if (rc) return rc;
   VML_LAUNCHED(n_launched);
   return VML_OK;

@@ -45,20 +45,6 @@ struct TfArgs {
   int mn_lbo, mn_sbo, mn_kstep, mn_ltype;      // MN-major descriptor parameters: 4096 / 512 / 1024 bytes, layout type 1 (debug knobs VML_TF_*)
 };
 
-namespace ptx {
-// kind::tf32 instruction descriptor: tf32 x tf32 -> fp32; bit 15 / 16: A / B operand MN-major
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-}  // namespace ptx
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TF_THREADS, 1)
@@ -205,7 +191,7 @@ __global__ void zero_tail_rows_kernel(float* __restrict__ p, int64_t ld, int col
 }
 
 int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
-                 uint32_t box_inner, uint32_t box_outer, int swizzle = 3);
+                 uint32_t box_inner, uint32_t box_outer, int swizzle);
 
 // Returns VML_OK when the product ran on the tensor cores, 1 when the shape is not eligible (caller falls back to the
 // CUDA-core kernel), < 0 on error.
@@ -228,10 +214,10 @@ int launch_gemm_tf32(const float* A, int64_t sam, int64_t sak, const float* B, i
   // K-major: dims {K, rows}, box {32, 128}, 128B swizzle;   MN-major: dims {rows, K}, box {32, 32}, 128B swizzle with 32-byte atoms
   auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
   const int swz_mn = knob("VML_TF_SWZ", 4);                // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-  if (a_k) rc = make_tmap_2d(&tmA, 1, A, (uint64_t)K, (uint64_t)M, (uint64_t)sam * 4, TF_BK, TF_BM);
+  if (a_k) rc = make_tmap_2d(&tmA, 1, A, (uint64_t)K, (uint64_t)M, (uint64_t)sam * 4, TF_BK, TF_BM, 3);
   else rc = make_tmap_2d(&tmA, 1, A, (uint64_t)M, (uint64_t)K, (uint64_t)sak * 4, 32, TF_BK, swz_mn);
   if (rc) return rc;
-  if (b_k) rc = make_tmap_2d(&tmB, 1, B, (uint64_t)K, (uint64_t)N, (uint64_t)sbn * 4, TF_BK, TF_BN);
+  if (b_k) rc = make_tmap_2d(&tmB, 1, B, (uint64_t)K, (uint64_t)N, (uint64_t)sbn * 4, TF_BK, TF_BN, 3);
   else rc = make_tmap_2d(&tmB, 1, B, (uint64_t)N, (uint64_t)K, (uint64_t)sbk * 4, 32, TF_BK, swz_mn);
   if (rc) return rc;
   const int tiles = ceil_div(M, TF_BM) * ceil_div(N, TF_BN);

@@ -57,7 +57,10 @@ struct UmmaCfg {
 // EW epilogue warps (8 or 16): EW / 4 of them share a TMEM lane quadrant and split the tile's columns.  With 128 x 256
 // tiles 8 warps need ~2x the main loop's time for a residual epilogue (measured: the moment GEMM ran at 53 % of the
 // tensor pipe whatever fed its operands), hence 16 for BN = 256.
-template <int BN, typename Epi, int CL = 1, int EW = UG_EPI_WARPS>
+// TF32 = true: the operands are fp32 tensors read as TF32 (kind::tf32; the training forward): a 128-byte box row then holds
+// 32 elements instead of 64, an MMA covers K = 8 instead of 16 -- the same 32 bytes per step, so only the K arithmetic, the
+// instruction descriptor and the instruction kind differ.
+template <int BN, typename Epi, int CL = 1, int EW = UG_EPI_WARPS, bool TF32 = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
@@ -75,8 +78,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (m_dev) M = min(M, *m_dev * m_scale);
+  constexpr int BK = TF32 ? UG_BK / 2 : UG_BK;             // elements per 128-byte box row
   const int tiles_m = (M + UG_BM - 1) / UG_BM, tiles_n = N / BN;
-  const int k_blocks = (K + UG_BK - 1) / UG_BK;
+  const int k_blocks = (K + BK - 1) / BK;
   // CL == 2: a cluster walks PAIRS of vertically adjacent tiles (same n); rank r takes m-tile 2*pair_m + r (a tile past
   // the end still takes part in the B multicast and the barriers: its A rows are out of bounds = zero-filled)
   const int crank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
@@ -108,12 +112,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);      // CL == 2: both CTAs' MMAs have retired from this stage
           unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * UG_BK, m0);
+          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
           if (CL == 2)                                       // my half of the B tile, to both CTAs of the cluster
-            ptx::tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * UG_BK,
+            ptx::tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
                                 n0 + crank * (BN / 2), (uint16_t)3);
           else
-            ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * UG_BK, n0);
+            ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -121,7 +125,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(UG_BM, BN);
+      constexpr uint32_t idesc = TF32 ? ptx::umma_idesc_tf32(UG_BM, BN, false, false) : ptx::umma_idesc_bf16(UG_BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -135,8 +139,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
           const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < UG_BK / 16; ++k)  // +32 B per K=16 step inside the 128B swizzle atom
-            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < UG_BK / 16; ++k) {  // +32 B per K step (16 bf16 / 8 tf32) inside the 128B swizzle atom
+            if (TF32) ptx::umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           if (CL == 2) ptx::umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in BOTH CTAs: the stage is refilled by multicast
           else ptx::umma_commit(&empty_bar[stage]);        // frees the smem stage when the MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -421,6 +427,42 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
   gemm_umma_kernel<BN, Epi><<<grid, UG_GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
   VML_LAUNCHED(1);
   return VML_OK;
+}
+
+int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle);
+
+// fp32 operands as TF32 (training forward): A float [M, lda], W float [N, ldw], both K-major; any float epilogue.
+template <int BN, typename Epi>
+int launch_gemm_umma_tf32_bn(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int32_t* m_dev,
+                             int m_scale, const Epi& epi, cudaStream_t stream) {
+  using Cfg = UmmaCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, 1, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 4, UG_BK / 2, UG_BM, 3);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, 1, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 4, UG_BK / 2, BN, 3);
+  if (rc) return rc;
+  constexpr int EW = BN == 256 ? 16 : UG_EPI_WARPS;
+  VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi, 1, EW, true>), (size_t)(Cfg::SMEM_BYTES)));
+  const int64_t tiles = (int64_t)ceil_div(M, UG_BM) * (N / BN);
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  gemm_umma_kernel<BN, Epi, 1, EW, true><<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+  VML_LAUNCHED(1);
+  return VML_OK;
+}
+template <typename Epi>
+int launch_gemm_umma_tf32(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int32_t* m_dev,
+                          int m_scale, const Epi& epi, cudaStream_t stream) {
+  VML_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && N % 32 == 0);
+  VML_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (M <= 0) return VML_OK;
+  static bool reg = (register_kernel("gemm_umma_kernel<tf32>"), true);
+  (void)reg;
+  if (N % 256 == 0 && (int64_t)ceil_div(M, UG_BM) * (N / 256) >= 2 * kNumSMs)
+    return launch_gemm_umma_tf32_bn<256, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  if (N % 128 == 0) return launch_gemm_umma_tf32_bn<128, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  if (N % 64 == 0) return launch_gemm_umma_tf32_bn<64, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  return launch_gemm_umma_tf32_bn<32, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
 }
 
 // A: bf16 [M, lda] (K <= lda), W: bf16 [N, ldw].  M is the capacity; live rows = *m_dev * m_scale.

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvml_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vml_b200.h")
 
-FP32, BF16 = 0, 1
+FP32, BF16, TF32 = 0, 1, 2          # TF32: fp32 tensors, dense products as tcgen05 kind::tf32 (training path only)
 PREC = {"fp32": FP32, "bf16": BF16}
 
 

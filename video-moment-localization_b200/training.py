@@ -11,6 +11,7 @@ through the algebraic folding of the query-side weights (``smin.fold_query_weigh
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List
 
 import torch
@@ -41,6 +42,9 @@ class Tape:
 def train_forward(pk: Dict[str, torch.Tensor], dims: Dims, inp: dict) -> tuple:
     """fp32 forward that keeps its intermediates.  ``inp`` comes from ``smin_ingest(..., prec=FP32)``."""
     P = L_.FP32
+    # the dense products of the forward run on the tensor cores as TF32 (fp32 tensors as they are, fp32 accumulation) like the
+    # backward's (gemm_tf32.cu); VML_TRAIN_FP32=1 keeps every product on CUDA-core FFMA (bit-for-bit the validation path)
+    PG = L_.FP32 if os.environ.get("VML_TRAIN_FP32") else L_.TF32
     B = inp["B"]
     T, Lm, Cc, D, dl, layers, d0, Nq, H = (dims.T, dims.L, dims.C, dims.D, dims.dl, dims.layers, dims.d0, dims.Nq, dims.H)
     dev = inp["qlen"].device
@@ -51,21 +55,21 @@ def train_forward(pk: Dict[str, torch.Tensor], dims: Dims, inp: dict) -> tuple:
     vmask, qmask, lmask, mmask, qlen = inp["vmask"], inp["qmask"], inp["lmask"], inp["mmask"], inp["qlen"]
     # a1
     tp.fv = E(B * T, D)
-    call("vml_clip_projection", ptr(inp["v"]), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(tp.fv), B, dims, d0, P, st)
+    call("vml_clip_projection", ptr(inp["v"]), ptr(pk["ve_w"]), ptr(pk["ve_b"]), ptr(pk["pe"]), ptr(vmask), ptr(tp.fv), B, dims, d0, PG, st)
     # a2 (saving gate activations)
     gin = E(B * Nq, 8 * H)
-    call("vml_linear", ptr(inp["q"]), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, 300, 8 * H, None, 1, P, 1, st)
+    call("vml_linear", ptr(inp["q"]), ptr(pk["lstm_wih0"]), ptr(pk["lstm_b0"]), ptr(gin), B * Nq, 8 * H, 300, 8 * H, None, 1, PG, 1, st)
     tp.y0, tp.acts0 = E(B, Nq, 2 * H), torch.zeros(B, Nq, 2, 5, H, device=dev, dtype=F32)
     call("vml_lstm_train_fwd", ptr(gin), ptr(pk["lstm_whht0"]), ptr(qlen), ptr(tp.y0), None, ptr(tp.acts0), B, Nq, H, st)
     gin1 = E(B * Nq, 8 * H)
-    call("vml_linear", ptr(tp.y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin1), B * Nq, 8 * H, 2 * H, 8 * H, None, 1, P, 1, st)
+    call("vml_linear", ptr(tp.y0), ptr(pk["lstm_wih1"]), ptr(pk["lstm_b1"]), ptr(gin1), B * Nq, 8 * H, 2 * H, 8 * H, None, 1, PG, 1, st)
     tp.fwfs, tp.acts1 = E(B * Nq + B, 2 * H), torch.zeros(B, Nq, 2, 5, H, device=dev, dtype=F32)
     fw, fs = tp.fwfs[: B * Nq], tp.fwfs[B * Nq:]
     call("vml_lstm_train_fwd", ptr(gin1), ptr(pk["lstm_whht1"]), ptr(qlen), ptr(fw), ptr(fs), ptr(tp.acts1), B, Nq, H, st)
     lay = query_layout(dims)
     ld = lay["ld"]
     tp.qproj = E(B * Nq + B, ld)
-    call("vml_linear", ptr(tp.fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(tp.qproj), B * Nq + B, ld, D, ld, None, 1, P, 1, st)
+    call("vml_linear", ptr(tp.fwfs), ptr(pk["qcat_w"]), ptr(pk["qcat_b"]), ptr(tp.qproj), B * Nq + B, ld, D, ld, None, 1, PG, 1, st)
     s_hat_base = tp.qproj.data_ptr() + (B * Nq * ld + lay["s0"]) * 4
     # cells + a3/a4
     cap = B * (Lm * (Lm + 1) // 2)
@@ -87,14 +91,14 @@ def train_forward(pk: Dict[str, torch.Tensor], dims: Dims, inp: dict) -> tuple:
              ptr(qmask), ptr(lmask), cells, ptr(G), ptr(Ab), ptr(bu), None, None, ptr(Pw), ptr(U), B, dims, P, st)
         c_hat, cc_hat, cu = E(cap * Cc, dl), E(cap * Cc, dl), E(cap, Cc, D)
         call("vml_linear", ptr(tp.fc[k]), ptr(pk[f"chat_w{k}"]), ptr(pk[f"chat_b{k}"]), ptr(c_hat), cap * Cc, dl, D, dl,
-             cells.n_cells, Cc, P, 0, st)
+             cells.n_cells, Cc, PG, 0, st)
         call("vml_content_attention", ptr(c_hat), ptr(tp.qproj), ld, o, o + dl, o + 2 * dl + D, s_hat_base + k * dl * 4, ld,
              ptr(qmask), cells, ptr(cc_hat), B, dims, P, st)
         call("vml_content_out", ptr(cc_hat), ptr(pk[f"cout_w{k}"]), ptr(pk[f"cout_b{k}"]), ptr(tp.fc[k]), ptr(tp.fm[k]), ptr(fs),
-             None, None, cells, ptr(cu), dims, P, st)
+             None, None, cells, ptr(cu), dims, PG, st)
         op, mu = E(cap, 2 * D), E(cap, D)
         call("vml_moment_operand", ptr(cu), ptr(bu), cells, ptr(op), dims, P, st)
-        call("vml_moment_out", ptr(op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(tp.fm[k]), cells, ptr(mu), dims, P, st)
+        call("vml_moment_out", ptr(op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(tp.fm[k]), cells, ptr(mu), dims, PG, st)
         tp.G.append(G); tp.Ab.append(Ab); tp.Pw.append(Pw); tp.U.append(U)
         tp.c_hat.append(c_hat); tp.cc_hat.append(cc_hat); tp.op.append(op)
         tp.fc.append(cu); tp.fm.append(mu); tp.fb.append(bu)
