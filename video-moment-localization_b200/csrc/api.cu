@@ -149,7 +149,8 @@ int moment_operand(const void*, const float*, vml_cells_t, void*, vml_dims_t, in
 int localize(const void*, const float*, const float*, const float*, vml_cells_t, const uint8_t*, float*, float*, float*,
              float*, int, vml_dims_t, int, cudaStream_t);
 int query_lengths(const uint8_t*, int32_t*, int, int, cudaStream_t);
-int lstm_layer(const float*, const float*, const int32_t*, float*, void*, float*, void*, int, int, int, cudaStream_t);
+int lstm_layer(const float*, const float*, const int32_t*, float*, void*, float*, void*, int, int, int, cudaStream_t, float* acts = nullptr);
+int lstm_bwd_cluster(const float*, const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, cudaStream_t);
 int lstm_layer_tc(const float*, const void*, const int32_t*, float*, void*, float*, void*, int, int, int, cudaStream_t);
 int scaled_iou_bce(const float*, const uint8_t*, const float*, const uint8_t*, const float*, const uint8_t*, const float*,
                    const float*, const uint8_t*, const float*, const float*, const uint8_t*, const uint8_t*, int, int,
@@ -461,10 +462,20 @@ VML_API int vml_adam_step(float* p, const float* g, float* m, float* v, int64_t 
 }
 VML_API int vml_lstm_train_fwd(const float* gin, const float* whh_t, const int32_t* qlen, float* y, float* fs, float* acts, int B,
                                int Nq, int H, void* stream) {
+  // the 8-CTA-cluster recurrence of the fp32 inference path (W_hh slices in shared memory, h exchanged through DSMEM), saving
+  // the gate activations on the way; the one-CTA-per-sample kernel only for shapes the cluster kernel does not take
+  const size_t UH = (size_t)H / 8;
+  const size_t smem = sizeof(float) * ((size_t)H * 4 * UH + 2 * (size_t)H * 8 + 8 * 8 * 4 * UH + (size_t)Nq * 8 * UH);
+  if (H % 32 == 0 && H <= 1024 && smem <= 227 * 1024 && getenv("VML_LSTM_TRAIN_NAIVE") == nullptr)
+    return lstm_layer(gin, whh_t, qlen, y, nullptr, fs, nullptr, B, Nq, H, ST(stream), acts);
   return lstm_train_fwd(gin, whh_t, qlen, y, fs, acts, B, Nq, H, ST(stream));
 }
 VML_API int vml_lstm_train_bwd(const float* dy, const float* dfs, const float* whh, const float* acts, const int32_t* qlen, float* dgin,
                                float* dgin_rec, int B, int Nq, int H, void* stream) {
+  if (getenv("VML_LSTM_TRAIN_NAIVE") == nullptr) {
+    const int rc = lstm_bwd_cluster(dy, dfs, whh, acts, qlen, dgin, dgin_rec, B, Nq, H, ST(stream));   // 1: shape not taken
+    if (rc <= 0) return rc;
+  }
   return lstm_train_bwd(dy, dfs, whh, acts, qlen, dgin, dgin_rec, B, Nq, H, ST(stream));
 }
 

@@ -476,7 +476,9 @@ int launch_gemm_umma(const void* A, const void* W, int M, int N, int K, int lda,
   (void)reg;
   // 128 x 256 tiles halve the shared-memory operand traffic per flop (the 128 x 128 shape sits exactly on the
   // 128 B/clk smem roof); used once there are enough tiles to fill the machine twice over
-  if (N % 256 == 0 && (int64_t)ceil_div(M, UG_BM) * (N / 256) >= 2 * kNumSMs)
+  const char* bn_knob = getenv("VML_GEMM_BN");              // (A/B knob) force the tile width: 128 or 256
+  const int bn_force = bn_knob ? atoi(bn_knob) : 0;
+  if (N % 256 == 0 && bn_force != 128 && ((int64_t)ceil_div(M, UG_BM) * (N / 256) >= 2 * kNumSMs || bn_force == 256))
     return launch_gemm_umma_bn<256, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 128 == 0) return launch_gemm_umma_bn<128, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 64 == 0) return launch_gemm_umma_bn<64, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);

@@ -33,8 +33,8 @@ constexpr int LSTM_CL = 8;   // CTAs per cluster == K-slices == samples per tile
 
 __global__ void __cluster_dims__(LSTM_CL, 1, 1)
 lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh_t, const int32_t* __restrict__ qlen,
-                    float* __restrict__ y, bf16* __restrict__ y16, float* __restrict__ fs, bf16* __restrict__ fs16, int B, int Nq,
-                    int H) {
+                    float* __restrict__ y, bf16* __restrict__ y16, float* __restrict__ fs, bf16* __restrict__ fs16,
+                    float* __restrict__ acts, int B, int Nq, int H) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   constexpr int BT = LSTM_CL;
@@ -141,6 +141,10 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
       h_state = og * tanhf(c_state);
       const int t = dir == 0 ? step : my_len - 1 - step;
       ybuf[((size_t)t * BT + s) * UH + u] = h_state;
+      if (acts) {            // training forward: i, f, g, o (after the non-linearities) and c of this step -> BPTT
+        float* a = acts + (((size_t)bs * Nq + t) * 2 + dir) * 5 * H + unit;
+        a[0] = ig; a[H] = fg; a[2 * H] = gg; a[3 * H] = og; a[4 * H] = c_state;
+      }
     }
 #pragma unroll
     for (int r = 0; r < LSTM_CL; ++r)
@@ -162,6 +166,128 @@ lstm_cluster_kernel(const float* __restrict__ gin, const float* __restrict__ whh
     if (fs16) fs16[(size_t)bs * 2 * H + (size_t)dir * H + unit] = __float2bfloat16_rn(h_state);
   }
   cluster.sync();                           // no CTA may exit while peers can still address its smem
+}
+
+// -------------------------------------------------------------------------------------
+// BPTT of one bi-LSTM layer (training path, behind loss.backward(), main.py:150), same decomposition as the forward:
+// an 8-CTA cluster per (direction, tile of 8 samples), CTA r owns hidden units [32r, 32r + 32) and keeps the 4 x 32 rows
+// of W_hh that produce THEIR gates in shared memory (128 KB).  A step is
+//   (1) thread (unit, sample): gate gradients from the saved activations and dh = dy + dh_rec  -> dgin / dgin_rec rows;
+//   (2) thread k: partial dh_prev[sample][k] = sum over the CTA's 128 gate rows of dg[sample][row] * W_hh[row][k];
+//   (3) reduce-scatter over the cluster: the partial of column k goes to the CTA that owns unit k (st.async into a
+//       per-source slot, counted on the destination's mbarrier); the owner sums its 8 slots -> dh_rec of the next step.
+// Samples past their length contribute zeros, so ragged tiles need no special casing.  (The round-1 kernel ran one CTA
+// per (sample, direction) and re-read all of W_hh from L2 every step: 1.0 ms per layer at B = 64 against ~0.1 ms.)
+// -------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(LSTM_CL, 1, 1)
+lstm_bwd_cluster_kernel(const float* __restrict__ dy, const float* __restrict__ dfs, const float* __restrict__ whh,
+                        const float* __restrict__ acts, const int32_t* __restrict__ qlen, float* __restrict__ dgin,
+                        float* __restrict__ dgin_rec, int B, int Nq, int H) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int BT = LSTM_CL;
+  extern __shared__ __align__(16) float lsm[];
+  const int UH = H / LSTM_CL, R = 4 * UH;          // R gate rows owned by this CTA
+  float* Wsl = lsm;                                // [R][H]   row q * UH + u  <-  W_hh[q * H + rank * UH + u][:]
+  float* dgs = Wsl + (size_t)R * H;                // [BT][R]  gate gradients of the current step
+  float* recv = dgs + BT * R;                      // [2][LSTM_CL src][BT][UH]
+  __shared__ __align__(8) uint64_t rbar[2];
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / LSTM_CL;
+  const int dir = cid & 1, b0 = (cid >> 1) * BT;
+  const int tid = threadIdx.x;                     // blockDim.x == H
+  const int u = tid % UH, s = tid / UH;            // phase (1) / (3) role: (unit, sample)
+  const int unit = rank * UH + u;
+  const float* W = whh + (size_t)dir * 4 * H * H;  // [4H][H]
+  for (int e = tid; e < R * H; e += blockDim.x) {
+    const int row = e / H, k = e - row * H, q = row / UH, uu = row - q * UH;
+    Wsl[e] = W[((size_t)q * H + rank * UH + uu) * H + k];
+  }
+  for (int e = tid; e < 2 * LSTM_CL * BT * UH; e += blockDim.x) recv[e] = 0.f;
+  const int bs = b0 + s;
+  const int my_len = bs < B ? min(qlen[bs], Nq) : 0;
+  int maxlen = 0;
+  for (int t = 0; t < BT; ++t) maxlen = max(maxlen, (b0 + t < B) ? min(qlen[b0 + t], Nq) : 0);
+  if (bs < B)
+    for (int t = my_len; t < Nq; ++t) {            // rows past the length: zero gradient of the input projections
+      float* o = dgin + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
+      float* o2 = dgin_rec + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { o[q * H] = 0.f; o2[q * H] = 0.f; }
+    }
+  // phase (2) role: output column k = tid, owned by CTA k / UH; my slot there is indexed by MY rank
+  const int k_owner = tid / UH, k_local = tid % UH;
+  uint32_t remote_slot = ptx::mapa(ptx::smem_u32(recv + ((size_t)rank * BT) * UH + k_local), k_owner);
+  uint32_t remote_bar = ptx::mapa(ptx::smem_u32(&rbar[0]), k_owner);
+  if (tid == 0) { ptx::mbar_init(&rbar[0], 1); ptx::mbar_init(&rbar[1], 1); ptx::fence_barrier_init(); }
+  const uint32_t step_bytes = (uint32_t)(LSTM_CL * BT * UH * sizeof(float));
+  float dh_rec = 0.f, dc_next = 0.f;
+  cluster.sync();
+
+  for (int step = maxlen - 1; step >= 0; --step) {
+    const int it = maxlen - 1 - step, cur = it & 1;
+    if (tid == 0) ptx::mbar_arrive_expect_tx(&rbar[cur], step_bytes);
+    // ---- (1) gate gradients of (unit, sample s) --------------------------------------------------------
+    float dg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (step < my_len) {
+      const int t = dir == 0 ? step : my_len - 1 - step;
+      const float* a = acts + (((size_t)bs * Nq + t) * 2 + dir) * 5 * H + unit;
+      const float ig = a[0], fg = a[H], gg = a[2 * H], og = a[3 * H], c = a[4 * H];
+      float c_prev = 0.f;
+      if (step > 0) {
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        c_prev = acts[(((size_t)bs * Nq + tp) * 2 + dir) * 5 * H + 4 * H + unit];
+      }
+      float dh = dy[((size_t)bs * Nq + t) * 2 * H + (size_t)dir * H + unit] + dh_rec;
+      if (dfs && step == my_len - 1) dh += dfs[(size_t)bs * 2 * H + (size_t)dir * H + unit];   // fs = h of the last processed step
+      const float tc = tanhf(c);
+      dg[3] = dh * tc * og * (1.f - og);
+      const float dc = dc_next + dh * og * (1.f - tc * tc);
+      dg[0] = dc * gg * ig * (1.f - ig);
+      dg[2] = dc * ig * (1.f - gg * gg);
+      dg[1] = dc * c_prev * fg * (1.f - fg);
+      dc_next = dc * fg;
+      float* o = dgin + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
+      float* o2 = dgin_rec + ((size_t)bs * Nq + t) * 8 * H + (size_t)dir * 4 * H + unit;
+      const float z = step == 0 ? 0.f : 1.f;         // the first processed step has no recurrent input
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { o[q * H] = dg[q]; o2[q * H] = dg[q] * z; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dgs[(size_t)s * R + q * UH + u] = dg[q];
+    __syncthreads();
+    // ---- (2) partial dh_prev[a][k] over this CTA's gate rows, (3) scatter to the owner of column k ------------
+    if (step > 0) {
+      float acc[BT];
+#pragma unroll
+      for (int a = 0; a < BT; ++a) acc[a] = 0.f;
+      for (int r0 = 0; r0 < R; r0 += 4) {
+        float4 d4[BT];
+#pragma unroll
+        for (int a = 0; a < BT; ++a) d4[a] = *reinterpret_cast<const float4*>(dgs + (size_t)a * R + r0);   // warp-uniform: broadcast
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float w = Wsl[(size_t)(r0 + j) * H + tid];
+#pragma unroll
+          for (int a = 0; a < BT; ++a) {
+            const float dv = j == 0 ? d4[a].x : j == 1 ? d4[a].y : j == 2 ? d4[a].z : d4[a].w;
+            acc[a] = fmaf(dv, w, acc[a]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < BT; ++a)
+        ptx::st_async_f32(remote_slot + (uint32_t)((cur * LSTM_CL * BT * UH + a * UH) * sizeof(float)), acc[a],
+                          remote_bar + (uint32_t)(cur * 8));
+      ptx::mbar_wait(&rbar[cur], (uint32_t)((it >> 1) & 1));      // the 8 partials of MY units have landed
+      float v = 0.f;
+#pragma unroll
+      for (int p = 0; p < LSTM_CL; ++p) v += recv[((size_t)(cur * LSTM_CL + p) * BT + s) * UH + u];
+      dh_rec = v;
+    }
+    __syncthreads();                                 // dgs is rewritten by the next step
+  }
+  cluster.sync();                                    // no CTA may exit while peers can still address its smem
 }
 
 // -------------------------------------------------------------------------------------
@@ -339,7 +465,7 @@ int query_lengths(const uint8_t* qmask, int32_t* qlen, int B, int Nq, cudaStream
 }
 
 int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float* y, void* y16, float* fs, void* fs16, int B,
-               int Nq, int H, cudaStream_t st) {
+               int Nq, int H, cudaStream_t st, float* acts) {
   VML_CHECK_ARG(H % 32 == 0 && H <= 1024);
   static bool reg = (register_kernel("lstm_cluster_kernel"), true); (void)reg;
   const int UH = H / LSTM_CL;
@@ -348,7 +474,21 @@ int lstm_layer(const float* gin, const float* whh_t, const int32_t* qlen, float*
   VML_CHECK_ARG(smem <= 227 * 1024);
   VML_CUDA(ensure_dyn_smem((const void*)(lstm_cluster_kernel), (size_t)((int)smem)));
   const int clusters = 2 * ceil_div(B, LSTM_CL);
-  lstm_cluster_kernel<<<clusters * LSTM_CL, H, smem, st>>>(gin, whh_t, qlen, y, (bf16*)y16, fs, (bf16*)fs16, B, Nq, H);
+  lstm_cluster_kernel<<<clusters * LSTM_CL, H, smem, st>>>(gin, whh_t, qlen, y, (bf16*)y16, fs, (bf16*)fs16, acts, B, Nq, H);
+  VML_LAUNCHED(1);
+  return VML_OK;
+}
+
+int lstm_bwd_cluster(const float* dy, const float* dfs, const float* whh, const float* acts, const int32_t* qlen, float* dgin,
+                     float* dgin_rec, int B, int Nq, int H, cudaStream_t st) {
+  VML_CHECK_ARG(H % 32 == 0 && H <= 1024);
+  static bool reg = (register_kernel("lstm_bwd_cluster_kernel"), true); (void)reg;
+  const int UH = H / LSTM_CL;
+  const size_t smem = sizeof(float) * ((size_t)4 * UH * H + (size_t)LSTM_CL * 4 * UH + 2 * (size_t)LSTM_CL * LSTM_CL * UH);
+  if (smem > 227 * 1024) return 1;               // caller falls back to the one-CTA-per-sample kernel
+  VML_CUDA(ensure_dyn_smem((const void*)(lstm_bwd_cluster_kernel), (size_t)((int)smem)));
+  const int clusters = 2 * ceil_div(B, LSTM_CL);
+  lstm_bwd_cluster_kernel<<<clusters * LSTM_CL, H, smem, st>>>(dy, dfs, whh, acts, qlen, dgin, dgin_rec, B, Nq, H);
   VML_LAUNCHED(1);
   return VML_OK;
 }

@@ -32,6 +32,7 @@ class FusedAdam:
                 p.data = self.flat[o:o + k].view(p.shape)            # the parameter now lives inside the flat buffer
                 o += k
         self._offsets = self._param_offsets()
+        self._grad_views = [self.flat_grad[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self._offsets)]
 
     def _param_offsets(self):
         out, o = [], 0
@@ -98,14 +99,11 @@ class FusedAdam:
 
     def gather_grads(self):
         """Copy the per-parameter .grad tensors into ``flat_grad`` (zeros where a parameter has no grad)."""
-        o = 0
-        for p in self.params:
-            k = p.numel()
-            if p.grad is None:
-                self.flat_grad[o:o + k].zero_()
-            else:
-                self.flat_grad[o:o + k].copy_(p.grad.reshape(-1))
-            o += k
+        have = [(v, p.grad) for v, p in zip(self._grad_views, self.params) if p.grad is not None]
+        if len(have) < len(self.params):
+            self.flat_grad.zero_()
+        if have:            # one multi-tensor copy instead of one launch per parameter (107 on the 3-layer model)
+            torch._foreach_copy_([v for v, _ in have], [g.reshape(v.shape) for v, g in have])
         return self.flat_grad
 
     @torch.no_grad()

@@ -39,6 +39,32 @@ class Tape:
     pass
 
 
+class ZeroArena:
+    """Zero-initialised fp32 buffers of one backward pass carved out of ONE allocation with ONE memset (the pass needs
+    ~60 of them; a torch.zeros each was 60 fill launches).  The size is learnt from the previous step; a request that
+    does not fit falls back to torch.zeros and enlarges the next arena."""
+    _want: Dict[str, int] = {}
+
+    def __init__(self, key: str, device):
+        self.key, self.device, self.used = key, device, 0
+        n = ZeroArena._want.get(key, 0)
+        self.buf = torch.zeros(n, device=device, dtype=F32) if n else None
+
+    def zeros(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 63) // 64 * 64                       # 256-byte aligned pieces
+        lo = self.used
+        self.used += n_al
+        if self.buf is not None and lo + n <= self.buf.numel():
+            return self.buf[lo:lo + n].view(*shape)
+        return torch.zeros(*shape, device=self.device, dtype=F32)
+
+    def close(self):
+        ZeroArena._want[self.key] = max(ZeroArena._want.get(self.key, 0), self.used)
+
+
 def train_forward(pk: Dict[str, torch.Tensor], dims: Dims, inp: dict) -> tuple:
     """fp32 forward that keeps its intermediates.  ``inp`` comes from ``smin_ingest(..., prec=FP32)``."""
     P = L_.FP32
@@ -117,7 +143,8 @@ def train_backward(pk: Dict[str, torch.Tensor], dims: Dims, tp: Tape, g_pm, g_ps
     inp, cells, cap = tp.inp, tp.cells, tp.cap
     dev = tp.fv.device
     st = stream_ptr()
-    Z = lambda *shape: torch.zeros(*shape, device=dev, dtype=F32)
+    arena = ZeroArena(f"bwd:{B}:{cap}:{dev}", dev)
+    Z = arena.zeros
     E = lambda *shape: torch.empty(*shape, device=dev, dtype=F32)
     vmask, qmask, lmask, qlen = inp["vmask"], inp["qmask"], inp["lmask"], inp["qlen"]
     lay = query_layout(dims)
@@ -241,6 +268,7 @@ def train_backward(pk: Dict[str, torch.Tensor], dims: Dims, tp: Tape, g_pm, g_ps
     d_y0 = E(rows, 2 * H)
     _gemm(ptr(dgin1), 8 * H, 1, 0, ptr(pk["lstm_wih1"]), 1, 2 * H, 0, ptr(d_y0), 2 * H, 1, 0, rows, 2 * H, 8 * H)
     lstm_layer_bwd(0, d_y0, None, tp.acts0, inp["q"], 300, tp.y0)
+    arena.close()
     return g
 
 
