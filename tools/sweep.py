@@ -8,6 +8,13 @@ For map side N in {16,32,64,128}, batch B in {32..1024}, window ratio r = T/N in
 before every launch, the fused span-pool/fusion kernel (HBM roofline, SURVEY.md 8d bytes) and the
 moment-unit GEMM = the "map-conv stack" (tensor roofline, 4*V*D^2 flops), full-length videos
 (V = N(N+1)/2 valid cells per query).  Peaks: MEASURED_PEAKS.json.
+
+``--stages`` additionally runs the whole drop-in forward at every point (random-init SMIN of that map size, d0 = 64) and times
+the two stages that dominate it: the content unit (one persistent tcgen05 kernel per layer; HBM roofline on the bytes of
+DESIGN.md section 4) and the boundary unit (gate + rows + stream kernels), by re-issuing the recorded launches of the first
+SMI layer.  For ncu counters per point run the same command under
+``ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_tensor.sum,sm__inst_executed.avg.per_cycle_elapsed
+-k regex:'content_unit_kernel|boundary' --clock-control none`` with ``--quick`` (tools/ncu_sweep_summary.py turns the CSV into a table).
 """
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -44,10 +51,48 @@ def cold_time(fn, flush, reps=8):
     return tot / reps * 1e3   # us
 
 
+def stage_times(T, N, B, n, flush, hbm):
+    """Content unit and boundary unit of the first SMI layer inside a full forward of a random-init model of this map size."""
+    from vml_b200 import synth
+    from vml_b200.configs import SminConfig
+    from vml_b200.smin import SMIN
+    D, C, layers = 512, 4, 3
+    cfg = SminConfig("sweep", T, N, C, D, 128, layers, 64, 13, 256)
+    torch.manual_seed(7)
+    model = SMIN(*cfg.ctor_args(), device=torch.device("cuda"), precision="bf16").cuda().eval()
+    parts = [synth.make_batch(cfg, min(64, B - lo), 50 + lo, full_length=True) for lo in range(0, B, 64)]
+    b = {k: torch.cat([p[k] for p in parts]).cuda() for k in synth.MODEL_INPUT_KEYS}
+    model(*[b[k] for k in synth.MODEL_INPUT_KEYS], overlap=False)           # buffers of this shape exist
+    torch.cuda.synchronize()
+    rec, marks = [], []
+    L_.set_recorder(rec)
+    model(*[b[k] for k in synth.MODEL_INPUT_KEYS], mark=lambda name: marks.append((name, len(rec))))
+    L_.set_recorder(None)
+    torch.cuda.synchronize()
+    out, lo, seen = {}, 0, set()
+    for name, hi in marks:
+        calls, lo = rec[lo:hi], hi
+        if name not in ("content_unit", "boundary_unit") or name in seen or not calls:
+            continue
+        seen.add(name)                                                          # first SMI layer only
+        us = cold_time(lambda: [L_.call(fn, *a[:-1], stream_ptr()) for fn, a in calls], flush)
+        if name == "content_unit":
+            bytes_ = 2 * (2 * n * C * D + 2 * n * D)          # first layer: fc in, cu out, fbar in, mean_c cu out (bf16)
+            out.update(content_unit_us=round(us, 1), content_unit_GBs=round(bytes_ / us / 1e3, 1),
+                       content_unit_frac=round(bytes_ / us / 1e3 / hbm, 4))
+        else:
+            bytes_ = 2 * n * D + 4 * 3 * B * N * D
+            out.update(boundary_unit_us=round(us, 1), boundary_unit_GBs=round(bytes_ / us / 1e3, 1),
+                       boundary_unit_frac=round(bytes_ / us / 1e3 / hbm, 4))
+    del model, b
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also time the content unit and the boundary unit of a full forward per point")
     ap.add_argument("--clean-flush", action="store_true",
                     help="memset flush followed by a 256 MiB read: the timed kernel then does not pay the write-back of the flush's dirty lines")
     args = ap.parse_args()
@@ -95,9 +140,12 @@ def main():
                 us2 = cold_time(lambda: call("vml_moment_out", ptr(op), ptr(W), ptr(bias), ptr(fm), cells, ptr(mu), dims, L_.BF16, st), flush)
                 tfl = 4.0 * n * D * D / us2 / 1e6
                 row.update(moment_gemm_us=round(us2, 1), moment_gemm_TFs=round(tfl, 1), moment_gemm_frac=round(tfl / tf, 4))
+                del op, mu, fm, fv
+                torch.cuda.empty_cache()
+                if args.stages and n * C * D * 2 * 2.5 < 60e9:
+                    row.update(stage_times(T, N, B, n, flush, hbm))
                 rows.append(row)
                 print(json.dumps(row), flush=True)
-                del op, mu, fm, fv
                 torch.cuda.empty_cache()
     out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "timing": "CUDA events, L2 flushed (256 MiB memset" + (" + 256 MiB read: clean lines" if CLEAN else "") + ") before every launch, mean of 8",
            "rows": rows}

@@ -478,7 +478,10 @@ int launch_gemm_umma(const void* A, const void* W, int M, int N, int K, int lda,
   // 128 B/clk smem roof); used once there are enough tiles to fill the machine twice over
   const char* bn_knob = getenv("VML_GEMM_BN");              // (A/B knob) force the tile width: 128 or 256
   const int bn_force = bn_knob ? atoi(bn_knob) : 0;
-  if (N % 256 == 0 && bn_force != 128 && ((int64_t)ceil_div(M, UG_BM) * (N / 256) >= 2 * kNumSMs || bn_force == 256))
+  // 128 x 256 tiles halve the operand traffic per flop but need >= ~4 waves of them to balance 148 persistent CTAs; below
+  // that (Charades pass: 340 wide tiles = 2.3 waves -> 3 rounds) twice as many 128 x 128 tiles finish earlier (measured
+  // 41.2 vs 43.2 us per layer; TACoS / ActivityNet with >= 5 waves keep the wide tile: 105 vs 110 us)
+  if (N % 256 == 0 && bn_force != 128 && ((int64_t)ceil_div(M, UG_BM) * (N / 256) >= 4 * kNumSMs || bn_force == 256))
     return launch_gemm_umma_bn<256, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 128 == 0) return launch_gemm_umma_bn<128, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 64 == 0) return launch_gemm_umma_bn<64, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
