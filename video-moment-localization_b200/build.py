@@ -30,21 +30,32 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest(paths):
+def _digest(paths, cflags=None):
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode() + b"\0" + f.read())
-    h.update(" ".join(ARCH + CFLAGS).encode())
+    h.update(" ".join(ARCH + (CFLAGS if cflags is None else cflags)).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+LIB_DBG = os.path.join(HERE, "libvml_b200_dbg.so")
+
+
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """``debug=True``: the bounds-checking build (-DVML_DEBUG_BOUNDS, see csrc/common.cuh) as ``libvml_b200_dbg.so``; select it
+    at run time with ``VML_LIB=<path>``."""
+    if debug:
+        return _build(LIB_DBG, os.path.join(ROOT, "build", "vml_b200_dbg"), CFLAGS + ["-DVML_DEBUG_BOUNDS"], force, verbose)
+    return _build(LIB, OBJ_DIR, CFLAGS, force, verbose)
+
+
+def _build(LIB, OBJ_DIR, CFLAGS, force, verbose) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
         [os.path.join(ROOT, "include", "vml_b200.h")]
     stamp = os.path.join(OBJ_DIR, "stamp")
-    dig = _digest(deps)
+    dig = _digest(deps, CFLAGS)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
 
@@ -73,4 +84,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

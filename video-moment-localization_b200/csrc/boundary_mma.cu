@@ -626,6 +626,7 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
   constexpr int CB = 4;
   for (int seg = n_lo; seg < n_hi; seg += 32) {        // 32 cells of the row per segment
     const int seg_n = min(32, n_hi - seg);
+    VML_DBG_ASSERT(seg >= 0 && seg + seg_n <= capacity && (lane >= seg_n || (__ldg(code + seg + lane) & 0xff) < L));
     const float a_lane = lane < seg_n ? __ldg(arow + (__ldg(code + seg + lane) & 0xff)) : 0.f;
     for (int c0 = 0; c0 < seg_n; c0 += CB) {
       f8 m[CB][NG];

@@ -19,6 +19,23 @@ void count_launches(int n);
 // so a later, smaller launch of the same kernel must not shrink it.
 cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
 
+// Device-side bounds checks of the debug build (python -m vml_b200.build --debug -> libvml_b200_dbg.so, -DVML_DEBUG_BOUNDS):
+// compute-sanitizer is not available on the GPU pool, so the indices a kernel derives from device data (cell codes, live
+// counts, ring slots, tensor-memory columns, shared-memory boxes) are asserted in place; a violation prints its location and
+// traps, which surfaces as a launch failure (VmlError) in the GPU test that runs the forward on this build.
+#ifdef VML_DEBUG_BOUNDS
+#define VML_DBG_ASSERT(cond)                                                                              \
+  do {                                                                                                    \
+    if (!(cond)) {                                                                                        \
+      printf("VML_DBG_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+             (int)threadIdx.x);                                                                           \
+      asm volatile("trap;");                                                                              \
+    }                                                                                                     \
+  } while (0)
+#else
+#define VML_DBG_ASSERT(cond) do { } while (0)
+#endif
+
 #define VML_CHECK_ARG(cond)                                                        \
   do {                                                                             \
     if (!(cond)) {                                                                 \

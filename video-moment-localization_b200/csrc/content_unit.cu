@@ -203,6 +203,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (lane == 0) {                                    // ===================== TMA producer (V4) =====================
       auto load = [&](int bi, const CUtensorMap* tm, int c0, int c1) {
         const int slot = bi % RB;
+        VML_DBG_ASSERT(bi >= 0 && slot < RB && (slot + 1) * CU_BOX <= Cfg::X_BYTES && c1 >= 0);
         ptx::mbar_wait(&bempty[slot], ((bi / RB) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&bfull[slot], CU_BOX);
         ptx::tma_load_2d(Ring + slot * CU_BOX, tm, &bfull[slot], c0, c1);
@@ -263,6 +264,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t yb = yi & 1;
           ptx::mbar_wait(&yempty[yb], ((yi >> 1) & 1) ^ 1);
           const uint32_t d_tmem = tmem_base + (yb ? CU_TMEM_Y1 : CU_TMEM_Y0);
+          VML_DBG_ASSERT((d_tmem & 0xffffu) + 128u <= (tmem_base & 0xffffu) + 512u);      // accumulator inside the 512 allocated columns
           int sw[2], sx[2];
           for (int j = 0; j < 2; ++j) sw[j] = wait_box(base + 4 * nb + j);
           for (int j = 0; j < 2; ++j) sx[j] = wait_box(base + 4 * nb + 2 + j);
@@ -483,6 +485,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int cell = tile * (UG_BM / 4) + lane;
       const bool live = cell * 4 < M;
+      VML_DBG_ASSERT(!live || cell < *n_cells);
       for (int nb = 0; nb < NB; ++nb, ++c) {
         ptx::mbar_wait(side_full, c & 1);
         ptx::tc_fence_after();
@@ -544,6 +547,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int row = m0 + r;
       const bool valid = row < M;
       const int b = valid ? (code[row >> 2] >> 16) : -1;
+      VML_DBG_ASSERT(!valid || (b >= 0 && b < B));
       const int b_first = code[tile * (UG_BM / 4)] >> 16;
       const int b_last = code[(min(m0 + UG_BM, M) - 1) >> 2] >> 16;
       const int ngroups = (b_last - b_first) / GS + 1;
@@ -794,6 +798,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int i = 0; i < NP; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
       for (int nb = 0; nb < NB; ++nb, ++yi) {
         const uint32_t yb = yi & 1, yph = (yi >> 1) & 1;
+        VML_DBG_ASSERT(V != 4 || (box_of >= 0 && box_of < 2 && pc0 + NP <= 8));
         unsigned char* xb = V == 4 ? Ring + ((base_tail((int)it) + 4 * nb + 2 + box_of) % RB) * CU_BOX
                             : (V >= 2 && nb == NB - 1) ? Cs + box_of * CU_BOX : Xs + (2 * nb + box_of) * CU_BOX;
         ptx::mbar_wait_relaxed(&yfull[yb], yph);              // TMEM data: ordered by the tcgen05 fence below

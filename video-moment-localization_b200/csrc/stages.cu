@@ -335,6 +335,7 @@ span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, cons
   for (int n = n_lo + lane_cell; n < n_hi; n += cells_per_iter) {
     const int cd = code[n];
     const int i = (cd >> 8) & 0xff, j = cd & 0xff;
+    VML_DBG_ASSERT(n >= 0 && n < capacity && (cd >> 16) == b && i <= j && j < L);
     const int nf = (j - i + 1) * r;
     const int cs = max(1, nf / C);
     const int nclips = min(C, nf);           // <= 0 below the diagonal -> all-zero cell
@@ -348,6 +349,7 @@ span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, cons
     for (int c = 0; c < C; ++c) {
       f8 o;
       if (c < nclips) {
+        VML_DBG_ASSERT(s0 + (c + 1) * cs <= T && dd + 8 <= dslice);           // prefix row inside the [(T + 1) x dslice] table
         const f8 cur = ld8(P + (size_t)(s0 + (c + 1) * cs) * dslice + dd);
 #pragma unroll
         for (int e = 0; e < 8; ++e) { o.v[e] = (cur.v[e] - prev.v[e]) * w; mean.v[e] += o.v[e]; }

@@ -11,7 +11,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvml_b200.so")
+LIB_PATH = os.environ.get("VML_LIB") or os.path.join(HERE, "libvml_b200.so")      # VML_LIB: e.g. the bounds-checking debug build
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vml_b200.h")
 
 FP32, BF16, TF32 = 0, 1, 2          # TF32: fp32 tensors, dense products as tcgen05 kind::tf32 (training path only)
