@@ -55,6 +55,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.marks = []                      # (t0, t1) wall-clock windows of the timed regions
 
     def __enter__(self):
         try:
@@ -68,7 +69,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def window(self, t0, t1):
+        self.marks.append((t0, t1))
 
     def __exit__(self, *a):
         if self.proc:
@@ -80,12 +84,20 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        """Clocks and throttle reasons sampled while the measured legs ran.  The poller is started BEFORE the warm-up and
+        runs through all timed regions: spawning nvidia-smi (NVML initialisation takes driver locks) at the start of a
+        4 ms timed window stalled kernel launches and cost a 20-step run ~12 % against a 1000-step run."""
+        rows = [r[1:] for r in self.rows]
+        in_win = [r[1:] for r in self.rows if any(t0 - 0.25 <= r[0] <= t1 + 0.25 for t0, t1 in self.marks)]
+        use = in_win if in_win else rows
+        sm = sorted(int(r[0]) for r in use if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "samples_total": len(rows),
+                "sampling": "nvidia-smi -lms 100 from before the warm-up to after the last timed region; median over the samples "
+                            "within 0.25 s of a timed region (all of them under load: warm-up, timed and e2e legs run back to back)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -610,7 +622,10 @@ def run_eval(args, cfg, rank, world, local_rank):
 
     out = {}
     value = e2e_value = None
+    clocks = ClockSampler(local_rank)
     if not args.stages_only:
+        clocks.__enter__()
+        time.sleep(0.3)                      # nvidia-smi is up and polling before anything is timed
         # ---------------- device-resident throughput ------------------------------------------------
         # ScoringPipeline: per step one eager ingest launch + one CUDA-graph replay per pass, `slots` passes in flight
         for i in range(max(args.warmup, (2 * args.slots + 1) * args.coalesce)):
@@ -625,9 +640,10 @@ def run_eval(args, cfg, rank, world, local_rank):
             launches_per_step = lib.launch_count() - l0
         barrier()
         launches0 = lib.launch_count()
-        with ClockSampler(local_rank) as clocks:
-            ms_win, t_host, how = eb.timed_steps(args.steps, lambda i: pipe.submit(resident[i % n_rot]))
-            barrier()
+        t_w0 = time.time()
+        ms_win, t_host, how = eb.timed_steps(args.steps, lambda i: pipe.submit(resident[i % n_rot]))
+        barrier()
+        clocks.window(t_w0, time.time())
         launches = lib.launch_count() - launches0
         if launches_per_step is not None:     # per step: its own ingest launch + its share of the pass's kernels
             launches = int(args.steps * (1 + (launches_per_step - 1) / args.coalesce))
@@ -675,8 +691,10 @@ def run_eval(args, cfg, rank, world, local_rank):
         # untimed: every staging area of the H2D ring allocated and every (slot, position) ingest launch recorded
         e2e_time(max(args.warmup, len(pipe.staging) + 2 * args.coalesce) // args.coalesce * args.coalesce + args.coalesce, pinned)
         barrier()
+        t_w0 = time.time()
         e2e_ms, _, _ = e2e_time(args.steps, pinned)
         barrier()
+        clocks.window(t_w0, time.time())
         e2e_ms = max_over_ranks(e2e_ms)
         e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
 
@@ -696,6 +714,7 @@ def run_eval(args, cfg, rank, world, local_rank):
                      "ms_per_step": ms16 / args.steps, "note": "clip features and word vectors stored as bf16 on the host; "
                      "same scores bit for bit (round-to-nearest before the copy instead of after it)"}
             del pinned16
+        clocks.__exit__(None, None, None)
         out.update({
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,

@@ -201,24 +201,28 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   if (V == 4 && warp == 0) {
     if (lane == 0) {                                    // ===================== TMA producer (V4) =====================
-      auto load = [&](int bi, const CUtensorMap* tm, int c0, int c1) {
+      // L2 policy: the tile's first read and the weights stay (evict_last: the tile is read again ~8 us later by this SM,
+      // the weights by every SM all the time); the second read is the last use (evict_first).  Without the hints 55 % of the
+      // re-reads missed L2 on the ActivityNet pass (ncu: 2.38 GB read against 1.64 GB algorithmic).
+      const uint64_t keep = ptx::l2_policy_evict_last(), once = ptx::l2_policy_evict_first();
+      auto load = [&](int bi, const CUtensorMap* tm, int c0, int c1, uint64_t policy) {
         const int slot = bi % RB;
         VML_DBG_ASSERT(bi >= 0 && slot < RB && (slot + 1) * CU_BOX <= Cfg::X_BYTES && c1 >= 0);
         ptx::mbar_wait(&bempty[slot], ((bi / RB) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&bfull[slot], CU_BOX);
-        ptx::tma_load_2d(Ring + slot * CU_BOX, tm, &bfull[slot], c0, c1);
+        ptx::tma_load_2d_hint(Ring + slot * CU_BOX, tm, &bfull[slot], c0, c1, policy);
       };
       auto do_main = [&](int t) {
         const int base = base_main(t), m0 = (tile_begin + t) * UG_BM;
-        for (int kb = 0; kb < KB; ++kb) { load(base + 2 * kb, &tmX, kb * UG_BK, m0); load(base + 2 * kb + 1, &tmW1, kb * UG_BK, 0); }
+        for (int kb = 0; kb < KB; ++kb) { load(base + 2 * kb, &tmX, kb * UG_BK, m0, keep); load(base + 2 * kb + 1, &tmW1, kb * UG_BK, 0, keep); }
       };
       auto do_tail = [&](int t) {
         const int base = base_tail(t), m0 = (tile_begin + t) * UG_BM;
         for (int nb = 0; nb < NB; ++nb) {
-          load(base + 4 * nb, &tmW2, 0, nb * 128);
-          load(base + 4 * nb + 1, &tmW2, UG_BK, nb * 128);
-          load(base + 4 * nb + 2, &tmX, (2 * nb) * UG_BK, m0);
-          load(base + 4 * nb + 3, &tmX, (2 * nb + 1) * UG_BK, m0);
+          load(base + 4 * nb, &tmW2, 0, nb * 128, keep);
+          load(base + 4 * nb + 1, &tmW2, UG_BK, nb * 128, keep);
+          load(base + 4 * nb + 2, &tmX, (2 * nb) * UG_BK, m0, once);
+          load(base + 4 * nb + 3, &tmX, (2 * nb + 1) * UG_BK, m0, once);
         }
       };
       if (n_my > 0) do_main(0);
@@ -303,9 +307,9 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const int sx0 = (base + 4 * nb + 2) % RB, sx1 = (base + 4 * nb + 3) % RB;
           const unsigned char* b0 = Ring + sx0 * CU_BOX;
           const unsigned char* b1 = Ring + sx1 * CU_BOX;
-          if (store_cu) {
-            ptx::tma_store_2d(&tmOut, b0, nb * 128, m0);
-            ptx::tma_store_2d(&tmOut, b1, nb * 128 + 64, m0);
+          if (store_cu) {               // the next reader of cu is a later kernel: do not let it push the tiles being re-read out of L2
+            ptx::tma_store_2d_hint(&tmOut, b0, nb * 128, m0, ptx::l2_policy_evict_first());
+            ptx::tma_store_2d_hint(&tmOut, b1, nb * 128 + 64, m0, ptx::l2_policy_evict_first());
             ptx::bulk_commit();
           }
           // mean over the cell's 4 clips of the finished block on the tensor cores (see V3)
