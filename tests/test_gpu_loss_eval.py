@@ -132,6 +132,26 @@ def test_loss_gradients_match_autograd_of_oracle():
         assert torch.all(a.grad.cpu()[~mk] == 0)
 
 
+def test_single_term_bce_loss_is_differentiable_like_the_reference():
+    """main.bce_loss (main.py:89-108) is used term by term with autograd in the reference: each of its three call forms must
+    back-propagate to its score tensor (round-1 finding: the drop-in returned a non-differentiable part)."""
+    cfg = CONFIGS["charadessta"]
+    batch, pm, ps, pe, pa = _scores(cfg, 4, 43)
+    g = lambda t: t.cuda()
+    forms = [(pm, batch["ym"], batch["sm"], batch["moment_mask"]), (ps, batch["ys"], batch["ss"], batch["length_mask"]),
+             (pa, batch["ya"], None, batch["length_mask"])]
+    for p, y, s_, mk in forms:
+        ref_p = p.clone().requires_grad_(True)
+        ref = mo.scaled_iou_bce(ref_p, y, s_, mk)
+        ref.backward()
+        dp = p.detach().cuda().requires_grad_(True)
+        out = bce_loss(dp, g(y), None if s_ is None else g(s_), g(mk))
+        assert out.requires_grad and abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+        (3.0 * out).backward()
+        assert torch.allclose(dp.grad.cpu()[mk], 3.0 * ref_p.grad[mk], rtol=1e-4, atol=1e-7)
+        assert torch.all(dp.grad.cpu()[~mk] == 0)
+
+
 @pytest.mark.parametrize("name,B,seed", [("charadessta", 8, 51), ("tacos", 4, 53), ("activitynet", 3, 54)])
 def test_end_to_end_fp32_indices_and_recall_exact(name, B, seed):
     """fp32 validation mode end to end: CUDA scores -> CUDA top-k == oracle scores -> oracle top-k, sample by sample

@@ -63,15 +63,34 @@ def loss_terms(pm, ym, sm, moment_mask, ps, ys, ss, pe, ye, se, pa, ya, length_m
     return _ScaledIouBce.apply(pm, ps, pe, pa, ym, sm, moment_mask, ys, ss, ye, se, ya, length_mask)
 
 
+class _SingleTerm(torch.autograd.Function):
+    """One term of the loss (main.py:89-108) through the same fused kernel, differentiable w.r.t. its score tensor: the kernel
+    returns d(L_m + L_s + L_e + 0.5 L_a) / d(score), so the auxiliary term's gradient is rescaled by 2."""
+
+    @staticmethod
+    def forward(ctx, p, which, args):
+        need = p.requires_grad
+        out, grads = _launch(*args, want_grad=need)
+        ctx.which = which
+        if need:
+            ctx.save_for_backward(grads[which] * (2.0 if which == 3 else 1.0))
+        return out[1 + which].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp,) = ctx.saved_tensors
+        return gp * g, None, None
+
+
 def bce_loss(p, y, s, mask):
-    """main.py:89-108 for a single term (3-D map branch or 2-D boundary branch)."""
+    """main.py:89-108 for a single term (3-D map branch or 2-D boundary branch); differentiable w.r.t. ``p`` like the
+    reference's (autograd-tested against the oracle)."""
     if p.dim() == 3:
         B, L = p.shape[0], p.shape[1]
         z = torch.zeros(B, L, device=p.device)
         zm = torch.ones(B, L, device=p.device, dtype=torch.uint8)
         half = torch.full((B, L), 0.5, device=p.device)
-        _, parts = loss_terms(p, y, s, mask, half, z, z, half, z, z, half, z, zm)
-        return parts[0]
+        return _SingleTerm.apply(p, 0, (p, y, s, mask, half, z, z, half, z, z, half, z, zm))
     B, L = p.shape
     zmap = torch.full((B, L, L), 0.5, device=p.device)
     z3 = torch.zeros(B, L, L, device=p.device)
@@ -79,7 +98,5 @@ def bce_loss(p, y, s, mask):
     half = torch.full((B, L), 0.5, device=p.device)
     z = torch.zeros(B, L, device=p.device)
     if s is None:
-        _, parts = loss_terms(zmap, z3, z3, o3, half, z, z, half, z, z, p, y, mask)
-        return parts[3]
-    _, parts = loss_terms(zmap, z3, z3, o3, p, y, s, half, z, z, half, z, mask)
-    return parts[1]
+        return _SingleTerm.apply(p, 3, (zmap, z3, z3, o3, half, z, z, half, z, z, p, y, mask))
+    return _SingleTerm.apply(p, 1, (zmap, z3, z3, o3, p, y, s, half, z, z, half, z, mask))
