@@ -243,6 +243,7 @@ VML_API int vml_linear(const void* A, const void* W, const float* bias, void* ou
   VML_PREC_OK(prec);
   VML_CHECK_ARG(ldo >= N && ldo % 4 == 0 && m_scale >= 1);
   if (prec == VML_BF16 && !out_fp32) {
+    VML_CHECK_ARG(ldo % 8 == 0);            // 16-byte bf16 stores in the epilogue
     EpiBias<bf16> e{bias, (bf16*)out, ldo};
     return gemm_dispatch(A, W, M, N, K, K, m_dev, m_scale, e, prec, ST(stream));
   }
@@ -255,7 +256,7 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
   VML_PREC_OK(prec);
   const int M = B * d.T;
   if (prec == VML_BF16) {
-    EpiClip<bf16> e{bias, pe, video_mask, d.T, (bf16*)fv, d.D};
+    EpiClipPre e{bias, pe, video_mask, d.T, (bf16*)fv, d.D};
     return launch_gemm_umma(v, W, M, d.D, k_pad, k_pad, k_pad, nullptr, 1, e, ST(stream));
   }
   EpiClip<float> e{bias, pe, video_mask, d.T, (float*)fv, d.D};
@@ -374,7 +375,8 @@ VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* b
     return gemm_res(operand, Wcat, bias_sum, fm, nullptr, mu, nullptr, cells.capacity, d.D, 2 * d.D, 2 * d.D, 0, cells.n_cells, 1,
                     ST(stream));
   if (prec == VML_BF16) {
-    EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D};
+    static const int pf = getenv("VML_GEMM_NO_PREFETCH") == nullptr;    // (A/B knob)
+    EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D, pf};
     return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
   }
   EpiMomentOut<float> e{bias_sum, (const float*)fm, (float*)mu, d.D};

@@ -21,11 +21,11 @@ constexpr int BMM_ROWS = 16, BMM_WARPS = 8, BMM_THREADS = BMM_WARPS * 32;
 constexpr int BMM_MAXQ = 32;      // word slots (Nq <= 32)
 constexpr int BMM_MAXD64 = 8;     // D <= 512: D/64 column tiles per warp
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> tf32, round to nearest, ties away from zero (= cvt.rna.tf32.f32 for every finite input that does not round up to
+// infinity): half an ulp of the 10-bit mantissa is added to the magnitude and the 13 dropped bits are cleared.  ptxas expands
+// cvt.rna.tf32 on sm_100a into a ~5-instruction compare/select sequence; with six conversions per mma.m16n8k8 that sequence was
+// a quarter of all instructions the gate / rows kernels issued (ncu source page, profiles/r02_boundary_gate_rows_hotspots.txt).
+__device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -351,8 +351,38 @@ boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
   const int dq = D / 4;
   // staging: 12 independent 16-byte loads in flight per thread before the first shared-memory store (the unit is
-  // latency-bound: one load per iteration meant ~20 dependent trips to L2 / HBM per CTA)
-  {
+  // latency-bound: one load per iteration meant ~20 dependent trips to L2 / HBM per CTA).  A thread keeps ONE column chunk
+  // and walks rows (BMM_THREADS / dq rows per sweep): no per-element division by the run-time row length.
+  if (BMM_THREADS % dq == 0) {
+    constexpr int UB = 4;
+    const int rstep = BMM_THREADS / dq, r0 = tid / dq, c4 = (tid - r0 * dq) * 4;
+    const int nrow = max(Nq, BMM_ROWS);
+    const float* kp = qproj + (size_t)b * Nq * ld + off_kbt + c4;
+    const float* wp = fw + (size_t)b * Nq * D + c4;
+    const float* xp = fb + (size_t)b * L * D + c4;
+    for (int k0 = r0; k0 < nrow; k0 += UB * rstep) {
+      float4 kv[UB], wv[UB], xv[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int k = k0 + u * rstep;
+        kv[u] = wv[u] = xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < Nq) {
+          kv[u] = __ldg(reinterpret_cast<const float4*>(kp + (size_t)k * ld));
+          wv[u] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * D));
+        }
+        if (k < L) xv[u] = __ldg(reinterpret_cast<const float4*>(xp + (size_t)k * D));
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int k = k0 + u * rstep;
+        if (k < Nq) {
+          *reinterpret_cast<float4*>(Ks + (size_t)k * DS + c4) = kv[u];
+          *reinterpret_cast<float4*>(Ws + (size_t)k * DS + c4) = wv[u];
+        }
+        if (k < BMM_ROWS) *reinterpret_cast<float4*>(Xs + (size_t)k * DS + c4) = xv[u];
+      }
+    }
+  } else {
     constexpr int UB = 4;
     const int nkw = Nq * dq, nx = BMM_ROWS * dq;
     for (int e0 = tid; e0 < max(nkw, nx); e0 += UB * BMM_THREADS) {

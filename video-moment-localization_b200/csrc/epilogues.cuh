@@ -7,6 +7,9 @@
 namespace vml {
 
 // out = acc + bias                                   (nn.Linear, models.py:134-135,236-239 ...)
+// A thread of the tcgen05 epilogue owns ONE output row (the TMEM lane), so every global access of a warp touches 32
+// different rows: the cost is the number of memory instructions (one L1 wavefront per row each), not bytes.  Hence
+// 16-byte accesses everywhere: bias as float4 (one broadcast wavefront), bf16 results eight at a time.
 template <typename OutT>
 struct EpiBias {
   const float* bias;  // [N] or nullptr
@@ -15,11 +18,27 @@ struct EpiBias {
   template <int N>
   __device__ __forceinline__ void apply(int row, int col0, const float* acc) const {
     OutT* o = out + (size_t)row * ldo + col0;
+    if constexpr (N % 8 == 0) {                // tcgen05 epilogue (N = 32): col0 and ldo are multiples of 8
 #pragma unroll
-    for (int c = 0; c < N; c += 4) {
-      float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-      if (bias) { v.x += bias[col0 + c]; v.y += bias[col0 + c + 1]; v.z += bias[col0 + c + 2]; v.w += bias[col0 + c + 3]; }
-      st4(o + c, v);
+      for (int c = 0; c < N; c += 8) {
+        f8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = acc[c + e];
+        if (bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + c + 4));
+          v.v[0] += b0.x; v.v[1] += b0.y; v.v[2] += b0.z; v.v[3] += b0.w;
+          v.v[4] += b1.x; v.v[5] += b1.y; v.v[6] += b1.z; v.v[7] += b1.w;
+        }
+        st8(o + c, v);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < N; c += 4) {
+        float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        if (bias) { v.x += bias[col0 + c]; v.y += bias[col0 + c + 1]; v.z += bias[col0 + c + 2]; v.w += bias[col0 + c + 3]; }
+        st4(o + c, v);
+      }
     }
   }
 };
@@ -46,6 +65,53 @@ struct EpiClip {
       v.z = (acc[c + 2] + bias[col0 + c + 2]) * m + p[c + 2] * m;
       v.w = (acc[c + 3] + bias[col0 + c + 3]) * m + p[c + 3] * m;
       st4(o + c, v);
+    }
+  }
+};
+
+// bf16 variant for the tcgen05 GEMM: the positional-encoding row of a thread (32 columns = eight 16-byte loads) and its mask
+// byte are fetched while the MMA of the tile is still running; the scalar version above issued 64 dependent 4-byte loads per
+// 32 columns, each a wavefront per row: the epilogue, not the tensor pipe, set the time of the projection (ncu: 14 % tensor
+// active, long-scoreboard stalls on the epilogue FADDs).
+struct EpiClipPre {
+  const float* bias;     // [D]
+  const float* pe;       // [T, D]
+  const uint8_t* vmask;  // [B*T]
+  int T;
+  bf16* out;             // [B*T, D]
+  int ldo;
+  struct Pre { float4 p[8]; float m; };
+  __device__ __forceinline__ Pre load(int row, int col0, bool valid) const {
+    Pre r;
+    if (valid) {
+      const float4* p = reinterpret_cast<const float4*>(pe + (size_t)(row % T) * ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.p[i] = __ldg(p + i);
+      r.m = vmask[row] ? 1.0f : 0.0f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.m = 0.f;
+    }
+    return r;
+  }
+  template <int N>
+  __device__ __forceinline__ void apply_pre(int row, int col0, const float* acc, const Pre& r, bool valid) const {
+    static_assert(N == 32, "prefetch bundle holds 32 columns");
+    if (!valid) return;
+    bf16* o = out + (size_t)row * ldo + col0;
+    const float m = r.m;
+#pragma unroll
+    for (int c = 0; c < N; c += 8) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + c + 4));
+      const float4 p0 = r.p[c / 4], p1 = r.p[c / 4 + 1];
+      f8 v;                                   // same expression, term by term, as EpiClip::apply
+      v.v[0] = (acc[c] + b0.x) * m + p0.x * m;     v.v[1] = (acc[c + 1] + b0.y) * m + p0.y * m;
+      v.v[2] = (acc[c + 2] + b0.z) * m + p0.z * m; v.v[3] = (acc[c + 3] + b0.w) * m + p0.w * m;
+      v.v[4] = (acc[c + 4] + b1.x) * m + p1.x * m; v.v[5] = (acc[c + 5] + b1.y) * m + p1.y * m;
+      v.v[6] = (acc[c + 6] + b1.z) * m + p1.z * m; v.v[7] = (acc[c + 7] + b1.w) * m + p1.w * m;
+      st8(o + c, v);
     }
   }
 };
@@ -119,9 +185,9 @@ struct EpiContentOutFused {
     for (int c = 0; c < N; c += 8) {
       f8 v;
       if (valid) {
-        const f8 xv = unpack8(p.x[c / 8]), fv = unpack8(p.f[c / 8]);
+        const f8 xv = unpack8(p.x[c / 8]), fv = unpack8(p.f[c / 8]), bv = ld8(bias + col0 + c);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bias[col0 + c + e]) + xv.v[e] + fv.v[e];
+        for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bv.v[e]) + xv.v[e] + fv.v[e];
         st8(o + c, v);
       } else {
 #pragma unroll
@@ -147,6 +213,7 @@ struct EpiMomentOutPre {
   const bf16* fm;     // [n, D]
   bf16* out;          // [n, D]
   int ldo;
+  int pf_a;           // L2 prefetch of the next tile's operand rows (gemm_umma.cuh)
   struct Pre { uint4 m[4]; };
   __device__ __forceinline__ Pre load(int row, int col0, bool valid) const {
     Pre p;
@@ -163,9 +230,10 @@ struct EpiMomentOutPre {
 #pragma unroll
     for (int c = 0; c < N; c += 8) {
       const f8 mv = unpack8(p.m[c / 8]);
+      const f8 bv = ld8(bias + col0 + c);      // two 16-byte broadcast loads instead of eight scalar ones
       f8 v;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bias[col0 + c + e]) + mv.v[e];
+      for (int e = 0; e < 8; ++e) v.v[e] = (acc[c + e] + bv.v[e]) + mv.v[e];
       st8(o + c, v);
     }
   }

@@ -12,6 +12,7 @@
 #pragma once
 #include <stdlib.h>
 #include <type_traits>
+#include <utility>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -43,6 +44,12 @@ template <typename E, typename = void>
 struct epi_has_pre : std::false_type {};
 template <typename E>
 struct epi_has_pre<E, std::void_t<typename E::Pre>> : std::true_type {};
+// an epilogue may carry a run-time switch `pf_a`: the producer then asks L2 for the NEXT tile's A boxes while the current
+// tile is being multiplied (the A rows of a tile are one contiguous block of memory when K spans the whole row)
+template <typename E, typename = void>
+struct epi_has_pf : std::false_type {};
+template <typename E>
+struct epi_has_pf<E, std::void_t<decltype(std::declval<const E&>().pf_a)>> : std::true_type {};
 
 template <int BN>
 struct UmmaCfg {
@@ -108,6 +115,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m0 = tile_m0(tile), n0 = (tile % tiles_n) * BN;
+        if constexpr (epi_has_pf<Epi>::value && CL == 1) {
+          // one CTA per m-tile asks (the tiles of the other n columns of that m-tile run at the same time on its neighbours)
+          const int nt = tile + tile_step;
+          if (epi.pf_a && nt < num_tiles && (nt % tiles_n == 0 || tile_step % tiles_n != 0))
+            for (int kb = 0; kb < k_blocks; ++kb) ptx::tma_prefetch_2d(&tmA, kb * BK, tile_m0(nt));
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);      // CL == 2: both CTAs' MMAs have retired from this stage
           unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -171,11 +184,19 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = c_lo; c < c_hi; c += 32) {
           float v[32];
           ptx::tmem_ld32(t_addr + (uint32_t)c, v);
-          typename Epi::Pre nxt = pre;
-          if (c + 32 < c_hi) nxt = epi.load(row, n0 + c + 32, row < M);
-          ptx::tmem_ld_wait();
-          epi.template apply_pre<32>(row, n0 + c, v, pre, row < M);
-          pre = nxt;
+          if constexpr (EW == 16 && sizeof(typename Epi::Pre) > 64) {
+            // 640 threads leave 96 registers: one bundle at a time (the next one is requested right after this chunk's
+            // arithmetic, under the next TMEM load)
+            ptx::tmem_ld_wait();
+            epi.template apply_pre<32>(row, n0 + c, v, pre, row < M);
+            if (c + 32 < c_hi) pre = epi.load(row, n0 + c + 32, row < M);
+          } else {
+            typename Epi::Pre nxt = pre;
+            if (c + 32 < c_hi) nxt = epi.load(row, n0 + c + 32, row < M);
+            ptx::tmem_ld_wait();
+            epi.template apply_pre<32>(row, n0 + c, v, pre, row < M);
+            pre = nxt;
+          }
         }
       } else {
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
