@@ -375,7 +375,9 @@ VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* b
     return gemm_res(operand, Wcat, bias_sum, fm, nullptr, mu, nullptr, cells.capacity, d.D, 2 * d.D, 2 * d.D, 0, cells.n_cells, 1,
                     ST(stream));
   if (prec == VML_BF16) {
-    static const int pf = getenv("VML_GEMM_NO_PREFETCH") == nullptr;    // (A/B knob)
+    // (A/B knob) L2 prefetch of the next tile's operand rows: measured on B200 it SLOWS the stage (20.9 -> 23.5 us per step at
+    // 640-query passes): the loop is not short of latency cover, the prefetches only add L2 request traffic
+    static const int pf = getenv("VML_GEMM_PREFETCH") != nullptr;
     EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D, pf};
     return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
   }

@@ -333,6 +333,10 @@ boundary_rows_mma_kernel(const float* __restrict__ G, const float* __restrict__ 
 // Same arithmetic, in the same order, as boundary_gate_mma_kernel followed by boundary_rows_mma_kernel (JR = 16): the
 // gated rows G stay in shared memory (over the dead key / word tiles) instead of a round trip through global memory,
 // and one launch + one staging pass disappear.  One CTA per sample.
+// (Measured dead end, round 2: 16 warps per sample with the word states fetched straight into MMA fragments -- 32 resident
+// warps per SM instead of 16, a third less shared memory -- runs in the same 54 us per 640 samples as this version; so does
+// the version before the cheaper tf32 rounding below at +25 % instructions.  The kernel's time is the chain of eight
+// barrier-separated phases per sample times 2.2 waves of CTAs, not issue slots or bytes.)
 template <bool PRECISE>
 __global__ void __launch_bounds__(BMM_THREADS)
 boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
@@ -657,7 +661,10 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
   for (int seg = n_lo; seg < n_hi; seg += 32) {        // 32 cells of the row per segment
     const int seg_n = min(32, n_hi - seg);
     VML_DBG_ASSERT(seg >= 0 && seg + seg_n <= capacity && (lane >= seg_n || (__ldg(code + seg + lane) & 0xff) < L));
-    const float a_lane = lane < seg_n ? __ldg(arow + (__ldg(code + seg + lane) & 0xff)) : 0.f;
+    // the attention weight of a cell hangs on a dependent pair of loads (code -> A_b[i, j]); the first batch of map loads is
+    // put in flight between the two so that the row pays two memory round trips, not three
+    const int cd_lane = lane < seg_n ? __ldg(code + seg + lane) : 0;
+    float a_lane = 0.f;
     for (int c0 = 0; c0 < seg_n; c0 += CB) {
       f8 m[CB][NG];
 #pragma unroll
@@ -670,6 +677,7 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
           if (q * 256 + lane * 8 < Dc) m[u][q] = ld8(fm + (size_t)n * ldD + q * 256 + lane * 8);
         }
       }
+      if (c0 == 0) a_lane = lane < seg_n ? __ldg(arow + (cd_lane & 0xff)) : 0.f;
 #pragma unroll
       for (int u = 0; u < CB; ++u) {
         const float a = __shfl_sync(0xffffffffu, a_lane, (c0 + u) & 31);
