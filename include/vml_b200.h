@@ -108,6 +108,16 @@ VML_API int vml_ingest_bf16(const void* video_features, const void* query_featur
                             const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
                             uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d,
                             int v_kpad, int q_kpad, int prec, void* stream);
+/* Same, with the clip features PACKED: video_rows holds only the first min(nfeats[b], T) rows of every sample, back to
+ * back ([sum_b min(nfeats[b], T), d0], float or -- src_bf16 != 0 -- bf16); the rows dataset.py:69-73
+ * (get_fixed_length_features: `out = np.zeros((T, d)); out[:nfeats] = cur_feat`) leaves at zero are re-created by this
+ * launch instead of crossing PCIe.  nfeats: device int64 [B] (dataset.py:72).  B <= 4096.  The operands written are
+ * bit-identical to vml_ingest's on the padded [B, T, d0] tensor. */
+VML_API int vml_ingest_packed(const void* video_rows, const void* query_features, const uint8_t* video_mask,
+                              const uint8_t* query_mask, const uint8_t* length_mask, const uint8_t* moment_mask,
+                              const float* sm, const int64_t* nfeats, void* v_out, void* q_out, uint8_t* vmask_out,
+                              uint8_t* qmask_out, uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen,
+                              int B, vml_dims_t d, int v_kpad, int q_kpad, int prec, int src_bf16, void* stream);
 
 /* ---- dense contractions --------------------------------------------------------------- */
 

@@ -194,3 +194,53 @@ def test_compact_batches_with_device_built_labels_equal_full_batches(from_host):
     t2 = b_.submit(src, from_host=from_host); b_.flush(); t2.synchronize()
     for x, y in zip(t1.slot.outputs[0], t2.slot.outputs[0]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("prec,feature_dtype", [("bf16", None), ("bf16", torch.bfloat16), ("fp32", None)])
+def test_packed_batches_equal_padded_batches(prec, feature_dtype):
+    """Clip features shipped WITHOUT their all-zero padding rows (dataset.py:69-73 pads to T): vml_ingest_packed re-creates the
+    padding on the device.  Scores, hit counters and per-step read-backs are bit-identical to the padded compact batches;
+    the blob shrinks to ~mean(nfeats) / T.  Includes full-length videos, a 1-clip video, a tail batch of another size and a
+    switch from padded to packed blobs on the same staging ring."""
+    from vml_b200.pipeline import pack_host_batch
+    cfg = CONFIGS["charadessta"]
+    model = model_for(cfg, prec)
+    batches = [synth.make_batch(cfg, 8, 900 + i) for i in range(4)]
+    batches.append(synth.make_batch(cfg, 8, 950, full_length=True))
+    batches.append(synth.make_batch(cfg, 8, 951, nfeats_range=(1, 5)))
+    batches += [synth.make_batch(cfg, 8, 960 + i) for i in range(2)]
+    batches.append(synth.make_batch(cfg, 3, 999))
+    ref = ScoringPipeline(model, slots=2, coalesce=2)
+    rb_ref = [torch.zeros(2, 4, dtype=torch.int64).pin_memory() for _ in batches]
+    for i, b in enumerate(batches):
+        ref.submit(pack_host_batch(b, feature_dtype=feature_dtype, compact=True), from_host=True, readback=rb_ref[i])
+    want = ref.result(normalize=False)
+    pipe = ScoringPipeline(model, slots=2, coalesce=2)
+    rb = [torch.zeros(2, 4, dtype=torch.int64).pin_memory() for _ in batches]
+    padded_bytes = packed_bytes = 0
+    for rounds in range(2):                   # second round: fast path (recorded ingest launches) + reused staging areas
+        for i, b in enumerate(batches):
+            pk = pack_host_batch(b, feature_dtype=feature_dtype, packed=True)
+            padded_bytes += pack_host_batch(b, feature_dtype=feature_dtype, compact=True)["_blob"].numel()
+            packed_bytes += pk["_blob"].numel()
+            pipe.submit(pk, from_host=True, readback=rb[i])
+    got = pipe.result(normalize=False)
+    assert got == {k: 2 * v for k, v in want.items()}
+    for x, y in zip(rb, rb_ref):
+        assert torch.equal(x, y)
+    assert packed_bytes < 0.9 * padded_bytes
+    # scores of one batch, bit for bit (and a padded blob followed by a packed one on the same staging area)
+    a = ScoringPipeline(model, slots=1, coalesce=1)
+    t1 = a.submit(pack_host_batch(batches[0], feature_dtype=feature_dtype, compact=True), from_host=True); a.flush(); t1.synchronize()
+    want_out = [x.clone() for x in t1.slot.outputs[0]]
+    for _ in range(3):
+        t2 = a.submit(pack_host_batch(batches[0], feature_dtype=feature_dtype, packed=True), from_host=True); a.flush(); t2.synchronize()
+        for x, y in zip(want_out, t2.slot.outputs[0]):
+            assert torch.equal(x, y)
+    # a device-resident packed batch is re-padded and scored as usual
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in pack_host_batch(batches[0], packed=True).items() if k != "_blob"}
+    b3 = ScoringPipeline(model, slots=1, coalesce=1)
+    t3 = b3.submit(dev); b3.flush(); t3.synchronize()
+    if feature_dtype is None:
+        for x, y in zip(want_out, t3.slot.outputs[0]):
+            assert torch.equal(x, y)

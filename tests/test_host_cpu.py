@@ -98,3 +98,17 @@ def test_dropin_modules_resolve_like_main_py_imports():
     env = dict(os.environ, PYTHONPATH=dropin)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_pack_video_rows_round_trip():
+    """Packed clip features (no padding rows) <-> the padded [B, T, d0] tensor of dataset.py:69-73."""
+    import torch
+    from vml_b200 import synth
+    from vml_b200.configs import CONFIGS
+    from vml_b200.pipeline import pack_video_rows, unpack_video_rows
+    cfg = CONFIGS["charadessta"]
+    for kw in ({}, {"full_length": True}, {"nfeats_range": (1, 3)}):
+        b = synth.make_batch(cfg, 6, 5, **kw)
+        rows = pack_video_rows(b["video_features"], b["nfeats"])
+        assert rows.shape == (int(b["nfeats"].clamp(max=cfg.T).sum()), cfg.d0)
+        assert torch.equal(unpack_video_rows(rows, b["nfeats"], cfg.T), b["video_features"])

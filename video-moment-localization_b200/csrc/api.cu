@@ -106,7 +106,7 @@ int build_cells(const uint8_t*, int, int, vml_cells_t, cudaStream_t);
 int unpack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
 int pack_cells(const void*, void*, vml_cells_t, int, int, int, int, cudaStream_t);
 int cast_pad(const float*, void*, int64_t, int, int, cudaStream_t);
-int ingest(const void*, const void*, int, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const float*, void*,
+int ingest(const void*, const void*, int, const int64_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const float*, void*,
            void*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, float*, int32_t*, int, vml_dims_t, int, int, int, cudaStream_t);
 int span_pool_fuse(const void*, const float*, vml_cells_t, void*, void*, float*, int, vml_dims_t, int, cudaStream_t);
 int content_attention(const void*, const float*, int, int, int, int, const float*, int, const uint8_t*, vml_cells_t,
@@ -210,7 +210,7 @@ VML_API int vml_ingest(const float* video_features, const float* query_features,
                        uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad, int q_kpad,
                        int prec, void* stream) {
   VML_PREC_OK(prec);
-  return ingest(video_features, query_features, 0, video_mask, query_mask, length_mask, moment_mask, sm, v_out, q_out, vmask_out,
+  return ingest(video_features, query_features, 0, nullptr, video_mask, query_mask, length_mask, moment_mask, sm, v_out, q_out, vmask_out,
                 qmask_out, lmask_out, mmask_out, sm_out, qlen, B, d, v_kpad, q_kpad, prec, ST(stream));
 }
 
@@ -220,8 +220,19 @@ VML_API int vml_ingest_bf16(const void* video_features, const void* query_featur
                     uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad, int q_kpad,
                     int prec, void* stream) {
   VML_PREC_OK(prec);
-  return ingest(video_features, query_features, 1, video_mask, query_mask, length_mask, moment_mask, sm, v_out, q_out, vmask_out,
+  return ingest(video_features, query_features, 1, nullptr, video_mask, query_mask, length_mask, moment_mask, sm, v_out, q_out, vmask_out,
                 qmask_out, lmask_out, mmask_out, sm_out, qlen, B, d, v_kpad, q_kpad, prec, ST(stream));
+}
+
+VML_API int vml_ingest_packed(const void* video_rows, const void* query_features, const uint8_t* video_mask,
+                              const uint8_t* query_mask, const uint8_t* length_mask, const uint8_t* moment_mask, const float* sm,
+                              const int64_t* nfeats, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
+                              uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d,
+                              int v_kpad, int q_kpad, int prec, int src_bf16, void* stream) {
+  VML_PREC_OK(prec);
+  if (nfeats == nullptr) { set_error("vml_ingest_packed: nfeats is NULL"); return VML_ERR_ARG; }
+  return ingest(video_rows, query_features, src_bf16 != 0, nfeats, video_mask, query_mask, length_mask, moment_mask, sm, v_out,
+                q_out, vmask_out, qmask_out, lmask_out, mmask_out, sm_out, qlen, B, d, v_kpad, q_kpad, prec, ST(stream));
 }
 
 VML_API int vml_gemm_strided(const float* A, int64_t sam, int64_t sak, int64_t sab, const float* B, int64_t sbn, int64_t sbk,

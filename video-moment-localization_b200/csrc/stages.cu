@@ -168,12 +168,33 @@ struct IngestArgs {
   int64_t mbytes[4];
   const float* sm_src; float* sm_dst; int64_t sm_n;
   const uint8_t* qmask; int32_t* qlen; int B, Nq;
+  // packed clip features (vml_ingest_packed): src[0] holds only the first min(nfeats[b], T) rows of every sample, back to
+  // back -- the rows dataset.py:69-73 leaves at zero never cross PCIe; they are re-created here
+  const int64_t* v_nfeats; int T;
 };
+
+constexpr int INGEST_MAXB = 4096;                     // samples per packed ingest launch (row offsets live in shared memory)
 
 template <bool BF16, bool SRC16>
 __global__ void __launch_bounds__(256)
 ingest_kernel(IngestArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  extern __shared__ int32_t s_rowoff[];                // packed mode: [B + 1] first source row of every sample
+  if (a.v_nfeats) {
+    // exclusive scan of min(nfeats, T) by warp 0: every lane sums a contiguous chunk, the chunk totals are scanned by shuffle
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x, per = (a.B + 31) / 32, lo = min(lane * per, a.B), hi = min(lo + per, a.B);
+      int sum = 0;
+      for (int b = lo; b < hi; ++b) sum += (int)min((int64_t)a.T, max((int64_t)0, a.v_nfeats[b]));
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+      int run = incl - sum;
+      for (int b = lo; b < hi; ++b) { s_rowoff[b] = run; run += (int)min((int64_t)a.T, max((int64_t)0, a.v_nfeats[b])); }
+      if (lane == 31) s_rowoff[a.B] = incl;
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (!a.dst[s]) continue;
@@ -181,22 +202,29 @@ ingest_kernel(IngestArgs a) {
     const int64_t total = a.rows[s] * kp4;
     const float* src = reinterpret_cast<const float*>(a.src[s]);
     const bf16* src16 = reinterpret_cast<const bf16*>(a.src[s]);
+    const bool packed = s == 0 && a.v_nfeats != nullptr;
     for (int64_t e = tid; e < total; e += nth) {
       const int64_t r = e / kp4;
       const int c = (int)(e - r * kp4) * 4;
+      int64_t rs = r;                                  // source row; < 0: a row past the sample's clips (all zero)
+      if (packed) {
+        const int b = (int)(r / a.T), t = (int)(r - (int64_t)b * a.T);
+        rs = t < s_rowoff[b + 1] - s_rowoff[b] ? (int64_t)s_rowoff[b] + t : -1;
+      }
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (SRC16) {                                     // half-width host features (k % 4 == 0: 8-byte aligned groups)
-        if (c + 3 < k) v = ld4(src16 + r * k + c);
+      if (rs < 0) {
+      } else if (SRC16) {                              // half-width host features (k % 4 == 0: 8-byte aligned groups)
+        if (c + 3 < k) v = ld4(src16 + rs * k + c);
         else {
-          if (c < k) v.x = to_f(src16[r * k + c]);
-          if (c + 1 < k) v.y = to_f(src16[r * k + c + 1]);
-          if (c + 2 < k) v.z = to_f(src16[r * k + c + 2]);
+          if (c < k) v.x = to_f(src16[rs * k + c]);
+          if (c + 1 < k) v.y = to_f(src16[rs * k + c + 1]);
+          if (c + 2 < k) v.z = to_f(src16[rs * k + c + 2]);
         }
-      } else if (c + 3 < k) v = __ldg(reinterpret_cast<const float4*>(src + r * k + c));
+      } else if (c + 3 < k) v = __ldg(reinterpret_cast<const float4*>(src + rs * k + c));
       else {
-        if (c < k) v.x = src[r * k + c];
-        if (c + 1 < k) v.y = src[r * k + c + 1];
-        if (c + 2 < k) v.z = src[r * k + c + 2];
+        if (c < k) v.x = src[rs * k + c];
+        if (c + 1 < k) v.y = src[rs * k + c + 1];
+        if (c + 2 < k) v.z = src[rs * k + c + 2];
       }
       if (BF16) st4(reinterpret_cast<bf16*>(a.dst[s]) + r * a.kpad[s] + c, v);
       else st4(reinterpret_cast<float*>(a.dst[s]) + r * a.kpad[s] + c, v);
@@ -217,8 +245,8 @@ ingest_kernel(IngestArgs a) {
     }
 }
 
-int ingest(const void* vf, const void* qf, int src_bf16, const uint8_t* vmask, const uint8_t* qmask, const uint8_t* lmask,
-           const uint8_t* mmask, const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
+int ingest(const void* vf, const void* qf, int src_bf16, const int64_t* v_nfeats, const uint8_t* vmask, const uint8_t* qmask,
+           const uint8_t* lmask, const uint8_t* mmask, const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
            uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad,
            int q_kpad, int prec, cudaStream_t st) {
   VML_CHECK_ARG(B > 0 && d.d0 % 4 == 0 && v_kpad % 4 == 0 && q_kpad % 4 == 0 && v_kpad >= d.d0 && q_kpad >= 300);
@@ -234,15 +262,18 @@ int ingest(const void* vf, const void* qf, int src_bf16, const uint8_t* vmask, c
   a.mbytes[3] = (int64_t)B * d.L * d.L;
   a.sm_src = sm; a.sm_dst = sm ? sm_out : nullptr; a.sm_n = (int64_t)B * d.L * d.L;
   a.qmask = qmask; a.qlen = qlen; a.B = B; a.Nq = d.Nq;
+  a.v_nfeats = v_nfeats; a.T = d.T;
+  VML_CHECK_ARG(v_nfeats == nullptr || (B <= INGEST_MAXB && v_out != nullptr));
+  const size_t smem = v_nfeats ? sizeof(int32_t) * (size_t)(B + 1) : 0;
   const int64_t total = (v_out ? a.rows[0] * (v_kpad / 4) : 0) + (q_out ? a.rows[1] * (q_kpad / 4) : 0) + a.mbytes[3];
   const int64_t want = ceil_div64(total, 256 * 4), cap = (int64_t)kNumSMs * 8;
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
   if (prec == VML_BF16) {
-    if (src_bf16) ingest_kernel<true, true><<<grid, 256, 0, st>>>(a);
-    else ingest_kernel<true, false><<<grid, 256, 0, st>>>(a);
+    if (src_bf16) ingest_kernel<true, true><<<grid, 256, smem, st>>>(a);
+    else ingest_kernel<true, false><<<grid, 256, smem, st>>>(a);
   } else {
-    if (src_bf16) ingest_kernel<false, true><<<grid, 256, 0, st>>>(a);
-    else ingest_kernel<false, false><<<grid, 256, 0, st>>>(a);
+    if (src_bf16) ingest_kernel<false, true><<<grid, 256, smem, st>>>(a);
+    else ingest_kernel<false, false><<<grid, 256, smem, st>>>(a);
   }
   VML_LAUNCHED(1);
   return VML_OK;

@@ -45,6 +45,7 @@ _SIGS = {
     "vml_cast_pad_bf16": [_P, _P, _I64, _I, _I, _P],
     "vml_ingest": [_P] * 15 + [_I, Dims, _I, _I, _I, _P],
     "vml_ingest_bf16": [_P] * 15 + [_I, Dims, _I, _I, _I, _P],
+    "vml_ingest_packed": [_P] * 16 + [_I, Dims, _I, _I, _I, _I, _P],
     "vml_gemm_strided": [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, C.c_float, _I, _I,
                          _P, _I, _P, _I, _P],
     "vml_linear": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P],

@@ -28,18 +28,45 @@ INPUT_KEYS = ("video_features", "video_mask", "query_features", "query_mask", "l
 # compact batches: the masks and the IoU map are generated on the device (vml_make_labels, dataset.py:95-110,139-149) from
 # the annotation scalars -- only the features, the word mask and three scalars per sample cross PCIe
 COMPACT_KEYS = ("video_features", "query_features", "query_mask", "times", "duration", "nfeats")
+# packed batches: compact, and ``video_features`` holds only each sample's first ``nfeats`` rows back to back ([rows, d0]) --
+# the all-zero rows get_fixed_length_features pads with (dataset.py:69-73) do not cross PCIe.  The variable-size tensor is
+# the last one of the blob, so every other offset is the same for every batch.
+PACKED_KEYS = ("query_features", "query_mask", "times", "duration", "nfeats", "video_features")
 
 
 def _is_compact(batch) -> bool:
     return "times" in batch and "sm" not in batch
 
 
+def _is_packed(batch) -> bool:
+    return bool(batch.get("_packed", False))
+
+
 def _keys_of(batch):
-    return COMPACT_KEYS if _is_compact(batch) else INPUT_KEYS
+    return PACKED_KEYS if _is_packed(batch) else COMPACT_KEYS if _is_compact(batch) else INPUT_KEYS
+
+
+def pack_video_rows(video_features: torch.Tensor, nfeats: torch.Tensor) -> torch.Tensor:
+    """[B, T, d0] -> [sum_b min(nfeats[b], T), d0]: the rows that are not padding, back to back."""
+    B, T, _ = video_features.shape
+    nf = nfeats.to(torch.int64).clamp(0, T).tolist()
+    return torch.cat([video_features[b, : nf[b]] for b in range(B)], dim=0) if B else video_features.reshape(0, video_features.shape[-1])
+
+
+def unpack_video_rows(rows: torch.Tensor, nfeats: torch.Tensor, T: int) -> torch.Tensor:
+    """Inverse of ``pack_video_rows`` (padding rows are zero, as dataset.py:69-73 makes them)."""
+    nf = nfeats.to(torch.int64).clamp(0, T)
+    B, total = nf.numel(), int(nf.sum().item())
+    out = rows.new_zeros(B, T, rows.shape[1])
+    b_idx = torch.repeat_interleave(torch.arange(B, device=rows.device), nf.to(rows.device))
+    first = (torch.cumsum(nf, 0) - nf).to(rows.device)
+    t_idx = torch.arange(total, device=rows.device) - first[b_idx]
+    out[b_idx, t_idx] = rows[:total]
+    return out
 
 
 def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torch.dtype] = None,
-                    compact: bool = False) -> Dict[str, torch.Tensor]:
+                    compact: bool = False, packed: bool = False) -> Dict[str, torch.Tensor]:
     """Re-lay one batch (dict with INPUT_KEYS) as views into ONE pinned host blob (key ``"_blob"``), so that
     ``ScoringPipeline.submit(..., from_host=True)`` moves it with a single H2D copy.  (A collate function
     can write straight into such a blob; the layout is the INPUT_KEYS order, each tensor 256-byte aligned.)
@@ -47,8 +74,13 @@ def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torc
     in bf16 precision the scores are bit-identical, the rounding just happens before the copy instead of after).
     ``compact=True`` keeps only COMPACT_KEYS (``times`` [B,2] / ``duration`` [B] as float64, ``nfeats`` [B] int64, as
     ``synth.make_batch`` and the dataset's annotations provide them): ``ScoringPipeline`` then builds the video / length /
-    moment masks and the IoU map ``sm`` on the device, bit-identical to the host-built ones (GPU test)."""
-    keys = COMPACT_KEYS if compact else INPUT_KEYS
+    moment masks and the IoU map ``sm`` on the device, bit-identical to the host-built ones (GPU test).
+    ``packed=True`` (implies compact): the clip features travel without their all-zero padding rows (``PACKED_KEYS``; the
+    blob is as long as the batch's videos are) and ``vml_ingest_packed`` re-creates the padding on the device --
+    bit-identical operands, ``mean(nfeats) / T`` of the bytes."""
+    compact = compact or packed
+    keys = PACKED_KEYS if packed else COMPACT_KEYS if compact else INPUT_KEYS
+    B_, T_ = batch["video_features"].shape[0], batch["video_features"].shape[1]
     if compact:
         batch = {"video_features": batch["video_features"], "query_features": batch["query_features"],
                  "query_mask": batch["query_mask"], "times": batch["times"].to(torch.float64),
@@ -57,12 +89,20 @@ def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torc
         batch = dict(batch)
         for k in ("video_features", "query_features"):
             batch[k] = batch[k].to(feature_dtype)
+    if packed:
+        batch = dict(batch)
+        d0_ = batch["video_features"].shape[-1]
+        batch["video_features"] = pack_video_rows(batch["video_features"], batch["nfeats"])
     offs, total = {}, 0
     for k in keys:
         offs[k] = total
         total += (batch[k].numel() * batch[k].element_size() + 255) // 256 * 256
     blob = torch.empty(total, dtype=torch.uint8).pin_memory()
     out = {"_blob": blob}
+    if packed:      # what a staging area must hold for ANY batch of this shape: every sample at full length
+        out["_packed"] = True
+        out["_rows_max"] = B_ * T_
+        out["_full_bytes"] = offs["video_features"] + (B_ * T_ * d0_ * batch["video_features"].element_size() + 255) // 256 * 256
     for k in keys:
         t = batch[k].contiguous()
         nbytes = t.numel() * t.element_size()
@@ -76,8 +116,11 @@ def _blob_views(blob: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str, 
     out, total = {}, 0
     for k in _keys_of(like):
         t = like[k]
-        nbytes = t.numel() * t.element_size()
-        out[k] = blob[total: total + nbytes].view(t.dtype).view(t.shape)
+        shape = (like["_rows_max"], t.shape[1]) if (k == "video_features" and _is_packed(like)) else tuple(t.shape)
+        nbytes = t.element_size()
+        for n in shape:
+            nbytes *= n
+        out[k] = blob[total: total + nbytes].view(t.dtype).view(shape)
         total += (nbytes + 255) // 256 * 256
     return out
 
@@ -120,6 +163,7 @@ class _Staging:
         self.src_ptrs = None                   # device pointers of the 7 views, in vml_ingest argument order
         self.labels: Optional[Dict[str, torch.Tensor]] = None     # compact batches: device-built masks + sm of this area
         self.label_args = None
+        self.packed = False                    # the area receives packed batches (video rows without padding, last in the blob)
 
 
 # canonical dtypes of a collated batch (dataset.py:165-176); anything else takes the generic (converting) path
@@ -134,8 +178,9 @@ class _Plan:
 
     def __init__(self, inp: dict, stream_ptr: int):
         a = inp["_ingest_args"]
-        self.tail = tuple(a[7:-1]) + (stream_ptr,)
+        self.tail = tuple(a[inp["_ingest_nsrc"]:-1]) + (stream_ptr,)
         self.fn_name = inp["_ingest_fn"]
+        self.tag = None                        # _canonical() of the batch the launch was recorded for
         self.fn = getattr(L_.load(), self.fn_name)
         self.inp = inp
         self.ev = torch.cuda.Event()
@@ -151,6 +196,10 @@ def _canonical(batch: Dict[str, torch.Tensor]):
         want = torch.bfloat16 if (f16 and k in ("video_features", "query_features")) else dt
         if t.dtype is not want or not t.is_contiguous():
             return None
+    if _is_packed(batch):
+        if batch["nfeats"].dtype is not torch.int64 or batch["video_features"].dim() != 2:
+            return None
+        return "vml_ingest_packed:bf16" if f16 else "vml_ingest_packed:f32"
     return "vml_ingest_bf16" if f16 else "vml_ingest"
 
 
@@ -243,7 +292,10 @@ class ScoringPipeline:
         batch's hit counters (async D2H after its pass).  Returns a Ticket; after
         ``ticket.synchronize()``, ``ticket.slot.outputs`` holds the pass's (pm, ps, pe, pa) and top-k
         records (rows ``ticket.index * B ...`` belong to this batch) until the slot is reused."""
-        B = batch["video_features"].shape[0]
+        B = batch["query_features"].shape[0]
+        if _is_packed(batch) and not from_host:       # device-resident packed batch: nothing to save, re-pad it
+            batch = {**{k: batch[k] for k in COMPACT_KEYS},
+                     "video_features": unpack_video_rows(batch["video_features"], batch["nfeats"], self.dims.T)}
         if _is_compact(batch) and not from_host:      # device-resident compact batch: build the masks + sm, then as usual
             from .labels import make_labels
             lab = make_labels(batch["times"], batch["duration"], batch["nfeats"], self.dims.T, self.dims.L)
@@ -262,23 +314,28 @@ class ScoringPipeline:
                     self._pk = pk
                     self.invalidate()
         plan = self._plans.get((self._cur, slot.fill))
-        fast = plan is not None and _canonical(batch) == plan.fn_name
+        fast = plan is not None and _canonical(batch) == plan.tag
         stg = None
         if from_host:
             stg = self.staging[self._next_staging]
             self._next_staging = (self._next_staging + 1) % len(self.staging)
             blob = batch.get("_blob")
-            if stg.buf is None or (blob is not None and (stg.blob is None or stg.blob.numel() != blob.numel())):
+            packed = _is_packed(batch)
+            need = batch["_full_bytes"] if packed else (blob.numel() if blob is not None else 0)
+            if packed and blob is None:
+                raise L_.VmlError("packed batches travel as one pinned blob: make them with pack_host_batch(..., packed=True)")
+            if stg.buf is None or stg.packed != packed or (blob is not None and (stg.blob is None or stg.blob.numel() != need)):
                 if stg.buf is not None:                       # layout change mid-run (rare): let the old area drain first
                     torch.cuda.synchronize(self.device)
+                stg.packed, stg.label_args, stg.labels = packed, None, None
                 if blob is not None:                          # one device blob mirroring the host blob: one copy per batch
-                    stg.blob = torch.empty(blob.numel(), dtype=torch.uint8, device=self.device)
+                    stg.blob = torch.empty(need, dtype=torch.uint8, device=self.device)
                     stg.buf = _blob_views(stg.blob, batch)
                 else:
                     stg.buf = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device) for k in _keys_of(batch)}
                 if _is_compact(batch):
                     self._attach_label_buffers(stg, B)
-                stg.src_ptrs = tuple(stg.buf[k].data_ptr() for k in _INGEST_ORDER)
+                stg.src_ptrs = tuple(stg.buf[k].data_ptr() for k in _INGEST_ORDER + (("nfeats",) if packed else ()))
             if stg.used:
                 self.copy_stream.wait_event(stg.free)         # the previous consumer's ingest has read it
             if blob is not None and stg.blob is not None:
@@ -322,12 +379,15 @@ class ScoringPipeline:
                     slot.stream.wait_event(ev)               # the caller's tensors are ready
                 with torch.cuda.stream(slot.stream):
                     slot.inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True,
-                                           b_off=slot.fill * B, b_total=self.coalesce * B)
+                                           b_off=slot.fill * B, b_total=self.coalesce * B,
+                                           nfeats=src["nfeats"] if (from_host and stg.packed) else None)
                 if not from_host:
                     for k in INPUT_KEYS:
                         src[k].record_stream(slot.stream)
-            if _canonical(src) is not None:
-                self._plans[(self._cur, slot.fill)] = _Plan(slot.inp, slot.stream.cuda_stream)
+            tag = _canonical(batch if from_host else src)
+            if tag is not None:
+                self._plans[(self._cur, slot.fill)] = plan = _Plan(slot.inp, slot.stream.cuda_stream)
+                plan.tag = tag
         if from_host:
             stg.free.record(slot.stream)
             stg.used = True
@@ -353,6 +413,8 @@ class ScoringPipeline:
             caller.wait_event(ev)
         with torch.no_grad():
             dev = {k: (batch[k].to(self.device, non_blocking=True) if not batch[k].is_cuda else batch[k]) for k in _keys_of(batch)}
+            if _is_packed(batch):
+                dev["video_features"] = unpack_video_rows(dev["video_features"], dev["nfeats"], self.dims.T)
             if _is_compact(batch):
                 from .labels import make_labels
                 dev.update(make_labels(dev["times"], dev["duration"], dev["nfeats"], self.dims.T, self.dims.L))

@@ -283,14 +283,16 @@ def _mask_u8(t, shape):
 
 
 def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask, query_features, query_mask, length_mask,
-                moment_mask, sm=None, static: bool = False, b_off: int = 0, b_total: Optional[int] = None):
+                moment_mask, sm=None, static: bool = False, b_off: int = 0, b_total: Optional[int] = None, nfeats=None):
     """Take the caller's ``forward`` arguments into library-owned operand buffers with ONE launch
     (``vml_ingest``): bf16 zero-padded feature rows (fast mode), query lengths, and -- when
     ``static`` (CUDA-graph replay of the rest of the step) -- copies of the masks / fp32 features /
     ``sm`` so that nothing downstream reads caller memory.  ``b_off`` / ``b_total`` (static mode):
     this call fills samples [b_off, b_off + B) of operand buffers sized for ``b_total`` samples, so
-    several submitted batches can be scored by one pass (samples are independent)."""
-    B = video_features.shape[0]
+    several submitted batches can be scored by one pass (samples are independent).  ``nfeats`` (device int64 [B]):
+    ``video_features`` is the PACKED form [sum_b min(nfeats[b], T), d0] -- only the rows that are not all-zero padding
+    (``vml_ingest_packed``; needs operand buffers, i.e. bf16 precision or ``static``)."""
+    B = query_features.shape[0]
     Bt = B if b_total is None else b_total
     assert static or (b_off == 0 and Bt == B)
     T, Lm, d0, Nq = dims.T, dims.L, dims.d0, dims.Nq
@@ -322,10 +324,19 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
     def at(t):                      # device pointer of sample b_off inside a [Bt, ...] operand buffer
         return None if t is None else t.data_ptr() + b_off * (t.numel() // Bt) * t.element_size()
 
-    args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
-            *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, stream_ptr())
-    call("vml_ingest_bf16" if src16 else "vml_ingest", *args)
-    inp["_ingest_fn"] = "vml_ingest_bf16" if src16 else "vml_ingest"
+    if nfeats is not None:
+        if v_out is None or nfeats.dtype != torch.int64 or not nfeats.is_contiguous() or vf.dim() != 2:
+            raise L_.VmlError("packed clip features need int64 nfeats, a 2-D row matrix and bf16 precision or static operands")
+        args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), ptr(nfeats), at(v_out), at(q_out),
+                *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, 1 if src16 else 0, stream_ptr())
+        fn = "vml_ingest_packed"
+    else:
+        args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
+                *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, stream_ptr())
+        fn = "vml_ingest_bf16" if src16 else "vml_ingest"
+    call(fn, *args)
+    inp["_ingest_fn"] = fn
+    inp["_ingest_nsrc"] = 8 if nfeats is not None else 7    # leading source pointers of the launch (replaced per step by the pipeline)
     inp["_ingest_args"] = args          # ScoringPipeline re-issues this launch with new source pointers (its per-step fast path)
     if v_out is None and src16:          # fp32 mode, eager call: the operands are the caller's tensors themselves
         vf, qf = vf.float(), qf.float()
