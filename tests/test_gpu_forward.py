@@ -209,3 +209,29 @@ def test_one_kernel_content_unit_against_split(name, B, rng, variant, monkeypatc
             assert (a - b_).abs().max().item() < 2e-3      # sigmoid outputs: a few 1e-4 apart at most
     for a, f in zip(prod, out_f):
         assert torch.equal(a, f)                           # keep-mode (serial) == production (overlapped, skipped store)
+
+
+@pytest.mark.parametrize("name,prec,B,kw", [("charadessta", "bf16", 9, {}), ("charadessta", "bf16", 6, {"nfeats_range": (1, 9)}),
+                                            ("charadessta", "bf16", 5, {"full_length": True}), ("tacos", "bf16", 4, {}),
+                                            ("charadessta", "fp32", 4, {}), ("tiny", "bf16", 5, {})])
+def test_boundary_schedules_are_bit_identical(name, prec, B, kw, monkeypatch):
+    """The boundary unit's two schedule knobs change WHEN things are loaded, never what is computed: rows staged by
+    cp.async.bulk (default) vs through registers, and the per-sample streaming kernel (default for L <= 16 in fast mode) vs
+    the warp-per-row kernel.  Scores must agree bit for bit in every combination (the launchers read the knobs per call)."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    p, dims = L_.PREC[prec], dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, p, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 4242, **kw))
+    outs = []
+    for gate_bulk in ("1", "0"):
+        for stream_sample in ("1", "0"):
+            monkeypatch.setenv("VML_GATE_BULK", gate_bulk)
+            monkeypatch.setenv("VML_STREAM_SAMPLE", stream_sample)
+            keep = {}
+            out = smin_forward(pk, dims, p, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+            torch.cuda.synchronize()
+            outs.append([o.clone() for o in out] + [keep[f"fb{cfg.layers}"].clone(), keep[f"fm{cfg.layers}"].clone()])
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)

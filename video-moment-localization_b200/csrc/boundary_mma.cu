@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace vml {
 
@@ -342,7 +343,8 @@ __global__ void __launch_bounds__(BMM_THREADS)
 boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
                           const float* __restrict__ fs, const float* __restrict__ fb, const uint8_t* __restrict__ qmask,
                           const uint8_t* __restrict__ lmask, float* __restrict__ G, float* __restrict__ prob_out,
-                          float* __restrict__ u_out, float* __restrict__ bu, float* __restrict__ ab_out, int L, int Nq, int D) {
+                          float* __restrict__ u_out, float* __restrict__ bu, float* __restrict__ ab_out, int L, int Nq, int D,
+                          int bulk_stage) {
   extern __shared__ __align__(16) float sg[];
   const int DS = D + 4;
   float* Ks = sg;                                     // [Nq][DS]  kbt          (later: G rows, [16][DS])
@@ -354,7 +356,33 @@ boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
   const int dq = D / 4;
-  // staging: 12 independent 16-byte loads in flight per thread before the first shared-memory store (the unit is
+  // staging, default: the copy engine moves the sample's rows (one cp.async.bulk per 2 KB row into the padded layout, issued
+  // by warp 0, counted on one mbarrier).  Through registers the staging was ~15 k of the 36 k warp instructions a sample
+  // costs (5.4 k LDG.128 + 5.4 k STS.128 + addressing; ncu source page, profiles/r02_boundary_gate_rows_hotspots.txt) in a
+  // kernel running at IPC ~2 of 4.
+  __shared__ __align__(8) uint64_t stage_bar;
+  if (bulk_stage) {
+    if (tid == 0) { ptx::mbar_init(&stage_bar, 1); ptx::fence_barrier_init(); }
+    __syncthreads();
+    const int nx = min(L, BMM_ROWS);
+    if (warp == 0) {
+      if (lane == 0) ptx::mbar_arrive_expect_tx(&stage_bar, (uint32_t)((2 * Nq + nx) * D) * 4u);
+      __syncwarp();
+      const uint32_t rb = (uint32_t)D * 4u;
+      for (int r = lane; r < 2 * Nq + nx; r += 32) {
+        if (r < Nq) ptx::bulk_load_1d(Ks + (size_t)r * DS, qproj + ((size_t)b * Nq + r) * ld + off_kbt, rb, &stage_bar);
+        else if (r < 2 * Nq) ptx::bulk_load_1d(Ws + (size_t)(r - Nq) * DS, fw + ((size_t)b * Nq + (r - Nq)) * D, rb, &stage_bar);
+        else ptx::bulk_load_1d(Xs + (size_t)(r - 2 * Nq) * DS, fb + ((size_t)b * L + (r - 2 * Nq)) * D, rb, &stage_bar);
+      }
+    } else {
+      for (int e = tid - 32; e < (BMM_ROWS - nx) * dq; e += BMM_THREADS - 32) {      // map rows past L: zero
+        const int rr = nx + e / dq, c4 = (e % dq) * 4;
+        *reinterpret_cast<float4*>(Xs + (size_t)rr * DS + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    ptx::mbar_wait(&stage_bar, 0);
+  } else
+  // staging through registers: 12 independent 16-byte loads in flight per thread before the first shared-memory store (the unit is
   // latency-bound: one load per iteration meant ~20 dependent trips to L2 / HBM per CTA).  A thread keeps ONE column chunk
   // and walks rows (BMM_THREADS / dq rows per sweep): no per-element division by the run-time row length.
   if (BMM_THREADS % dq == 0) {
@@ -713,6 +741,101 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
     }
 }
 
+// ---- stream, one CTA per SAMPLE (fast mode, L <= 16, D = 256 * {1, 2}) ------------------------------------------------
+// Same arithmetic in the same order as boundary_stream_kernel (bit-identical fbar and bu), different schedule.  There a
+// warp owns one map row of ~5 cells and pays the dependent chain row_start -> cell code -> A_b[i, j] for it; here the
+// sample's attention rows, row offsets and cell codes are staged in shared memory once per CTA (two round trips for up to
+// 136 cells x 1 KB), a warp owns the row PAIR (p, L - 1 - p) of one 256-column group -- L + 1 cells for a full-length
+// video whatever p is -- and streams them four at a time with the weights read from shared memory.
+constexpr int BSS_L = 16, BSS_CB = 4;
+
+__global__ void __launch_bounds__(512, 2)
+boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const bf16* __restrict__ fm,
+                              const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
+                              bf16* __restrict__ fbar, const float* __restrict__ fbar_bias, int L, int D, int capacity) {
+  __shared__ float s_ab[BSS_L * BSS_L];
+  __shared__ int s_rs[BSS_L + 1];
+  __shared__ int s_j[BSS_L * BSS_L];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int ng = D / 256, g = warp % ng, p = warp / ng;          // column group, row pair
+  if (tid <= L) s_rs[tid] = min(__ldg(row_start + (size_t)b * L + tid), capacity);
+  for (int e = tid; e < L * L; e += blockDim.x) s_ab[e] = __ldg(ab + (size_t)b * L * L + e);
+  const int col = g * 256 + lane * 8;
+  const f8 s8 = ld8(fs + (size_t)b * D + col);
+  __shared__ __align__(16) float s_bias[512];                   // the stored fbar's bias (kept out of the registers: 64 per thread)
+  for (int e = tid; e < D; e += blockDim.x) s_bias[e] = fbar_bias ? __ldg(fbar_bias + e) : 0.f;
+  __syncthreads();
+  const int n0 = s_rs[0], ncell = min(s_rs[L] - n0, BSS_L * BSS_L);
+  const int row0 = p, row1 = L - 1 - p;
+  const bool active = row0 <= row1;
+  const int lo0 = active ? s_rs[row0] : 0, cnt0 = active ? s_rs[row0 + 1] - lo0 : 0;
+  const int lo1 = (active && row1 != row0) ? s_rs[row1] : 0, cnt1 = (active && row1 != row0) ? s_rs[row1 + 1] - lo1 : 0;
+  const int total = cnt0 + cnt1;
+  auto cell_of = [&](int q) { q = min(q, total - 1); return q < cnt0 ? lo0 + q : lo1 + (q - cnt0); };
+  // the first batch of map loads goes out before the cell codes have landed
+  uint4 m[BSS_CB];
+  if (total > 0) {
+#pragma unroll
+    for (int u = 0; u < BSS_CB; ++u) m[u] = __ldg(reinterpret_cast<const uint4*>(fm + (size_t)cell_of(u) * D + col));
+  }
+  for (int e = tid; e < ncell; e += blockDim.x) s_j[e] = __ldg(code + n0 + e) & 0xff;
+  __syncthreads();
+  if (total <= 0) return;
+  VML_DBG_ASSERT(lo0 >= n0 && lo0 + cnt0 <= n0 + ncell && (cnt1 == 0 || (lo1 >= n0 && lo1 + cnt1 <= n0 + ncell)));
+  float bm0[8], bm1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { bm0[e] = 0.f; bm1[e] = 0.f; }
+  for (int q0 = 0; q0 < total; q0 += BSS_CB) {
+    if (q0 > 0) {
+#pragma unroll
+      for (int u = 0; u < BSS_CB; ++u) m[u] = __ldg(reinterpret_cast<const uint4*>(fm + (size_t)cell_of(q0 + u) * D + col));
+    }
+#pragma unroll
+    for (int u = 0; u < BSS_CB; ++u) {
+      const int q = q0 + u;
+      if (q < total) {                                   // warp-uniform
+        const bool second = q >= cnt0;
+        const int n = second ? lo1 + (q - cnt0) : lo0 + q;
+        const float a = s_ab[(second ? row1 : row0) * L + s_j[n - n0]];
+        const f8 x8 = unpack8(m[u]);
+        f8 gv;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = x8.v[e], z = x * s8.v[e];
+          gv.v[e] = __fdividef(x, 1.0f + __expf(-z));
+        }
+        if (second) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bm1[e] = fmaf(a, gv.v[e], bm1[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bm0[e] = fmaf(a, gv.v[e], bm0[e]);
+        }
+        if (fbar) {
+          const f8 fb8 = ld8(s_bias + col);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gv.v[e] += fb8.v[e];
+          st8(fbar + (size_t)n * D + col, gv);
+        }
+      }
+    }
+  }
+  if (cnt0 > 0) {
+    float* o = bu + ((size_t)b * L + row0) * D + col;
+    f8 tot = ld8(o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tot.v[e] = tot.v[e] + bm0[e];
+    st8(o, tot);
+  }
+  if (cnt1 > 0) {
+    float* o = bu + ((size_t)b * L + row1) * D + col;
+    f8 tot = ld8(o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tot.v[e] = tot.v[e] + bm1[e];
+    st8(o, tot);
+  }
+}
+
 template <bool PRECISE>
 static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, float* bu, float* ab, int B, vml_dims_t d,
                        cudaStream_t st) {
@@ -752,12 +875,17 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
     static bool reg2 = (register_kernel("boundary_gate_rows_kernel"), true); (void)reg2;
     const int rows_kw = 2 * d.Nq > BMM_ROWS ? 2 * d.Nq : BMM_ROWS;
     const size_t smem_f = sizeof(float) * (size_t)(rows_kw + BMM_ROWS) * (d.D + 4);
+    // rows moved by cp.async.bulk need 16-byte aligned sources (A/B knob: VML_GATE_BULK=0 stages through registers)
+    const char* gb_env = getenv("VML_GATE_BULK");
+    const bool bulk_env = gb_env == nullptr || atoi(gb_env) != 0;
+    const int bulk = bulk_env && d.D % 4 == 0 && ((reinterpret_cast<uintptr_t>(qproj) | reinterpret_cast<uintptr_t>(fw) |
+                                                   reinterpret_cast<uintptr_t>(fb)) & 15) == 0;
     if (prec == VML_FP32) {
       VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<true>), (size_t)((int)smem_f)));
-      boundary_gate_rows_kernel<true><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D);
+      boundary_gate_rows_kernel<true><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D, bulk);
     } else {
       VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<false>), (size_t)((int)smem_f)));
-      boundary_gate_rows_kernel<false><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D);
+      boundary_gate_rows_kernel<false><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D, bulk);
     }
     n_launched = 2;
   } else {
@@ -775,6 +903,15 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   if (rc) return rc;
   }
   const int ng = ceil_div(d.D, 256);
+  // fast mode, small maps: one CTA per sample (A/B knob: VML_STREAM_SAMPLE=0 selects the warp-per-row kernel)
+  const char* ss_env = getenv("VML_STREAM_SAMPLE");
+  if (prec != VML_FP32 && d.L <= BSS_L && d.D % 256 == 0 && d.D <= 512 && (ss_env == nullptr || atoi(ss_env) != 0)) {
+    static bool reg3 = (register_kernel("boundary_stream_sample_kernel"), true); (void)reg3;
+    boundary_stream_sample_kernel<<<B, 8 * 32 * (d.D / 256), 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
+                                                                (bf16*)fbar, fbar_bias, d.L, d.D, cells.capacity);
+    VML_LAUNCHED(n_launched);
+    return VML_OK;
+  }
   if (prec == VML_FP32) rc = ng <= 1 ? launch_stream<float, 1, true>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st)
                                      : launch_stream<float, 2, true>(ab_scratch, fs, fm, cells, bu, fbar, fbar_bias, B, d, st);
   else rc = (ng <= 1 || getenv("VML_STREAM_NG2") == nullptr)        // fast mode: one 256-column group per warp (A/B knob: both in one)
