@@ -34,13 +34,22 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 // d[16x8] += a[16x8] . b[8x8]; fragment layout of mma.m16n8k8 (g = lane/4, t = lane%4):
 //   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k=t, n=g)  b1 (k=t+4, n=g);  d0,d1 (g, 2t..2t+1)  d2,d3 (g+8, ..)
+// Fast mode (PRECISE = false): the fp32 bits go to the tensor core as they are -- mma.tf32 reads the upper 19 bits of each
+// operand register, i.e. the operands are TRUNCATED to tf32 (<= 2^-10 relative, against 2^-11 with round-to-nearest; the
+// unit's outputs are compared at 2e-2).  The six roundings per mma were 12 of the ~25 instructions per mma of these
+// latency-bound kernels (4 resident warps per scheduler, ~12 cycles per issued instruction).  VML_TF32_RNA restores them.
 template <bool PRECISE>
 __device__ __forceinline__ void mma_16x8x8(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
   uint32_t ah[4], bh[2];
+#if defined(VML_TF32_RNA)
+  constexpr bool kRound = true;
+#else
+  constexpr bool kRound = PRECISE;
+#endif
 #pragma unroll
-  for (int e = 0; e < 4; ++e) ah[e] = f2tf32(a[e]);
+  for (int e = 0; e < 4; ++e) ah[e] = kRound ? f2tf32(a[e]) : __float_as_uint(a[e]);
 #pragma unroll
-  for (int e = 0; e < 2; ++e) bh[e] = f2tf32(b[e]);
+  for (int e = 0; e < 2; ++e) bh[e] = kRound ? f2tf32(b[e]) : __float_as_uint(b[e]);
   if (PRECISE) {
     uint32_t al[4], bl[2];
 #pragma unroll
@@ -338,13 +347,14 @@ boundary_rows_mma_kernel(const float* __restrict__ G, const float* __restrict__ 
 // warps per SM instead of 16, a third less shared memory -- runs in the same 54 us per 640 samples as this version; so does
 // the version before the cheaper tf32 rounding below at +25 % instructions.  The kernel's time is the chain of eight
 // barrier-separated phases per sample times 2.2 waves of CTAs, not issue slots or bytes.)
-template <bool PRECISE>
+template <bool PRECISE, int DT /* D at compile time (loops unroll, shared-memory offsets become immediates); 0 = run time */>
 __global__ void __launch_bounds__(BMM_THREADS)
 boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
                           const float* __restrict__ fs, const float* __restrict__ fb, const uint8_t* __restrict__ qmask,
                           const uint8_t* __restrict__ lmask, float* __restrict__ G, float* __restrict__ prob_out,
-                          float* __restrict__ u_out, float* __restrict__ bu, float* __restrict__ ab_out, int L, int Nq, int D,
+                          float* __restrict__ u_out, float* __restrict__ bu, float* __restrict__ ab_out, int L, int Nq, int D_rt,
                           int bulk_stage) {
+  const int D = DT > 0 ? DT : D_rt;
   extern __shared__ __align__(16) float sg[];
   const int DS = D + 4;
   float* Ks = sg;                                     // [Nq][DS]  kbt          (later: G rows, [16][DS])
@@ -647,6 +657,23 @@ boundary_gate_rows_kernel(const float* __restrict__ qproj, int ld, int off_kbt, 
   }
 }
 
+// fbar gate of the fast mode for two adjacent columns: x * sigmoid(x * s) = x / (1 + 2^(x * ns)), ns = -s * log2(e) folded
+// once per (sample, column).  ex2.approx.ftz / rcp.approx.ftz straight (no denormal / range fix-ups: a huge 2^(.) gives
+// rcp(inf) = 0, a flushed one gives x itself) and the fp32 arithmetic as f32x2 instructions: 4.5 issue slots per element
+// where `__fdividef(x, 1.0f + __expf(-z))` took ~14 (the per-sample stream kernel ran at 57 % issue-slot utilisation with
+// 23 thread instructions per element, ncu).  Both stream kernels use it, so their outputs stay bit-identical.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void gate2_fast(float x0, float x1, float ns0, float ns1, float& g0, float& g1) {
+  float z0 = x0, z1 = x1;
+  ptx::mul2(z0, z1, ns0, ns1);
+  float e0 = ex2_ftz(z0), e1 = ex2_ftz(z1);
+  ptx::add2(e0, e1, 1.0f, 1.0f);
+  g0 = rcp_ftz(e0); g1 = rcp_ftz(e1);
+  ptx::mul2(g0, g1, x0, x1);
+}
+constexpr float kNegLog2e = -1.4426950408889634f;
+
 // ---- stream:  fbar_ij = sigmoid(fm_ij*fs)*fm_ij for every valid cell;  bu[i] += sum_j A_b[i,j] fbar_ij ----------------
 // One WARP per map row (b, i), four rows per CTA, no shared memory and no block barrier: a lane owns the 8
 // consecutive columns {256*q + 8*lane} of every cell (one 16-byte load per cell and column group in fast mode),
@@ -682,6 +709,10 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
     for (int e = 0; e < 8; ++e) { s8[q].v[e] = 0.f; bm[q].v[e] = 0.f; fb8[q].v[e] = 0.f; }
     if (q * 256 + lane * 8 < Dc) {
       s8[q] = ld8(fs + (size_t)b * ldD + q * 256 + lane * 8);
+      if (!PRECISE) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s8[q].v[e] *= kNegLog2e;     // fast mode: see gate2_fast
+      }
       if (fbar_bias) fb8[q] = ld8(fbar_bias + q * 256 + lane * 8);
     }
   }
@@ -714,15 +745,23 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
           for (int q = 0; q < NG; ++q)
             if (q * 256 + lane * 8 < Dc) {
               f8 gv;
+              if (PRECISE) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float x = m[u][q].v[e], z = x * s8[q].v[e];
-                gv.v[e] = PRECISE ? sigmoidf_(z) * x : __fdividef(x, 1.0f + __expf(-z));
-                bm[q].v[e] = fmaf(a, gv.v[e], bm[q].v[e]);
+                for (int e = 0; e < 8; ++e) {
+                  const float x = m[u][q].v[e], z = x * s8[q].v[e];
+                  gv.v[e] = sigmoidf_(z) * x;
+                  bm[q].v[e] = fmaf(a, gv.v[e], bm[q].v[e]);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  gate2_fast(m[u][q].v[e], m[u][q].v[e + 1], s8[q].v[e], s8[q].v[e + 1], gv.v[e], gv.v[e + 1]);
+                  ptx::fma2(bm[q].v[e], bm[q].v[e + 1], a, a, gv.v[e], gv.v[e + 1]);
+                }
               }
               if (fbar) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) gv.v[e] += fb8[q].v[e];
+                for (int e = 0; e < 8; e += 2) ptx::add2(gv.v[e], gv.v[e + 1], fb8[q].v[e], fb8[q].v[e + 1]);
                 st8(fbar + (size_t)(seg + c0 + u) * ldD + q * 256 + lane * 8, gv);
               }
             }
@@ -749,10 +788,11 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
 // video whatever p is -- and streams them four at a time with the weights read from shared memory.
 constexpr int BSS_L = 16, BSS_CB = 4;
 
-__global__ void __launch_bounds__(512, 2)
+template <int D /* 256 or 512 */>
+__global__ void __launch_bounds__(D, 1024 / D)
 boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const bf16* __restrict__ fm,
                               const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
-                              bf16* __restrict__ fbar, const float* __restrict__ fbar_bias, int L, int D, int capacity) {
+                              bf16* __restrict__ fbar, const float* __restrict__ fbar_bias, int L, int capacity) {
   __shared__ float s_ab[BSS_L * BSS_L];
   __shared__ int s_rs[BSS_L + 1];
   __shared__ int s_j[BSS_L * BSS_L];
@@ -761,8 +801,10 @@ boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restr
   if (tid <= L) s_rs[tid] = min(__ldg(row_start + (size_t)b * L + tid), capacity);
   for (int e = tid; e < L * L; e += blockDim.x) s_ab[e] = __ldg(ab + (size_t)b * L * L + e);
   const int col = g * 256 + lane * 8;
-  const f8 s8 = ld8(fs + (size_t)b * D + col);
-  __shared__ __align__(16) float s_bias[512];                   // the stored fbar's bias (kept out of the registers: 64 per thread)
+  f8 s8 = ld8(fs + (size_t)b * D + col);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s8.v[e] *= kNegLog2e;              // see gate2_fast
+  __shared__ __align__(16) float s_bias[D];                   // the stored fbar's bias (kept out of the registers: 64 per thread)
   for (int e = tid; e < D; e += blockDim.x) s_bias[e] = fbar_bias ? __ldg(fbar_bias + e) : 0.f;
   __syncthreads();
   const int n0 = s_rs[0], ncell = min(s_rs[L] - n0, BSS_L * BSS_L);
@@ -800,21 +842,18 @@ boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restr
         const f8 x8 = unpack8(m[u]);
         f8 gv;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float x = x8.v[e], z = x * s8.v[e];
-          gv.v[e] = __fdividef(x, 1.0f + __expf(-z));
-        }
+        for (int e = 0; e < 8; e += 2) gate2_fast(x8.v[e], x8.v[e + 1], s8.v[e], s8.v[e + 1], gv.v[e], gv.v[e + 1]);
         if (second) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) bm1[e] = fmaf(a, gv.v[e], bm1[e]);
+          for (int e = 0; e < 8; e += 2) ptx::fma2(bm1[e], bm1[e + 1], a, a, gv.v[e], gv.v[e + 1]);
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) bm0[e] = fmaf(a, gv.v[e], bm0[e]);
+          for (int e = 0; e < 8; e += 2) ptx::fma2(bm0[e], bm0[e + 1], a, a, gv.v[e], gv.v[e + 1]);
         }
         if (fbar) {
           const f8 fb8 = ld8(s_bias + col);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) gv.v[e] += fb8.v[e];
+          for (int e = 0; e < 8; e += 2) ptx::add2(gv.v[e], gv.v[e + 1], fb8.v[e], fb8.v[e + 1]);
           st8(fbar + (size_t)n * D + col, gv);
         }
       }
@@ -880,13 +919,17 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
     const bool bulk_env = gb_env == nullptr || atoi(gb_env) != 0;
     const int bulk = bulk_env && d.D % 4 == 0 && ((reinterpret_cast<uintptr_t>(qproj) | reinterpret_cast<uintptr_t>(fw) |
                                                    reinterpret_cast<uintptr_t>(fb)) & 15) == 0;
-    if (prec == VML_FP32) {
-      VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<true>), (size_t)((int)smem_f)));
-      boundary_gate_rows_kernel<true><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D, bulk);
-    } else {
-      VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<false>), (size_t)((int)smem_f)));
-      boundary_gate_rows_kernel<false><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D, bulk);
-    }
+#define VML_GR(P, DT)                                                                                                     \
+  do {                                                                                                                    \
+    VML_CUDA(ensure_dyn_smem((const void*)(boundary_gate_rows_kernel<P, DT>), (size_t)((int)smem_f)));                   \
+    boundary_gate_rows_kernel<P, DT><<<B, BMM_THREADS, smem_f, st>>>(qproj, ld, off_kbt, off_betab, fw, fs, fb, qmask, lmask, \
+                                                                    g_scratch, prob_out, u_out, bu, ab_scratch, d.L, d.Nq, d.D, bulk); \
+  } while (0)
+    const char* dt_env = getenv("VML_GATE_DT");                    // A/B knob: VML_GATE_DT=0 keeps D a run-time value
+    const bool dt512 = d.D == 512 && (dt_env == nullptr || atoi(dt_env) != 0);
+    if (prec == VML_FP32) { if (dt512) VML_GR(true, 512); else VML_GR(true, 0); }
+    else { if (dt512) VML_GR(false, 512); else VML_GR(false, 0); }
+#undef VML_GR
     n_launched = 2;
   } else {
   dim3 grid(ceil_div(d.L, BMM_ROWS), B);
@@ -905,10 +948,12 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   const int ng = ceil_div(d.D, 256);
   // fast mode, small maps: one CTA per sample (A/B knob: VML_STREAM_SAMPLE=0 selects the warp-per-row kernel)
   const char* ss_env = getenv("VML_STREAM_SAMPLE");
-  if (prec != VML_FP32 && d.L <= BSS_L && d.D % 256 == 0 && d.D <= 512 && (ss_env == nullptr || atoi(ss_env) != 0)) {
+  if (prec != VML_FP32 && d.L <= BSS_L && (d.D == 256 || d.D == 512) && (ss_env == nullptr || atoi(ss_env) != 0)) {
     static bool reg3 = (register_kernel("boundary_stream_sample_kernel"), true); (void)reg3;
-    boundary_stream_sample_kernel<<<B, 8 * 32 * (d.D / 256), 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
-                                                                (bf16*)fbar, fbar_bias, d.L, d.D, cells.capacity);
+    if (d.D == 512) boundary_stream_sample_kernel<512><<<B, 512, 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
+                                                                      (bf16*)fbar, fbar_bias, d.L, cells.capacity);
+    else boundary_stream_sample_kernel<256><<<B, 256, 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
+                                                           (bf16*)fbar, fbar_bias, d.L, cells.capacity);
     VML_LAUNCHED(n_launched);
     return VML_OK;
   }

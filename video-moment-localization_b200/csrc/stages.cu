@@ -175,12 +175,12 @@ struct IngestArgs {
 
 constexpr int INGEST_MAXB = 4096;                     // samples per packed ingest launch (row offsets live in shared memory)
 
-template <bool BF16, bool SRC16>
+template <bool BF16, bool SRC16, bool PACKED>
 __global__ void __launch_bounds__(256)
 ingest_kernel(IngestArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   extern __shared__ int32_t s_rowoff[];                // packed mode: [B + 1] first source row of every sample
-  if (a.v_nfeats) {
+  if (PACKED) {
     // exclusive scan of min(nfeats, T) by warp 0: every lane sums a contiguous chunk, the chunk totals are scanned by shuffle
     if (threadIdx.x < 32) {
       const int lane = threadIdx.x, per = (a.B + 31) / 32, lo = min(lane * per, a.B), hi = min(lo + per, a.B);
@@ -202,7 +202,7 @@ ingest_kernel(IngestArgs a) {
     const int64_t total = a.rows[s] * kp4;
     const float* src = reinterpret_cast<const float*>(a.src[s]);
     const bf16* src16 = reinterpret_cast<const bf16*>(a.src[s]);
-    const bool packed = s == 0 && a.v_nfeats != nullptr;
+    const bool packed = PACKED && s == 0;
     for (int64_t e = tid; e < total; e += nth) {
       const int64_t r = e / kp4;
       const int c = (int)(e - r * kp4) * 4;
@@ -268,12 +268,20 @@ int ingest(const void* vf, const void* qf, int src_bf16, const int64_t* v_nfeats
   const int64_t total = (v_out ? a.rows[0] * (v_kpad / 4) : 0) + (q_out ? a.rows[1] * (q_kpad / 4) : 0) + a.mbytes[3];
   const int64_t want = ceil_div64(total, 256 * 4), cap = (int64_t)kNumSMs * 8;
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-  if (prec == VML_BF16) {
-    if (src_bf16) ingest_kernel<true, true><<<grid, 256, smem, st>>>(a);
-    else ingest_kernel<true, false><<<grid, 256, smem, st>>>(a);
+  if (v_nfeats) {
+    if (prec == VML_BF16) {
+      if (src_bf16) ingest_kernel<true, true, true><<<grid, 256, smem, st>>>(a);
+      else ingest_kernel<true, false, true><<<grid, 256, smem, st>>>(a);
+    } else {
+      if (src_bf16) ingest_kernel<false, true, true><<<grid, 256, smem, st>>>(a);
+      else ingest_kernel<false, false, true><<<grid, 256, smem, st>>>(a);
+    }
+  } else if (prec == VML_BF16) {
+    if (src_bf16) ingest_kernel<true, true, false><<<grid, 256, 0, st>>>(a);
+    else ingest_kernel<true, false, false><<<grid, 256, 0, st>>>(a);
   } else {
-    if (src_bf16) ingest_kernel<false, true><<<grid, 256, smem, st>>>(a);
-    else ingest_kernel<false, false><<<grid, 256, smem, st>>>(a);
+    if (src_bf16) ingest_kernel<false, true, false><<<grid, 256, 0, st>>>(a);
+    else ingest_kernel<false, false, false><<<grid, 256, 0, st>>>(a);
   }
   VML_LAUNCHED(1);
   return VML_OK;
