@@ -215,23 +215,21 @@ def test_one_kernel_content_unit_against_split(name, B, rng, variant, monkeypatc
                                             ("charadessta", "bf16", 5, {"full_length": True}), ("tacos", "bf16", 4, {}),
                                             ("charadessta", "fp32", 4, {}), ("tiny", "bf16", 5, {})])
 def test_boundary_schedules_are_bit_identical(name, prec, B, kw, monkeypatch):
-    """The schedule knobs of the boundary unit and of the content unit's fbar fetch change WHEN things are loaded, never what
-    is computed: rows staged by cp.async.bulk (default) vs through registers, D as a compile-time constant, the per-sample
-    streaming kernel (default for L <= 16 in fast mode) vs the warp-per-row kernel, fbar prefetched into L2 / fetched one
-    column block ahead.  Scores must agree bit for bit in every combination (the launchers read the knobs per call)."""
+    """The schedule knobs of the boundary unit change WHEN things are loaded, never what is computed: rows staged by
+    cp.async.bulk (default) vs through registers, D as a compile-time constant, the per-sample streaming kernel (default
+    for L <= 16 in fast mode) vs the warp-per-row kernel.  Scores must agree bit for bit in every combination (the
+    launchers read the knobs per call)."""
     from vml_b200.smin import Workspace, pack_weights, smin_forward
     cfg = CONFIGS[name]
     p, dims = L_.PREC[prec], dims_of(cfg)
     pk = pack_weights(init_params(cfg, 43), dims, p, torch.device("cuda"))
     batch = to_dev(synth.make_batch(cfg, B, 4242, **kw))
     outs = []
-    for gate_bulk, gate_dt, stream_sample, cu_knobs in (("1", "1", "1", "3"), ("0", "1", "1", "0"), ("1", "0", "0", "1"), ("0", "0", "0", "2"),
-                                                         ("1", "1", "0", "3")):
+    for gate_bulk, gate_dt, stream_sample in (("1", "1", "1"), ("0", "1", "1"), ("1", "0", "0"), ("0", "0", "0"), ("1", "1", "0")):
         if True:
             monkeypatch.setenv("VML_GATE_BULK", gate_bulk)
             monkeypatch.setenv("VML_GATE_DT", gate_dt)              # D as a compile-time constant in the gate+rows kernel
             monkeypatch.setenv("VML_STREAM_SAMPLE", stream_sample)
-            monkeypatch.setenv("VML_CU_KNOBS", cu_knobs)            # content unit: fbar L2 prefetch (1) / fetched one block ahead (2)
             keep = {}
             out = smin_forward(pk, dims, p, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
             torch.cuda.synchronize()
@@ -240,3 +238,28 @@ def test_boundary_schedules_are_bit_identical(name, prec, B, kw, monkeypatch):
     for other in outs[1:]:
         for x, y in zip(outs[0], other):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,B,kw", [("charadessta", 9, {}), ("charadessta", 64, {}), ("charadessta", 5, {"nfeats_range": (1, 9)}),
+                                       ("charadessta", 3, {"full_length": True}), ("tacos", 6, {}), ("activitynet", 3, {}),
+                                       ("tiny", 5, {})])
+def test_ping_pong_content_unit_is_bit_identical(name, B, kw, monkeypatch):
+    """content_unit_pp_kernel (two row-warp groups on alternate tiles, one Y accumulator, mean_c in 64-column halves, 8-box
+    ring) computes exactly what content_unit_kernel<.., 4> computes: every layer's cu / fm / fb and the scores bit for bit,
+    over single-tile, multi-tile, multi-sample-per-tile and ragged-last-tile maps."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    dims = dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, L_.BF16, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 5151, **kw))
+    n = int(batch["moment_mask"].sum().item())
+    res = {}
+    for variant in ("4", "5"):
+        monkeypatch.setenv("VML_CU_VARIANT", variant)
+        keep = {}
+        out = smin_forward(pk, dims, L_.BF16, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+        torch.cuda.synchronize()
+        res[variant] = [o.clone() for o in out] + [keep[f"f{x}{k}"][:n if x != "b" else None].clone()
+                                                   for k in range(1, cfg.layers + 1) for x in ("c", "m", "b")]
+    for x, y in zip(res["4"], res["5"]):
+        assert torch.equal(x, y)

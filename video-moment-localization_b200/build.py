@@ -42,6 +42,15 @@ def _digest(paths, cflags=None):
 LIB_DBG = os.path.join(HERE, "libvml_b200_dbg.so")
 
 
+LIB_TIMING = os.path.join(HERE, "libvml_b200_timing.so")
+
+
+def build_timing() -> str:
+    """Development aid: the library with %globaltimer stamps in the content-unit kernels (-DVML_CU_TIMING; tools/cu_timing.py,
+    tools/pp_timing.py), as ``libvml_b200_timing.so``; select it with ``VML_LIB=<path>``."""
+    return _build(LIB_TIMING, os.path.join(ROOT, "build", "vml_b200_timing"), CFLAGS + ["-DVML_CU_TIMING"], False, False)
+
+
 def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
     """``debug=True``: the bounds-checking build (-DVML_DEBUG_BOUNDS, see csrc/common.cuh) as ``libvml_b200_dbg.so``; select it
     at run time with ``VML_LIB=<path>``."""
@@ -84,4 +93,7 @@ def _build(LIB, OBJ_DIR, CFLAGS, force, verbose) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))
+    if "--timing" in sys.argv:
+        print(build_timing())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -111,9 +111,8 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const float* __restrict__ bias1, const float* __restrict__ bias2, const float* __restrict__ qproj, int ld,
                     int off_what, int off_ktil, int off_beta, const float* __restrict__ s_hat, int s_ld,
                     const uint8_t* __restrict__ qmask, const int32_t* __restrict__ code, const int32_t* __restrict__ n_cells,
-                    int Nq, int B, int store_cu, int knobs) {
+                    int Nq, int B, int store_cu) {
   using Cfg = CuCfg<NQP, GS, V>;
-  const bool fbar_pf = (knobs & 1) != 0, fq_ahead = (knobs & 2) != 0;      // A/B knobs (VML_CU_KNOBS), both on by default
   constexpr int NW = Cfg::NW, KG = Cfg::KG;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
@@ -215,12 +214,6 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       };
       auto do_main = [&](int t) {
         const int base = base_main(t), m0 = (tile_begin + t) * UG_BM;
-        // the tile's fbar rows (32 cells x D, contiguous) are read by the row warps ~10 us from now, straight from global
-        // memory: pull them into L2 (21 % of the row warps' stall samples were those loads, ncu source page)
-        if (fbar_pf) {
-          const int c0 = m0 >> 2, nc = min(UG_BM / 4, (M >> 2) - c0);
-          if (nc > 0) ptx::bulk_prefetch_l2(fbar + (size_t)c0 * D, (uint32_t)(nc * D * 2));
-        }
         for (int kb = 0; kb < KB; ++kb) { load(base + 2 * kb, &tmX, kb * UG_BK, m0, keep); load(base + 2 * kb + 1, &tmW1, kb * UG_BK, 0, keep); }
       };
       auto do_tail = [&](int t) {
@@ -807,15 +800,9 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       uint4 fq[NP];
 #pragma unroll
       for (int i = 0; i < NP; ++i) fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow) + i) : make_uint4(0, 0, 0, 0);
-      uint4 fqn[NP];
       for (int nb = 0; nb < NB; ++nb, ++yi) {
         const uint32_t yb = yi & 1, yph = (yi >> 1) & 1;
         VML_DBG_ASSERT(V != 4 || (box_of >= 0 && box_of < 2 && pc0 + NP <= 8));
-        if (V >= 2 && fq_ahead) {          // block nb + 1's fbar goes out before the wait for block nb's accumulator: a whole block of cover
-#pragma unroll
-          for (int i = 0; i < NP; ++i)
-            fqn[i] = (valid && nb + 1 < NB) ? __ldg(reinterpret_cast<const uint4*>(frow + (nb + 1) * 128) + i) : make_uint4(0, 0, 0, 0);
-        }
         unsigned char* xb = V == 4 ? Ring + ((base_tail((int)it) + 4 * nb + 2 + box_of) % RB) * CU_BOX
                             : (V >= 2 && nb == NB - 1) ? Cs + box_of * CU_BOX : Xs + (2 * nb + box_of) * CU_BOX;
         ptx::mbar_wait_relaxed(&yfull[yb], yph);              // TMEM data: ordered by the tcgen05 fence below
@@ -911,10 +898,7 @@ content_unit_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
         }
         CU_T(38 + nb);
-        if (V >= 2 && fq_ahead) {
-#pragma unroll
-          for (int i = 0; i < NP; ++i) fq[i] = fqn[i];
-        } else if (nb + 1 < NB) {
+        if (nb + 1 < NB) {
 #pragma unroll
           for (int i = 0; i < NP; ++i)
             fq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(frow + (nb + 1) * 128) + i) : make_uint4(0, 0, 0, 0);
@@ -944,11 +928,14 @@ static int launch_content_unit(const CUtensorMap* tm, int grid, const bf16* fbar
   VML_CUDA(ensure_dyn_smem((const void*)(content_unit_kernel<NQP, GS, V>), (size_t)(Cfg::SMEM)));
   content_unit_kernel<NQP, GS, V><<<grid, V >= 3 ? CU_THREADS_V2 : CU_THREADS, Cfg::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], d.D, fbar, side, ld_side, b1, b2, qproj, ld,
                                                                     off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells.code,
-                                                                    cells.n_cells, d.Nq, B, store_cu,
-                                                                    getenv("VML_CU_KNOBS") ? atoi(getenv("VML_CU_KNOBS")) : 3);
+                                                                    cells.n_cells, d.Nq, B, store_cu);
   VML_LAUNCHED(1);
   return VML_OK;
 }
+
+int content_unit_pp(const CUtensorMap* tm, int grid, const void* fbar, void* side, int ld_side, const float* b1, const float* qproj,
+                    int ld, int off_what, int off_ktil, int off_beta, const float* s_hat, int s_ld, const uint8_t* qmask,
+                    vml_cells_t cells, int B, vml_dims_t d, int store_cu, cudaStream_t st);      // content_unit_pp.cu
 
 bool content_unit_supported(vml_dims_t d) {
   return d.dl == CU_DL && d.C == 4 && d.D % 128 == 0 && d.D <= CU_MAXKB * 64 && d.Nq <= 31;
@@ -976,6 +963,9 @@ int content_unit(const void* fc, const void* W1, const float* b1, const float* q
 #define VML_CU(NQP, GS, V) return launch_content_unit<NQP, GS, V>(tm, grid, (const bf16*)fbar, (bf16*)side, ld_side, b1, b2, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, B, d, store_cu, st)
   if (bias_in_fbar) {            // V2 / V3: output bias folded into fbar by the boundary unit, residual on the tensor cores
     const int variant = getenv("VML_CU_VARIANT") != nullptr ? atoi(getenv("VML_CU_VARIANT")) : 4;   // (A/B knob)
+    if (variant == 5)              // ping-pong schedule: two row-warp groups on alternate tiles (content_unit_pp.cu)
+      return content_unit_pp(tm, grid, fbar, side, ld_side, b1, qproj, ld, off_what, off_ktil, off_beta, s_hat, s_ld, qmask, cells, B, d,
+                             store_cu, st);
     if (variant == 2) {            // mean_c read back by the row warps
       if (d.Nq + 1 <= 8) VML_CU(8, 2, 2);
       if (d.Nq + 1 <= 16) VML_CU(16, 2, 2);
