@@ -263,3 +263,31 @@ def test_ping_pong_content_unit_is_bit_identical(name, B, kw, monkeypatch):
                                                    for k in range(1, cfg.layers + 1) for x in ("c", "m", "b")]
     for x, y in zip(res["4"], res["5"]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,prec,B,kw", [("charadessta", "bf16", 7, {}), ("charadessta", "fp32", 5, {}), ("tacos", "bf16", 3, {}),
+                                            ("activitynet", "bf16", 2, {}), ("activitynet", "fp32", 2, {}),
+                                            ("charadessta", "bf16", 6, {"nfeats_range": (1, 9)}), ("tiny", "fp32", 5, {}),
+                                            ("tiny_r2", "fp32", 5, {})])
+def test_span_pool_c4_kernel_matches_generic_kernel(name, prec, B, kw, monkeypatch):
+    """span_pool_c4_kernel (C = 4, compile-time slice width, table-driven clip sizes, f32x2 math) against span_pool_kernel
+    on the same inputs: pooled clips fc, moment features fm and boundary features fb bit for bit (same operations in the
+    same order), ActivityNet's irregular windows and 1-clip videos included."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    p, dims = L_.PREC[prec], dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, p, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 6161, **kw))
+    n = int(batch["moment_mask"].sum().item())
+    got = {}
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("VML_SPAN_GENERIC", "1")
+        else:
+            monkeypatch.delenv("VML_SPAN_GENERIC", raising=False)
+        keep = {}
+        smin_forward(pk, dims, p, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+        torch.cuda.synchronize()
+        got[generic] = (keep["fc0"][:n].clone(), keep["fm0"][:n].clone(), keep["fb0"].clone())
+    for x, y in zip(got[False], got[True]):
+        assert torch.equal(x, y)

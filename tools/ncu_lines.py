@@ -25,6 +25,20 @@ for r in rows:
         st = sorted(((f(r[i]), n[6:]) for i, n in stall_is if i < len(r)), reverse=True)[:3]
         out.append((f(r[samp_i]), f(r[inst_i]), fname, int(r[0]), r[1].strip()[:90], " ".join(f"{n}:{int(v)}" for v, n in st if v > 0)))
 tot_s, tot_i = sum(o[0] for o in out), sum(o[1] for o in out)
+# stall reasons summed over the whole kernel
+agg = {}
+hdr2 = None
+for r in rows:
+    if r and r[0] == "Line No":
+        hdr2 = [(i, n[6:]) for i, n in enumerate(r) if n.startswith("stall_") and "Not Issued" not in n]
+    elif hdr2 and r and r[0].strip().isdigit():
+        for i, n in hdr2:
+            try:
+                agg[n] = agg.get(n, 0.0) + float(r[i].replace(",", ""))
+            except Exception:
+                pass
+tt = sum(agg.values()) or 1.0
+print("# stall reasons: " + "  ".join(f"{n} {v / tt:.2f}" for n, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
 print(f"# total samples {int(tot_s)}, warp instructions {int(tot_i)}")
 print("# by samples")
 for o in sorted(out, reverse=True)[:top]:

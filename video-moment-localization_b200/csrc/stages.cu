@@ -4,6 +4,7 @@
 // bf16 = fast mode); all arithmetic is fp32.
 #include <stdlib.h>
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace vml {
 
@@ -405,6 +406,140 @@ span_pool_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, cons
   }
 }
 
+// ---- fast path: C = 4 clips per cell, the D-slice a compile-time constant ----------------------------------------------
+// Same arithmetic in the same order as span_pool_kernel (bit-identical outputs).  That kernel ran at 60 % issue-slot
+// utilisation with 69 M warp instructions per 640-query Charades pass (ncu) -- an instruction-bound write stream: run-time
+// slice widths (a multiply per shared-memory access), an integer division by C and a float division per cell and
+// thread, scalar fp32 math.  Here: shifts and immediates, the per-length clip size / weight from a small table, f32x2
+// arithmetic, the sentence factor hoisted out of the load loop.
+template <typename ActT, int DS>
+__global__ void __launch_bounds__(512)
+span_pool_c4_kernel(const ActT* __restrict__ fv, const float* __restrict__ fs, const int32_t* __restrict__ code,
+                    const int32_t* __restrict__ row_start, ActT* __restrict__ fc, ActT* __restrict__ fm,
+                    float* __restrict__ fb, int T, int L, int D, int capacity) {
+  constexpr int C = 4;
+  extern __shared__ __align__(16) float P[];  // [(T+1)][DS]
+  __shared__ int s_cs[256];                    // per span length (in map cells): clip size | clips << 16
+  __shared__ float s_w[256];                   // fp32(1 / clip size)
+  const int b = blockIdx.x, d0 = blockIdx.y * DS;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int r = T / L;
+  constexpr int GROUPS = DS / 8;             // write phase: 8 columns per thread
+  const int g = tid % GROUPS, lane_cell = tid / GROUPS, cells_per_iter = nthr / GROUPS;
+  // the sample's cell range and this thread's first cell code: two dependent trips to L2, taken under the tile load
+  const int n_lo = __ldg(row_start + b * L), n_hi = min(__ldg(row_start + (b + 1) * L), capacity);
+  int cd_next = n_lo + lane_cell < n_hi ? __ldg(code + n_lo + lane_cell) : 0;
+
+  // ---- load the tile, fuse with fs (a3) ----------------------------------------------------
+  {
+    constexpr int Q4 = DS / 4;
+    const int c4 = (tid % Q4) * 4, t0 = tid / Q4, tstep = nthr / Q4;
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(fs + (size_t)b * D + d0 + c4));
+    const ActT* src = fv + (size_t)b * T * D + d0 + c4;
+#pragma unroll 8
+    for (int t = t0; t < T; t += tstep) {
+      const float4 x = ld4(src + (size_t)t * D);
+      *reinterpret_cast<float4*>(P + (t + 1) * DS + c4) = make_float4(x.x * s4.x, x.y * s4.y, x.z * s4.z, x.w * s4.w);
+    }
+  }
+  for (int e = tid; e < DS; e += nthr) P[e] = 0.f;
+  for (int len = tid + 1; len <= L; len += nthr) {
+    const int nf = len * r;
+    const int cs = max(1, nf / C);
+    s_cs[len - 1] = cs | (min(C, nf) << 16);
+    s_w[len - 1] = 1.0f / (float)cs;           // fp32(1/clip_size), as the reference's Wc
+  }
+  __syncthreads();
+  // ---- inclusive scan over t (the summation order of span_pool_kernel: fixed 16-row segments, then segment offsets) ----
+  {
+    constexpr int SEG = 16, MAXI = 8;
+    const int nseg = (T + SEG - 1) / SEG;
+    const int items = DS * nseg;
+    for (int e = tid; e < items; e += nthr) {
+      const int col = e % DS, seg = e / DS;
+      const int lo = seg * SEG, hi = min(lo + SEG, T);
+      float run = 0.f;
+      float* p = P + (lo + 1) * DS + col;
+      for (int t = lo; t < hi; ++t, p += DS) { run += *p; *p = run; }
+    }
+    __syncthreads();
+    float off[MAXI];
+    int it = 0;
+    for (int e = tid; e < items; e += nthr, ++it) {
+      const int col = e % DS, seg = e / DS;
+      float o = 0.f;
+      for (int s2 = 0; s2 < seg; ++s2) o += P[min((s2 + 1) * SEG, T) * DS + col];
+      if (it < MAXI) off[it] = o;
+    }
+    __syncthreads();
+    it = 0;
+    for (int e = tid; e < items; e += nthr, ++it) {
+      const int col = e % DS, seg = e / DS;
+      if (seg == 0) continue;
+      const int lo = seg * SEG, hi = min(lo + SEG, T);
+      const float o = off[it < MAXI ? it : 0];
+      float* p = P + (lo + 1) * DS + col;
+      for (int t = lo; t < hi; ++t, p += DS) *p += o;
+    }
+  }
+  __syncthreads();
+
+  const int dd = g * 8;
+
+  // fb: unmasked average pool (models.py:120-125)
+  const float inv_r = 1.0f / (float)r;
+  for (int l = lane_cell; l < L; l += cells_per_iter) {
+    const f8 a = ld8(P + ((l + 1) * r) * DS + dd), c = ld8(P + (l * r) * DS + dd);
+    f8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = (a.v[e] - c.v[e]) * inv_r;
+    st8(fb + ((size_t)b * L + l) * D + d0 + dd, o);
+  }
+
+  const float inv_C = 1.0f / (float)C;
+  ActT* fc_col = fc + d0 + dd;
+  ActT* fm_col = fm + d0 + dd;
+  // the cell code of the NEXT iteration is requested before this iteration's work: the per-cell global load was a third of
+  // all stall samples (long scoreboard at the decode, ncu source page)
+  for (int n = n_lo + lane_cell; n < n_hi; n += cells_per_iter) {
+    const int cd = cd_next;
+    if (n + cells_per_iter < n_hi) cd_next = __ldg(code + n + cells_per_iter);
+    const int i = (cd >> 8) & 0xff, j = cd & 0xff;
+    VML_DBG_ASSERT(n >= 0 && n < capacity && (cd >> 16) == b && i <= j && j < L);
+    const int info = s_cs[j - i], cs = info & 0xffff, nclips = info >> 16;
+    const float w = s_w[j - i];
+    const float* prow = P + (i * r) * DS + dd;
+    f8 mean;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mean.v[e] = 0.f;
+    ActT* fc_row = fc_col + (size_t)n * (C * D);
+    f8 prev = ld8(prow);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      f8 o;
+      if (c < nclips) {
+        VML_DBG_ASSERT(i * r + (c + 1) * cs <= T);
+        const f8 cur = ld8(prow + ((c + 1) * cs) * DS);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          o.v[e] = cur.v[e]; o.v[e + 1] = cur.v[e + 1];
+          ptx::add2(o.v[e], o.v[e + 1], -prev.v[e], -prev.v[e + 1]);            // (cur - prev)
+          ptx::mul2(o.v[e], o.v[e + 1], w, w);
+          ptx::add2(mean.v[e], mean.v[e + 1], o.v[e], o.v[e + 1]);
+        }
+        prev = cur;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = 0.f;
+      }
+      st8(fc_row + c * D, o);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) ptx::mul2(mean.v[e], mean.v[e + 1], inv_C, inv_C);
+    st8(fm_col + (size_t)n * D, mean);
+  }
+}
+
 int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc, void* fm, float* fb, int B,
                    vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.T % d.L == 0 && d.D % 8 == 0 && d.C >= 1);
@@ -428,6 +563,22 @@ int span_pool_fuse(const void* fv, const float* fs, vml_cells_t cells, void* fc,
   const int threads = smem > 75 * 1024 ? 512 : 256;
   VML_CHECK_ARG((int64_t)dslice * ceil_div(d.T, 16) <= 8 * threads);     // scan work items per thread
   dim3 grid(B, d.D / dslice);
+  // C = 4 and a slice of 64 / 128 / 256 columns: the specialised kernel (A/B knob: VML_SPAN_GENERIC=1 keeps the generic one)
+  if (d.C == 4 && d.L <= 256 && (dslice == 64 || dslice == 128 || dslice == 256) && threads % (dslice / 4) == 0 &&
+      getenv("VML_SPAN_GENERIC") == nullptr) {
+    static bool reg2 = (register_kernel("span_pool_c4_kernel"), true); (void)reg2;
+#define VML_SP(ACT, DS)                                                                                                   \
+  do {                                                                                                                    \
+    VML_CUDA(ensure_dyn_smem((const void*)(span_pool_c4_kernel<ACT, DS>), (size_t)((int)smem)));                          \
+    span_pool_c4_kernel<ACT, DS><<<grid, threads, smem, st>>>((const ACT*)fv, fs, cells.code, cells.row_start, (ACT*)fc,  \
+                                                              (ACT*)fm, fb, d.T, d.L, d.D, cells.capacity);              \
+  } while (0)
+    if (prec == VML_BF16) { if (dslice == 64) VML_SP(bf16, 64); else if (dslice == 128) VML_SP(bf16, 128); else VML_SP(bf16, 256); }
+    else { if (dslice == 64) VML_SP(float, 64); else if (dslice == 128) VML_SP(float, 128); else VML_SP(float, 256); }
+#undef VML_SP
+    VML_LAUNCHED(1);
+    return VML_OK;
+  }
   if (prec == VML_BF16) {
     VML_CUDA(ensure_dyn_smem((const void*)(span_pool_kernel<bf16>), (size_t)((int)smem)));
     span_pool_kernel<bf16><<<grid, threads, smem, st>>>((const bf16*)fv, fs, cells.code, cells.row_start, (bf16*)fc,
