@@ -806,6 +806,8 @@ moment_pair_kernel(const float* __restrict__ bu, const int32_t* __restrict__ cod
   const int n_total = *n_cells;
   const int per = D / 8, cells_per_blk = blockDim.x / per;
   const int t = threadIdx.x % per, sub = threadIdx.x / per;
+  // (measured: giving a CTA a contiguous range of cells -- boundary rows re-used from L1 -- plus a one-iteration-ahead code
+  // fetch is SLOWER than this grid-stride loop: 8.3 against 7.4 us per step on the Charades pass)
   for (int n = blockIdx.x * cells_per_blk + sub; n < n_total; n += gridDim.x * cells_per_blk) {
     int b, i, j; decode_cell(code[n], b, i, j);
     const int dd = t * 8;
@@ -883,11 +885,71 @@ localize_boundary_kernel(const float* __restrict__ fb, const float* __restrict__
   }
 }
 
+// Both heads in ONE launch (fast path, D % 8 == 0): a warp per item, items = valid cells (p_m) followed by the B * L boundary
+// rows (p_s, p_e, p_a).  16-byte loads (8 map features / 4 boundary features per lane and instruction; the scalar row
+// kernel issued 64 four-byte loads per lane), the cell code requested before the dot product instead of after it, and the
+// two heads no longer wait for each other in the stream.
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+localize_fused_kernel(const ActT* __restrict__ fm, const float* __restrict__ fb, const float* __restrict__ w4,
+                      const float* __restrict__ b4, const int32_t* __restrict__ code, const int32_t* __restrict__ n_cells,
+                      const uint8_t* __restrict__ lmask, float* __restrict__ pm, float* __restrict__ ps, float* __restrict__ pe,
+                      float* __restrict__ pa, int rows, int L, int D) {
+  const int n_total = *n_cells, items = n_total + rows;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  for (int item = blockIdx.x * nw + warp; item < items; item += gridDim.x * nw) {
+    if (item < n_total) {
+      const int cd = __ldg(code + item);                 // all lanes, one address: a broadcast, off the critical path
+      float acc = 0.f;
+      const ActT* x = fm + (size_t)item * D;
+      for (int e = lane * 8; e < D; e += 256) {
+        const f8 xv = ld8(x + e), wv = ld8(w4 + e);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fmaf(xv.v[q], wv.v[q], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        int b, i, j; decode_cell(cd, b, i, j);
+        pm[((size_t)b * L + i) * L + j] = sigmoidf_(acc + b4[0]);
+      }
+    } else {
+      const int row = item - n_total;
+      float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* x = fb + (size_t)row * D;
+      for (int e = lane * 4; e < D; e += 128) {
+        const float4 xv = ld4(x + e), w1 = ld4(w4 + D + e), w2 = ld4(w4 + 2 * D + e), w3 = ld4(w4 + 3 * D + e);
+        a1 = fmaf(xv.x, w1.x, a1); a1 = fmaf(xv.y, w1.y, a1); a1 = fmaf(xv.z, w1.z, a1); a1 = fmaf(xv.w, w1.w, a1);
+        a2 = fmaf(xv.x, w2.x, a2); a2 = fmaf(xv.y, w2.y, a2); a2 = fmaf(xv.z, w2.z, a2); a2 = fmaf(xv.w, w2.w, a2);
+        a3 = fmaf(xv.x, w3.x, a3); a3 = fmaf(xv.y, w3.y, a3); a3 = fmaf(xv.z, w3.z, a3); a3 = fmaf(xv.w, w3.w, a3);
+      }
+      a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+      if (lane == 0) {
+        const float m = lmask[row] ? 1.f : 0.f;
+        ps[row] = sigmoidf_(a1 + b4[1]) * m;
+        pe[row] = sigmoidf_(a2 + b4[2]) * m;
+        pa[row] = sigmoidf_(a3 + b4[3]) * m;
+      }
+    }
+  }
+}
+
 int localize(const void* fm, const float* fb, const float* w4, const float* b4, vml_cells_t cells, const uint8_t* lmask,
              float* pm, float* ps, float* pe, float* pa, int B, vml_dims_t d, int prec, cudaStream_t st) {
   VML_CHECK_ARG(d.D % 4 == 0);
   static bool reg = (register_kernel("localize_pm_kernel"), register_kernel("localize_boundary_kernel"), true); (void)reg;
   VML_CUDA(cudaMemsetAsync(pm, 0, sizeof(float) * (size_t)B * d.L * d.L, st));
+  if (d.D % 8 == 0 && getenv("VML_LOCALIZE_SPLIT") == nullptr) {
+    static bool reg2 = (register_kernel("localize_fused_kernel"), true); (void)reg2;
+    const int gridf = min(ceil_div(cells.capacity + B * d.L, 8), kNumSMs * 8);
+    if (prec == VML_BF16)
+      localize_fused_kernel<bf16><<<gridf, 256, 0, st>>>((const bf16*)fm, fb, w4, b4, cells.code, cells.n_cells, lmask, pm, ps, pe, pa,
+                                                        B * d.L, d.L, d.D);
+    else
+      localize_fused_kernel<float><<<gridf, 256, 0, st>>>((const float*)fm, fb, w4, b4, cells.code, cells.n_cells, lmask, pm, ps, pe,
+                                                         pa, B * d.L, d.L, d.D);
+    VML_LAUNCHED(1);
+    return VML_OK;
+  }
   const int grid = min(ceil_div(cells.capacity, 8), kNumSMs * 8);
   if (prec == VML_BF16)
     localize_pm_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)fm, w4, b4, cells.code, cells.n_cells, pm, d.L, d.D);
