@@ -291,3 +291,30 @@ def test_span_pool_c4_kernel_matches_generic_kernel(name, prec, B, kw, monkeypat
         got[generic] = (keep["fc0"][:n].clone(), keep["fm0"][:n].clone(), keep["fb0"].clone())
     for x, y in zip(got[False], got[True]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,B,kw", [("charadessta", 9, {}), ("charadessta", 64, {}), ("tacos", 5, {}), ("activitynet", 3, {}),
+                                       ("charadessta", 5, {"nfeats_range": (1, 9)}), ("tiny", 5, {})])
+def test_transposing_gemm_epilogues_are_bit_identical(name, B, kw, monkeypatch):
+    """EpiBiasT / EpiClipT / EpiMomentOutT (tcgen05 GEMM results re-laid through a shared-memory tile so that every warp
+    store covers whole lines) perform the same additions in the same order as the register epilogues they replace
+    (VML_EPI_DIRECT=1): clip projection, query states, every layer's fm and the scores agree bit for bit."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    dims = dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, L_.BF16, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 7171, **kw))
+    n = int(batch["moment_mask"].sum().item())
+    res = {}
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv("VML_EPI_DIRECT", "1")
+        else:
+            monkeypatch.delenv("VML_EPI_DIRECT", raising=False)
+        keep = {}
+        out = smin_forward(pk, dims, L_.BF16, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+        torch.cuda.synchronize()
+        res[direct] = [o.clone() for o in out] + [keep["fv"].clone(), keep["fs"].clone(), keep["fw"].clone()] + \
+                      [keep[f"fm{k}"][:n].clone() for k in range(1, cfg.layers + 1)]
+    for x, y in zip(res[False], res[True]):
+        assert torch.equal(x, y)

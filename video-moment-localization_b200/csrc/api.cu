@@ -258,6 +258,11 @@ VML_API int vml_linear(const void* A, const void* W, const float* bias, void* ou
     EpiBias<bf16> e{bias, (bf16*)out, ldo};
     return gemm_dispatch(A, W, M, N, K, K, m_dev, m_scale, e, prec, ST(stream));
   }
+  if (prec == VML_BF16 && N % 32 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && getenv("VML_EPI_DIRECT") == nullptr) {
+    EpiBiasT e{bias, (float*)out, ldo};          // fp32 result of the tcgen05 GEMM: coalesced stores (epilogues.cuh)
+    return launch_gemm_umma(A, W, M, N, K, K, K, m_dev, m_scale, e, ST(stream));
+  }
   EpiBias<float> e{bias, (float*)out, ldo};
   return gemm_dispatch(A, W, M, N, K, K, m_dev, m_scale, e, prec, ST(stream));
 }
@@ -267,6 +272,10 @@ VML_API int vml_clip_projection(const void* v, const void* W, const float* bias,
   VML_PREC_OK(prec);
   const int M = B * d.T;
   if (prec == VML_BF16) {
+    if (getenv("VML_EPI_DIRECT") == nullptr) {
+      EpiClipT e{bias, pe, video_mask, d.T, (bf16*)fv, d.D, M};
+      return launch_gemm_umma(v, W, M, d.D, k_pad, k_pad, k_pad, nullptr, 1, e, ST(stream));
+    }
     EpiClipPre e{bias, pe, video_mask, d.T, (bf16*)fv, d.D};
     return launch_gemm_umma(v, W, M, d.D, k_pad, k_pad, k_pad, nullptr, 1, e, ST(stream));
   }
@@ -389,6 +398,10 @@ VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* b
     // (A/B knob) L2 prefetch of the next tile's operand rows: measured on B200 it SLOWS the stage (20.9 -> 23.5 us per step at
     // 640-query passes): the loop is not short of latency cover, the prefetches only add L2 request traffic
     static const int pf = getenv("VML_GEMM_PREFETCH") != nullptr;
+    if (getenv("VML_EPI_DIRECT") == nullptr) {        // coalescing epilogue through a shared-memory transpose (epilogues.cuh)
+      EpiMomentOutT e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D, pf, cells.capacity};
+      return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
+    }
     EpiMomentOutPre e{bias_sum, (const bf16*)fm, (bf16*)mu, d.D, pf};
     return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
   }

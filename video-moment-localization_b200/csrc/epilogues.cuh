@@ -43,6 +43,42 @@ struct EpiBias {
   }
 };
 
+// out = acc + bias, fp32, stored through a per-warp shared-memory transpose (tcgen05 GEMM with 8 epilogue warps only).
+// In the TMEM register layout a thread owns one output ROW, so a warp's 16-byte store touches 32 different 128-byte lines
+// (32 LSU wavefronts per instruction, 256 per 32 x 32 chunk); the LSTM input projections and the folded query projection
+// write 50-70 MB of fp32 per pass behind K = 300-512 and ran at 1-1.8 TB/s with the tensor pipe at 16-24 % (ncu).  Here the
+// 32 x 32 chunk goes through a padded shared-memory tile (conflict-free both ways) and leaves as 8 stores of four full
+// lines each: 32 wavefronts per chunk.  Same additions, same bits.
+struct EpiBiasT {
+  static constexpr bool kWarpCollective = true;
+  static constexpr int kMaxBN = 128;          // 8 epilogue warps: the scratch below is sized for them
+  const float* bias;  // [N] or nullptr
+  float* out;
+  int ldo;
+  template <int N>
+  __device__ __forceinline__ void apply_warp(int row, int col0, const float* acc, bool valid) const {
+    static_assert(N == 32, "one 32 x 32 chunk per call");
+    __shared__ __align__(16) float scratch[8][32][36];
+    const int lane = threadIdx.x % 32, w = (threadIdx.x / 32 - 2) & 7;
+    float (*s)[36] = scratch[w];
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(&s[lane][c]) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+    const uint32_t live = __ballot_sync(0xffffffffu, valid);
+    __syncwarp();                                                 // tile written -> readable by the other lanes
+    const int cc = (lane % 8) * 4, rsub = lane / 8, row0 = row - lane;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + cc));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = 4 * k + rsub;
+      float4 v = *reinterpret_cast<const float4*>(&s[r][cc]);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      if ((live >> r) & 1u) *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * ldo + col0 + cc) = v;
+    }
+    __syncwarp();                                                 // the next chunk overwrites the tile
+  }
+};
+
 // a1  fv = (acc + bias)*mask + pe[t]*mask             (VideoEncoder.forward, models.py:27-34)
 template <typename OutT>
 struct EpiClip {
@@ -258,6 +294,118 @@ struct EpiMomentOut {
       v.w = (acc[c + 3] + bias[col0 + c + 3]) + mv.w;
       st4(o + c, v);
     }
+  }
+};
+
+// ---- transposing variants of the two big bf16 epilogues (shared-memory scratch, see EpiBiasT and gemm_umma.cuh) --------
+// The fp32 32 x 32 chunk of a warp goes through a padded tile; afterwards lane l owns 8 consecutive columns
+// (l % 4) * 8 .. of the rows 8k + l / 4, k = 0..3, so that every 16-byte access of a warp covers 8 rows x 64 contiguous
+// bytes (full sectors) instead of 32 rows x 16 bytes -- for the result AND for the operands that are added to it (the
+// residual / the positional encoding), which are prefetched in that layout.  Same operations in the same order: bit-identical.
+constexpr int kEpiTile = 32 * 36 * 4;      // bytes of a padded fp32 32 x 32 tile (conflict-free both ways)
+
+__device__ __forceinline__ void epi_tile_put(float* s, int lane, const float* acc) {
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(s + lane * 36 + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+  __syncwarp();
+}
+__device__ __forceinline__ f8 epi_tile_get(const float* s, int r, int cc) {
+  const float4 a = *reinterpret_cast<const float4*>(s + r * 36 + cc), b = *reinterpret_cast<const float4*>(s + r * 36 + cc + 4);
+  f8 v; v.v[0] = a.x; v.v[1] = a.y; v.v[2] = a.z; v.v[3] = a.w; v.v[4] = b.x; v.v[5] = b.y; v.v[6] = b.z; v.v[7] = b.w;
+  return v;
+}
+
+// a8, bf16:  fm' = (acc + bias) + fm
+struct EpiMomentOutT {            // (the opt-in cluster / CTA-pair GEMM variants keep the register epilogue: VML_EPI_DIRECT=1)
+  static constexpr int kScratchPerWarp = kEpiTile;
+  const float* bias;  // [D] = b_fb + b_fc
+  const bf16* fm;     // [n, D]
+  bf16* out;          // [n, D]
+  int ldo;
+  int pf_a;           // L2 prefetch of the next tile's operand rows (gemm_umma.cuh)
+  int rows_cap;       // rows of fm / out that exist (capacity; live rows are decided per launch on the device)
+  struct Pre { uint4 m[4]; };
+  __device__ __forceinline__ Pre load(int row, int col0, bool) const {
+    const int lane = threadIdx.x % 32, row0 = row - lane, cc = (lane % 4) * 8;
+    Pre p;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = row0 + 8 * k + lane / 4;
+      p.m[k] = r < rows_cap ? __ldg(reinterpret_cast<const uint4*>(fm + (size_t)r * ldo + col0 + cc)) : make_uint4(0, 0, 0, 0);
+    }
+    return p;
+  }
+  template <int N>
+  __device__ __forceinline__ void apply_pre_scr(int row, int col0, const float* acc, const Pre& p, bool valid, unsigned char* scr) const {
+    static_assert(N == 32, "one 32 x 32 chunk per call");
+    float* s = reinterpret_cast<float*>(scr);
+    const int lane = threadIdx.x % 32, row0 = row - lane, cc = (lane % 4) * 8;
+    const uint32_t live = __ballot_sync(0xffffffffu, valid);
+    epi_tile_put(s, lane, acc);
+    const f8 bv = ld8(bias + col0 + cc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 8 * k + lane / 4;
+      const f8 a = epi_tile_get(s, r, cc), mv = unpack8(p.m[k]);
+      f8 v;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] = (a.v[e] + bv.v[e]) + mv.v[e];
+      if ((live >> r) & 1u) st8(out + (size_t)(row0 + r) * ldo + col0 + cc, v);
+    }
+    __syncwarp();
+  }
+};
+
+// a1, bf16:  fv = (acc + bias)*mask + pe[t]*mask
+struct EpiClipT {
+  static constexpr int kScratchPerWarp = kEpiTile;
+  const float* bias;     // [D]
+  const float* pe;       // [T, D]
+  const uint8_t* vmask;  // [B*T]
+  int T;
+  bf16* out;             // [B*T, D]
+  int ldo;
+  int rows_cap;          // B*T
+  struct Pre { float4 p[8]; float m[4]; };
+  __device__ __forceinline__ Pre load(int row, int col0, bool) const {
+    const int lane = threadIdx.x % 32, row0 = row - lane, cc = (lane % 4) * 8;
+    Pre q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = row0 + 8 * k + lane / 4;
+      if (r < rows_cap) {
+        const float4* p = reinterpret_cast<const float4*>(pe + (size_t)(r % T) * ldo + col0 + cc);
+        q.p[2 * k] = __ldg(p); q.p[2 * k + 1] = __ldg(p + 1);
+        q.m[k] = vmask[r] ? 1.0f : 0.0f;
+      } else {
+        q.p[2 * k] = q.p[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        q.m[k] = 0.f;
+      }
+    }
+    return q;
+  }
+  template <int N>
+  __device__ __forceinline__ void apply_pre_scr(int row, int col0, const float* acc, const Pre& q, bool valid, unsigned char* scr) const {
+    static_assert(N == 32, "one 32 x 32 chunk per call");
+    float* s = reinterpret_cast<float*>(scr);
+    const int lane = threadIdx.x % 32, row0 = row - lane, cc = (lane % 4) * 8;
+    const uint32_t live = __ballot_sync(0xffffffffu, valid);
+    epi_tile_put(s, lane, acc);
+    const f8 bv = ld8(bias + col0 + cc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 8 * k + lane / 4;
+      const f8 a = epi_tile_get(s, r, cc);
+      const float m = q.m[k];
+      const float4 p0 = q.p[2 * k], p1 = q.p[2 * k + 1];
+      f8 v;                                   // same expression, term by term, as EpiClip::apply
+      v.v[0] = (a.v[0] + bv.v[0]) * m + p0.x * m; v.v[1] = (a.v[1] + bv.v[1]) * m + p0.y * m;
+      v.v[2] = (a.v[2] + bv.v[2]) * m + p0.z * m; v.v[3] = (a.v[3] + bv.v[3]) * m + p0.w * m;
+      v.v[4] = (a.v[4] + bv.v[4]) * m + p1.x * m; v.v[5] = (a.v[5] + bv.v[5]) * m + p1.y * m;
+      v.v[6] = (a.v[6] + bv.v[6]) * m + p1.z * m; v.v[7] = (a.v[7] + bv.v[7]) * m + p1.w * m;
+      if ((live >> r) & 1u) st8(out + (size_t)(row0 + r) * ldo + col0 + cc, v);
+    }
+    __syncwarp();
   }
 };
 

@@ -40,6 +40,19 @@ struct epi_wants_cluster : std::false_type {};
 template <typename E>
 struct epi_wants_cluster<E, std::enable_if_t<E::kCluster2>> : std::true_type {};
 
+// an epilogue may cap the tile width (e.g. one whose shared-memory scratch is sized for 8 epilogue warps)
+template <typename E, typename = void>
+struct epi_max_bn : std::integral_constant<int, 256> {};
+template <typename E>
+struct epi_max_bn<E, std::void_t<decltype(E::kMaxBN)>> : std::integral_constant<int, E::kMaxBN> {};
+
+// an epilogue may ask for per-warp shared-memory scratch (kScratchPerWarp bytes): the kernel places it behind the barrier block,
+// the pipeline gives up stages if need be, and the epilogue is called as apply_pre_scr(..., scratch) by ALL lanes of the warp
+template <typename E, typename = void>
+struct epi_scratch : std::integral_constant<int, 0> {};
+template <typename E>
+struct epi_scratch<E, std::void_t<decltype(E::kScratchPerWarp)>> : std::integral_constant<int, E::kScratchPerWarp> {};
+
 template <typename E, typename = void>
 struct epi_has_pre : std::false_type {};
 template <typename E>
@@ -51,14 +64,17 @@ struct epi_has_pf : std::false_type {};
 template <typename E>
 struct epi_has_pf<E, std::void_t<decltype(std::declval<const E&>().pf_a)>> : std::true_type {};
 
-template <int BN>
+template <int BN, int SCR = 0 /* epilogue scratch bytes per CTA */>
 struct UmmaCfg {
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
   static constexpr int A_BYTES = UG_BM * UG_BK * 2;
   static constexpr int B_BYTES = BN * UG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int DEF_STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int FIT_STAGES = (232448 - 1024 - 256 - SCR) / STAGE_BYTES;
+  static constexpr int STAGES = DEF_STAGES < FIT_STAGES ? DEF_STAGES : FIT_STAGES;
+  static_assert(STAGES >= 2, "pipeline depth");
   static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);   // power of two for BN in {16,32,64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SCR;
 };
 
 // EW epilogue warps (8 or 16): EW / 4 of them share a TMEM lane quadrant and split the tile's columns.  With 128 x 256
@@ -72,7 +88,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
   static_assert(CL == 1 || CL == 2, "single CTA or 2-CTA cluster");
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, EW * epi_scratch<Epi>::value>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
   // compiler (LDS/STS instead of generic LD/ST, which an integer round-trip of the pointer would force)
@@ -184,7 +200,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = c_lo; c < c_hi; c += 32) {
           float v[32];
           ptx::tmem_ld32(t_addr + (uint32_t)c, v);
-          if constexpr (EW == 16 && sizeof(typename Epi::Pre) > 64) {
+          if constexpr (epi_scratch<Epi>::value > 0) {
+            unsigned char* scr = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * epi_scratch<Epi>::value;
+            if constexpr (EW == 16 && sizeof(typename Epi::Pre) > 64) {      // register budget: one bundle at a time (see below)
+              ptx::tmem_ld_wait();
+              epi.template apply_pre_scr<32>(row, n0 + c, v, pre, row < M, scr);
+              if (c + 32 < c_hi) pre = epi.load(row, n0 + c + 32, row < M);
+            } else {
+              typename Epi::Pre nxt = pre;
+              if (c + 32 < c_hi) nxt = epi.load(row, n0 + c + 32, row < M);
+              ptx::tmem_ld_wait();
+              epi.template apply_pre_scr<32>(row, n0 + c, v, pre, row < M, scr);
+              pre = nxt;
+            }
+          } else if constexpr (EW == 16 && sizeof(typename Epi::Pre) > 64) {
             // 640 threads leave 96 registers: one bundle at a time (the next one is requested right after this chunk's
             // arithmetic, under the next TMEM load)
             ptx::tmem_ld_wait();
@@ -364,7 +393,8 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
 template <int BN, typename Epi>
 int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int32_t* m_dev,
                         int m_scale, const Epi& epi, cudaStream_t stream) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, UG_EPI_WARPS * epi_scratch<Epi>::value>;       // 8 epilogue warps
+  using Cfg16 = UmmaCfg<BN, 16 * epi_scratch<Epi>::value>;               // 16 epilogue warps (wide tiles)
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, UG_BM);
   if (rc) return rc;
@@ -437,10 +467,10 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
     if (getenv("VML_GEMM_EPI8") == nullptr) {               // (A/B knob) 16 epilogue warps for the wide tile
       static bool attr16 = false;
       if (!attr16) {
-        VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi, 1, 16>), (size_t)(Cfg::SMEM_BYTES)));
+        VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi, 1, 16>), (size_t)(Cfg16::SMEM_BYTES)));
         attr16 = true;
       }
-      gemm_umma_kernel<BN, Epi, 1, 16><<<grid, 64 + 32 * 16, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+      gemm_umma_kernel<BN, Epi, 1, 16><<<grid, 64 + 32 * 16, Cfg16::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
       VML_LAUNCHED(1);
       return VML_OK;
     }
@@ -457,7 +487,7 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t inner, u
 template <int BN, typename Epi>
 int launch_gemm_umma_tf32_bn(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int32_t* m_dev,
                              int m_scale, const Epi& epi, cudaStream_t stream) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, (BN == 256 ? 16 : UG_EPI_WARPS) * epi_scratch<Epi>::value>;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, 1, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 4, UG_BK / 2, UG_BM, 3);
   if (rc) return rc;
@@ -502,8 +532,10 @@ int launch_gemm_umma(const void* A, const void* W, int M, int N, int K, int lda,
   // 128 x 256 tiles halve the operand traffic per flop but need >= ~4 waves of them to balance 148 persistent CTAs; below
   // that (Charades pass: 340 wide tiles = 2.3 waves -> 3 rounds) twice as many 128 x 128 tiles finish earlier (measured
   // 41.2 vs 43.2 us per layer; TACoS / ActivityNet with >= 5 waves keep the wide tile: 105 vs 110 us)
-  if (N % 256 == 0 && bn_force != 128 && ((int64_t)ceil_div(M, UG_BM) * (N / 256) >= 4 * kNumSMs || bn_force == 256))
-    return launch_gemm_umma_bn<256, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  if constexpr (epi_max_bn<Epi>::value >= 256) {
+    if (N % 256 == 0 && bn_force != 128 && ((int64_t)ceil_div(M, UG_BM) * (N / 256) >= 4 * kNumSMs || bn_force == 256))
+      return launch_gemm_umma_bn<256, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
+  }
   if (N % 128 == 0) return launch_gemm_umma_bn<128, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   if (N % 64 == 0) return launch_gemm_umma_bn<64, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
   return launch_gemm_umma_bn<32, Epi>(A, W, M, N, K, lda, ldw, m_dev, m_scale, epi, stream);
