@@ -103,7 +103,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # algorithmic work per stage: valid cells only
 # ---------------------------------------------------------------------------------------------
-def stage_work(cfg, B, n_cells, prec_bytes):
+def stage_work(cfg, B, n_cells, prec_bytes, pair_fused=False):
     T, L, C, D, dl, d0, Nq = cfg.T, cfg.L, cfg.C, cfg.D, cfg.dl, cfg.d0, cfg.Nq
     a = prec_bytes
     w = {}
@@ -119,7 +119,8 @@ def stage_work(cfg, B, n_cells, prec_bytes):
     # fast mode: only the bu_i*bu_j half is built here (the mean_c cu half comes from the content-out epilogue)
     w["moment_operand"] = ("hbm", a * n_cells * D + 4 * B * L * D) if a == 2 and C == 4 else ("hbm", a * (n_cells * C * D + n_cells * 2 * D))
     w["moment_out_gemm"] = ("tensor", 4.0 * n_cells * D * D)
-    w["boundary_unit"] = ("hbm", a * n_cells * D + 4 * 3 * B * L * D)
+    # (with the moment operand's bu_i*bu_j half written by the boundary unit's streaming kernel, its bytes are counted here)
+    w["boundary_unit"] = ("hbm", a * n_cells * D + 4 * 3 * B * L * D + (a * n_cells * D if pair_fused else 0))
     w["localize"] = ("hbm", a * n_cells * D + 4 * B * L * D)
     return w
 
@@ -876,7 +877,10 @@ def measure_stages(args, cfg, eb, peaks):
     calls_per_step = {k: float(v) / args.coalesce for k, v in stage_calls.items()}
     total_inst = sum(per_step.values())
     mean_cells = float(sum(n_cells[i % n_rot] for i in range(args.coalesce)))
-    work = stage_work(cfg, PB, mean_cells, 2 if eb.precision == "bf16" else 4)
+    from vml_b200.lib import Dims
+    dims_ = Dims(cfg.T, cfg.L, cfg.C, cfg.D, cfg.dl, cfg.layers, cfg.d0, cfg.Nq, cfg.H)
+    pair_fused = eb.precision == "bf16" and cfg.C == 4 and bool(lib.load().vml_boundary_pair_fused(dims_, lib.PREC[eb.precision]))
+    work = stage_work(cfg, PB, mean_cells, 2 if eb.precision == "bf16" else 4, pair_fused)
     stages = {}
     for name, ms in sorted(per_step.items(), key=lambda kv: -kv[1]):
         ent = {"ms_per_step": round(ms, 5), "share": round(ms / total_inst, 4), "launch_groups_per_step": calls_per_step[name]}

@@ -263,6 +263,16 @@ VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_b
 /* prob_out (optional, float [B,L,Nq]) and u_out (optional, float [B,L,D] = Aq*lmask + fs) are the saved
  * activations the backward pass needs (training path only). */
 
+/* a7 + the first half of a8's operand in one call: as vml_boundary_unit, and the per-sample streaming kernel also writes
+ * operand[n, 0:D] = bu[b,i] * bu[b,j] (models.py:292-295; what vml_moment_pair computes) while the sample's boundary rows are
+ * still on the SM.  operand: act [n, 2D].  Only where vml_boundary_pair_fused(d, prec) returns 1 (fast mode, L <= 16,
+ * D = 256 or 512); bit-identical to vml_boundary_unit followed by vml_moment_pair. */
+VML_API int vml_boundary_pair_fused(vml_dims_t d, int prec);
+VML_API int vml_boundary_unit_pair(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
+                                   const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
+                                   vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar,
+                                   const float* fbar_bias, void* operand, int B, vml_dims_t d, int prec, void* stream);
+
 /* ---- a8: MomentUnit (models.py:288-303) ------------------------------------------------------ */
 
 /* operand[n, 2D] = [ bu[b,i]*bu[b,j] | mean_c cu[n,c,:] ]  (act) */

@@ -318,3 +318,30 @@ def test_transposing_gemm_epilogues_are_bit_identical(name, B, kw, monkeypatch):
                       [keep[f"fm{k}"][:n].clone() for k in range(1, cfg.layers + 1)]
     for x, y in zip(res[False], res[True]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,B,kw", [("charadessta", 9, {}), ("charadessta", 64, {}), ("tacos", 5, {}),
+                                       ("charadessta", 5, {"nfeats_range": (1, 9)}), ("charadessta", 3, {"full_length": True}),
+                                       ("tiny", 5, {})])
+def test_pair_products_from_the_boundary_kernel_are_bit_identical(name, B, kw, monkeypatch):
+    """vml_boundary_unit_pair (the per-sample streaming kernel also writes operand[n, 0:D] = bu_i * bu_j) against
+    vml_boundary_unit + vml_moment_pair (VML_PAIR_SPLIT=1): every layer's fm / fb and the scores bit for bit."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    dims = dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, L_.BF16, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 8181, **kw))
+    n = int(batch["moment_mask"].sum().item())
+    res = {}
+    for split in (False, True):
+        if split:
+            monkeypatch.setenv("VML_PAIR_SPLIT", "1")
+        else:
+            monkeypatch.delenv("VML_PAIR_SPLIT", raising=False)
+        keep = {}
+        out = smin_forward(pk, dims, L_.BF16, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+        torch.cuda.synchronize()
+        res[split] = [o.clone() for o in out] + [keep[f"f{x}{k}"][:n if x == "m" else None].clone()
+                                                 for k in range(1, cfg.layers + 1) for x in ("m", "b")]
+    for x, y in zip(res[False], res[True]):
+        assert torch.equal(x, y)

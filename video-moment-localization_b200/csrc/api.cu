@@ -113,7 +113,8 @@ int content_attention(const void*, const float*, int, int, int, int, const float
                       void*, int, vml_dims_t, int, cudaStream_t);
 int boundary_unit(const float*, int, int, int, const float*, const float*, const float*, const void*,
                   const uint8_t*, const uint8_t*, vml_cells_t, float*, float*, float*, void*, const float*, float*, float*, int,
-                  vml_dims_t, int, cudaStream_t);
+                  vml_dims_t, int, cudaStream_t, void* pair_out = nullptr, int ld_pair = 0);
+bool boundary_pair_fused(vml_dims_t, int);
 // backward.cu
 int colsum(const float*, int64_t, int64_t, float*, int64_t, int, int, int, const int32_t*, int, float, cudaStream_t);
 int localize_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
@@ -374,6 +375,18 @@ VML_API int vml_boundary_unit(const float* qproj, int ld, int off_kbt, int off_b
   VML_PREC_OK(prec);
   return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, ab_scratch, bu,
                        fbar, fbar_bias, prob_out, u_out, B, d, prec, ST(stream));
+}
+
+VML_API int vml_boundary_pair_fused(vml_dims_t d, int prec) { return boundary_pair_fused(d, prec) ? 1 : 0; }
+
+VML_API int vml_boundary_unit_pair(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
+                                   const float* fb, const void* fm, const uint8_t* query_mask, const uint8_t* length_mask,
+                                   vml_cells_t cells, float* g_scratch, float* ab_scratch, float* bu, void* fbar,
+                                   const float* fbar_bias, void* operand, int B, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  VML_CHECK_ARG(operand != nullptr && (reinterpret_cast<uintptr_t>(operand) & 15) == 0);
+  return boundary_unit(qproj, ld, off_kbt, off_betab, fw, fs, fb, fm, query_mask, length_mask, cells, g_scratch, ab_scratch, bu,
+                       fbar, fbar_bias, nullptr, nullptr, B, d, prec, ST(stream), operand, 2 * d.D);
 }
 
 VML_API int vml_moment_operand(const void* cu, const float* bu, vml_cells_t cells, void* operand, vml_dims_t d, int prec, void* stream) {

@@ -792,7 +792,8 @@ template <int D /* 256 or 512 */>
 __global__ void __launch_bounds__(D, 1024 / D)
 boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const bf16* __restrict__ fm,
                               const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
-                              bf16* __restrict__ fbar, const float* __restrict__ fbar_bias, int L, int capacity) {
+                              bf16* __restrict__ fbar, const float* __restrict__ fbar_bias, int L, int capacity,
+                              bf16* __restrict__ pair_out, int ld_pair) {
   __shared__ float s_ab[BSS_L * BSS_L];
   __shared__ int s_rs[BSS_L + 1];
   __shared__ int s_j[BSS_L * BSS_L];
@@ -822,11 +823,11 @@ boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restr
   }
   for (int e = tid; e < ncell; e += blockDim.x) s_j[e] = __ldg(code + n0 + e) & 0xff;
   __syncthreads();
-  if (total <= 0) return;
-  VML_DBG_ASSERT(lo0 >= n0 && lo0 + cnt0 <= n0 + ncell && (cnt1 == 0 || (lo1 >= n0 && lo1 + cnt1 <= n0 + ncell)));
   float bm0[8], bm1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { bm0[e] = 0.f; bm1[e] = 0.f; }
+  if (total > 0) {
+  VML_DBG_ASSERT(lo0 >= n0 && lo0 + cnt0 <= n0 + ncell && (cnt1 == 0 || (lo1 >= n0 && lo1 + cnt1 <= n0 + ncell)));
   for (int q0 = 0; q0 < total; q0 += BSS_CB) {
     if (q0 > 0) {
 #pragma unroll
@@ -859,19 +860,52 @@ boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restr
       }
     }
   }
-  if (cnt0 > 0) {
-    float* o = bu + ((size_t)b * L + row0) * D + col;
-    f8 tot = ld8(o);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) tot.v[e] = tot.v[e] + bm0[e];
-    st8(o, tot);
   }
-  if (cnt1 > 0) {
-    float* o = bu + ((size_t)b * L + row1) * D + col;
-    f8 tot = ld8(o);
+  // bu = (f_bb + f_b) + f_bm for this warp's rows; rows without cells keep what the gate + rows kernel wrote
+  f8 own0, own1;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) tot.v[e] = tot.v[e] + bm1[e];
-    st8(o, tot);
+  for (int e = 0; e < 8; ++e) { own0.v[e] = 0.f; own1.v[e] = 0.f; }
+  if (active && (cnt0 > 0 || pair_out)) {
+    float* o = bu + ((size_t)b * L + row0) * D + col;
+    own0 = ld8(o);
+    if (cnt0 > 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) own0.v[e] = own0.v[e] + bm0[e];
+      st8(o, own0);
+    }
+  }
+  if (active && row1 != row0 && (cnt1 > 0 || pair_out)) {
+    float* o = bu + ((size_t)b * L + row1) * D + col;
+    own1 = ld8(o);
+    if (cnt1 > 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) own1.v[e] = own1.v[e] + bm1[e];
+      st8(o, own1);
+    }
+  }
+  if (pair_out == nullptr) return;
+  // ---- a8, first half of the moment unit's operand: operand[n, 0:D] = bu_i * bu_j (models.py:292-295) for the sample's
+  // cells, while its boundary rows are still in this CTA (moment_pair_kernel re-reads two 2 KB rows per cell from L2: 285 MB
+  // of L2 traffic for 57 MB written on the 640-query Charades pass).  Same product, same rounding.
+  __shared__ __align__(16) float s_bu[BSS_L][D];
+  if (active) {
+    st8(&s_bu[row0][col], own0);
+    if (row1 != row0) st8(&s_bu[row1][col], own1);
+  }
+  __syncthreads();
+  if (!active) return;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int lo = half ? lo1 : lo0, cnt = half ? cnt1 : cnt0;
+    const f8 x = half ? own1 : own0;
+    for (int q = 0; q < cnt; ++q) {
+      const int n = lo + q;
+      const f8 y = ld8(&s_bu[s_j[n - n0]][col]);
+      f8 o;
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) { o.v[e] = x.v[e]; o.v[e + 1] = x.v[e + 1]; ptx::mul2(o.v[e], o.v[e + 1], y.v[e], y.v[e + 1]); }
+      st8(pair_out + (size_t)n * ld_pair + col, o);
+    }
   }
 }
 
@@ -900,10 +934,17 @@ static int launch_stream(const float* ab, const float* fs, const void* fm, vml_c
   return VML_OK;
 }
 
+// the per-sample streaming kernel (fast mode, small maps) can also write the moment operand's first half, bu_i * bu_j
+bool boundary_pair_fused(vml_dims_t d, int prec) {
+  const char* ss_env = getenv("VML_STREAM_SAMPLE");
+  return prec != VML_FP32 && d.L <= BSS_L && (d.D == 256 || d.D == 512) && (ss_env == nullptr || atoi(ss_env) != 0) &&
+         getenv("VML_PAIR_SPLIT") == nullptr;
+}
+
 int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const float* fw, const float* fs,
                   const float* fb, const void* fm, const uint8_t* qmask, const uint8_t* lmask, vml_cells_t cells,
                   float* g_scratch, float* ab_scratch, float* bu, void* fbar, const float* fbar_bias, float* prob_out, float* u_out,
-                  int B, vml_dims_t d, int prec, cudaStream_t st) {
+                  int B, vml_dims_t d, int prec, cudaStream_t st, void* pair_out, int ld_pair) {
   VML_CHECK_ARG(d.Nq <= BMM_MAXQ && d.D % 64 == 0 && d.D <= 64 * BMM_MAXD64 && d.L <= 248 && ld % 4 == 0 && off_kbt % 4 == 0);
   VML_CHECK_ARG(g_scratch != nullptr && ab_scratch != nullptr);
   static bool reg = (register_kernel("boundary_gate_mma_kernel"), register_kernel("boundary_rows_mma_kernel"),
@@ -948,12 +989,13 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
   const int ng = ceil_div(d.D, 256);
   // fast mode, small maps: one CTA per sample (A/B knob: VML_STREAM_SAMPLE=0 selects the warp-per-row kernel)
   const char* ss_env = getenv("VML_STREAM_SAMPLE");
+  VML_CHECK_ARG(pair_out == nullptr || boundary_pair_fused(d, prec));
   if (prec != VML_FP32 && d.L <= BSS_L && (d.D == 256 || d.D == 512) && (ss_env == nullptr || atoi(ss_env) != 0)) {
     static bool reg3 = (register_kernel("boundary_stream_sample_kernel"), true); (void)reg3;
     if (d.D == 512) boundary_stream_sample_kernel<512><<<B, 512, 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
-                                                                      (bf16*)fbar, fbar_bias, d.L, cells.capacity);
+                                                                      (bf16*)fbar, fbar_bias, d.L, cells.capacity, (bf16*)pair_out, ld_pair);
     else boundary_stream_sample_kernel<256><<<B, 256, 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
-                                                           (bf16*)fbar, fbar_bias, d.L, cells.capacity);
+                                                           (bf16*)fbar, fbar_bias, d.L, cells.capacity, (bf16*)pair_out, ld_pair);
     VML_LAUNCHED(n_launched);
     return VML_OK;
   }

@@ -63,6 +63,8 @@ _SIGS = {
     "vml_content_unit_supported": [Dims],
     "vml_content_out": [_P, _P, _P, _P, _P, _P, _P, _P, Cells, _P, Dims, _I, _P],
     "vml_boundary_unit": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
+    "vml_boundary_pair_fused": [Dims, _I],
+    "vml_boundary_unit_pair": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_colsum": [_P, _I64, _I64, _P, _I64, _I, _I, _I, _P, _I, C.c_float, _P],
     "vml_localize_bwd": [_P] * 12 + [Cells, _P, _P, _P, _P, _I, Dims, _P],
     "vml_pair_bwd": [_P, _I, _P, Cells, _P, _I, Dims, _P],

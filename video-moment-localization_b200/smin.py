@@ -451,6 +451,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     # fast mode: the content unit's output bias b_c rides inside fbar (added by the boundary unit before the rounding), so the
     # one-kernel content unit (bc = NULL: residual on the tensor cores) only adds fbar; VML_CU_V1=1 selects the round-1 kernel
     bias_in_fbar = fused and os.environ.get("VML_CU_V1") is None
+    pair_fused = fused and bool(L_.load().vml_boundary_pair_fused(dims, prec))
     n_dev = cells.n_cells
     two_chains = fused and side is not main
     cside = side if two_chains else main
@@ -461,9 +462,14 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         nxt = cur ^ 1
         o = k * lay["blk"]
         # a7 boundary unit (main)
-        call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
-             ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar),
-             ptr(pk[f"cout_b{k}"]) if bias_in_fbar else None, None, None, B, dims, prec, st)
+        if pair_fused:        # ... and the bu_i * bu_j half of the moment operand, while the sample's boundary rows are on the SM
+            call("vml_boundary_unit_pair", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]),
+                 ptr(fm[cur]), ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar),
+                 ptr(pk[f"cout_b{k}"]) if bias_in_fbar else None, ptr(mu_op), B, dims, prec, st)
+        else:
+            call("vml_boundary_unit", ptr(qproj), ld, o + 2 * dl, o + 2 * dl + D + 1, ptr(fw), ptr(fs), ptr(fb[cur]), ptr(fm[cur]),
+                 ptr(qmask), ptr(lmask), cells, ptr(g_scr), ptr(ab_scr), ptr(fb[nxt]), ptr(fbar),
+                 ptr(pk[f"cout_b{k}"]) if bias_in_fbar else None, None, None, B, dims, prec, st)
         mark("boundary_unit")
         ev_bu = None
         if two_chains:
@@ -498,7 +504,9 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
                      ptr(fc[cur]), ptr(fm[cur]), ptr(fs), ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
                 mark("content_out_gemm")
         # a8 moment unit (main)
-        if fused:
+        if pair_fused:
+            pass
+        elif fused:
             call("vml_moment_pair", ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
         else:
             call("vml_moment_operand", ptr(fc[nxt]), ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
