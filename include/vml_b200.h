@@ -283,6 +283,14 @@ VML_API int vml_moment_pair(const float* bu, vml_cells_t cells, void* operand, v
 /* mu = operand.[Wfb|Wfc]^T + (bfb+bfc) + fm */
 VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* bias_sum, const void* fm,
                    vml_cells_t cells, void* mu, vml_dims_t d, int prec, void* stream);
+/* Same product with the bu[b,i] * bu[b,j] half of the operand generated INSIDE the GEMM from the boundary rows bu float [B, L, D]
+ * (four extra warps write those k-blocks of the A operand straight into the pipeline stages, rounded to the activation type as
+ * vml_moment_pair rounds them): operand[n, 0:D] is neither written nor read, only operand[n, D:2D] = mean_c cu is loaded.
+ * Only where vml_moment_gen_supported(d, prec) returns 1 (VML_BF16, D a multiple of 64); bit-identical to vml_moment_pair +
+ * vml_moment_out. */
+VML_API int vml_moment_gen_supported(vml_dims_t d, int prec);
+VML_API int vml_moment_out_gen(const void* operand, const void* Wcat, const float* bias_sum, const void* fm, vml_cells_t cells,
+                               const float* bu, void* mu, int B, vml_dims_t d, int prec, void* stream);
 
 /* ---- a9: Localization (models.py:335-344) ------------------------------------------------------ */
 

@@ -345,3 +345,29 @@ def test_pair_products_from_the_boundary_kernel_are_bit_identical(name, B, kw, m
                                                  for k in range(1, cfg.layers + 1) for x in ("m", "b")]
     for x, y in zip(res[False], res[True]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,B,kw", [("charadessta", 9, {}), ("charadessta", 64, {}), ("tacos", 5, {}), ("activitynet", 3, {}),
+                                       ("charadessta", 5, {"nfeats_range": (1, 9)}), ("charadessta", 3, {"full_length": True}),
+                                       ("tiny", 5, {})])
+def test_moment_gemm_with_generated_pair_operand_is_bit_identical(name, B, kw, monkeypatch):
+    """vml_moment_out_gen (four generator warps write the bu_i * bu_j k-blocks of the A operand straight into the GEMM's
+    pipeline stages) against the path that materialises the pair tensor (VML_MOMENT_GEN=0: boundary kernel / vml_moment_pair,
+    then vml_moment_out): every layer's fm / fb and the scores bit for bit, over 128- and 256-wide tiles, ragged last tiles
+    and tiles spanning several samples."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    dims = dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, L_.BF16, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 9191, **kw))
+    n = int(batch["moment_mask"].sum().item())
+    res = {}
+    for gen in ("1", "0"):
+        monkeypatch.setenv("VML_MOMENT_GEN", gen)
+        keep = {}
+        out = smin_forward(pk, dims, L_.BF16, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+        torch.cuda.synchronize()
+        res[gen] = [o.clone() for o in out] + [keep[f"f{x}{k}"][:n if x == "m" else None].clone()
+                                               for k in range(1, cfg.layers + 1) for x in ("m", "b")]
+    for x, y in zip(res["1"], res["0"]):
+        assert torch.equal(x, y)

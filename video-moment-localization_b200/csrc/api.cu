@@ -422,6 +422,26 @@ VML_API int vml_moment_out(const void* operand, const void* Wcat, const float* b
   return gemm_dispatch(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, prec, ST(stream));
 }
 
+// Opt-in (VML_MOMENT_GEN=1).  Validated bit-identical on B200 (GPU test) and measured 2.4x SLOWER (20.9 -> 50.9 us per step on
+// the 640-query Charades pass): with 222 KB of the SM's 256 KB in use as shared memory the L1 is ~30 KB, so the generator warps'
+// boundary-row loads go to L2 (~700 cycles under load) and the 80-register budget of the 704-thread CTA lets a lane keep only
+// one of its eight row chunks in flight: ~2 us per generated k-block against a 0.7 us stage cadence.  It would need the
+// tile's boundary rows staged in shared memory (64 KB that the pipeline + epilogue scratch do not leave).
+static bool moment_gen_ok(vml_dims_t d, int prec) {
+  const char* e = getenv("VML_MOMENT_GEN");
+  return prec == VML_BF16 && d.D % 64 == 0 && d.L <= 255 && e != nullptr && atoi(e) != 0;
+}
+VML_API int vml_moment_gen_supported(vml_dims_t d, int prec) { return moment_gen_ok(d, prec) ? 1 : 0; }
+
+VML_API int vml_moment_out_gen(const void* operand, const void* Wcat, const float* bias_sum, const void* fm, vml_cells_t cells,
+                               const float* bu, void* mu, int B, vml_dims_t d, int prec, void* stream) {
+  VML_PREC_OK(prec);
+  VML_CHECK_ARG(moment_gen_ok(d, prec) && bu != nullptr && (int64_t)B * d.L * d.D < (int64_t)1 << 31 &&
+                (reinterpret_cast<uintptr_t>(bu) & 15) == 0);
+  EpiMomentOutGen e{{bias_sum, (const bf16*)fm, (bf16*)mu, d.D, 0, cells.capacity}, bu, cells.code, d.L, d.D};
+  return launch_gemm_umma(operand, Wcat, cells.capacity, d.D, 2 * d.D, 2 * d.D, 2 * d.D, cells.n_cells, 1, e, ST(stream));
+}
+
 VML_API int vml_localize(const void* fm, const float* fb, const float* w4, const float* b4, vml_cells_t cells,
                  const uint8_t* length_mask, float* pm, float* ps, float* pe, float* pa, int B, vml_dims_t d, int prec,
                  void* stream) {

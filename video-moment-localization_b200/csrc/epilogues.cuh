@@ -409,4 +409,48 @@ struct EpiClipT {
   }
 };
 
+// a8 with the bu_i * bu_j half of the operand GENERATED inside the GEMM (models.py:292-295 + :296-303): four extra warps write
+// the A box of the first D/64 k-blocks straight into the pipeline stage -- element (r, k) = bu[b_r, i_r][64 kb + k] *
+// bu[b_r, j_r][64 kb + k], rounded to bf16 exactly as vml_moment_pair rounds it -- so the pair tensor is neither written to
+// nor read from HBM (57 MB each way per layer on the 640-query Charades pass).  A lane owns one 16-byte chunk (8 columns) of
+// 8 rows of the tile: every load of a warp covers 4 rows x 128 contiguous bytes of the (L1-resident) boundary rows.
+struct EpiMomentOutGen : EpiMomentOutT {
+  static constexpr int kGenWarps = 4;
+  const float* bu;        // [B, L, D] fp32
+  const int32_t* code;    // [n] cell codes b<<16 | i<<8 | j
+  int L, D;
+  struct Gen { int oi[8], oj[8]; };            // element offsets of this lane's 8 rows' bu_i / bu_j rows (-1: row past the live count)
+  __device__ __forceinline__ bool gen_kblock(int kb) const { return kb * 64 < D; }
+  __device__ __forceinline__ void gen_setup(Gen& g, int m0, int gw, int lane, int M) const {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = m0 + gw * 32 + 4 * it + (lane >> 3);
+      int oi = -1, oj = -1;
+      if (row < M) {
+        const int cd = __ldg(code + row);
+        const int b = cd >> 16, i = (cd >> 8) & 0xff, j = cd & 0xff;
+        oi = (b * L + i) * D; oj = (b * L + j) * D;
+      }
+      g.oi[it] = oi; g.oj[it] = oj;
+    }
+  }
+  __device__ __forceinline__ void gen_fill(const Gen& g, unsigned char* sa, int kb, int gw, int lane) const {
+    const int p = lane & 7, col = kb * 64 + p * 8;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = gw * 32 + 4 * it + (lane >> 3);
+      f8 o;
+      if (g.oi[it] >= 0) {
+        const f8 x = ld8(bu + g.oi[it] + col), y = ld8(bu + g.oj[it] + col);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = x.v[e] * y.v[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = 0.f;
+      }
+      st8(reinterpret_cast<bf16*>(sa + r * 128 + ((p ^ (r & 7)) << 4)), o);
+    }
+  }
+};
+
 }  // namespace vml

@@ -53,6 +53,14 @@ struct epi_scratch : std::integral_constant<int, 0> {};
 template <typename E>
 struct epi_scratch<E, std::void_t<decltype(E::kScratchPerWarp)>> : std::integral_constant<int, E::kScratchPerWarp> {};
 
+// an epilogue may GENERATE the leading k-blocks of the A operand on the SM instead of having them loaded (kGenWarps extra
+// warps write the 128 x 64 bf16 box of such a k-block in the 128B-swizzled layout TMA would have produced; the stage's full
+// barrier then also counts one arrival per generator warp).  Single-CTA kernel only.
+template <typename E, typename = void>
+struct epi_gen : std::integral_constant<int, 0> {};
+template <typename E>
+struct epi_gen<E, std::void_t<decltype(E::kGenWarps)>> : std::integral_constant<int, E::kGenWarps> {};
+
 template <typename E, typename = void>
 struct epi_has_pre : std::false_type {};
 template <typename E>
@@ -84,10 +92,12 @@ struct UmmaCfg {
 // 32 elements instead of 64, an MMA covers K = 8 instead of 16 -- the same 32 bytes per step, so only the K arithmetic, the
 // instruction descriptor and the instruction kind differ.
 template <int BN, typename Epi, int CL = 1, int EW = UG_EPI_WARPS, bool TF32 = false>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+__global__ void __launch_bounds__(64 + 32 * EW + 32 * epi_gen<Epi>::value, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  const int32_t* __restrict__ m_dev, int m_scale, Epi epi) {
   static_assert(CL == 1 || CL == 2, "single CTA or 2-CTA cluster");
+  constexpr int GW = epi_gen<Epi>::value;
+  static_assert(GW == 0 || (GW == 4 && CL == 1 && !TF32), "operand generator: 4 warps = 128 tile rows, single CTA, bf16");
   using Cfg = UmmaCfg<BN, EW * epi_scratch<Epi>::value>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: keeps the shared address space visible to the
@@ -114,7 +124,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
-    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], CL); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1 + GW); ptx::mbar_init(&empty_bar[s], CL); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], EW); }
     ptx::fence_barrier_init();
   }
@@ -140,8 +150,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);      // CL == 2: both CTAs' MMAs have retired from this stage
           unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          bool gen_a = false;
+          if constexpr (GW > 0) gen_a = epi.gen_kblock(kb);  // this k-block's A box is written by the generator warps
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], gen_a ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
+          if (!gen_a) ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
           if (CL == 2)                                       // my half of the B tile, to both CTAs of the cluster
             ptx::tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
                                 n0 + crank * (BN / 2), (uint16_t)3);
@@ -178,6 +190,28 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (GW > 0 && warp >= 2 + EW) {
+    // ===================== operand generator warps =====================
+    if constexpr (GW > 0) {
+      const int gw = warp - 2 - EW;
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m0 = tile_m0(tile);
+        typename Epi::Gen g;
+        epi.gen_setup(g, m0, gw, lane, M);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          // (always: an arrival for the stage's NEXT use must not land in the phase of its current one)
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);      // the MMAs that read this stage have retired
+          if (epi.gen_kblock(kb)) {
+            epi.gen_fill(g, smem + stage * Cfg::STAGE_BYTES, kb, gw, lane);
+            ptx::fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -470,12 +504,12 @@ int launch_gemm_umma_bn(const void* A, const void* W, int M, int N, int K, int l
         VML_CUDA(ensure_dyn_smem((const void*)(gemm_umma_kernel<BN, Epi, 1, 16>), (size_t)(Cfg16::SMEM_BYTES)));
         attr16 = true;
       }
-      gemm_umma_kernel<BN, Epi, 1, 16><<<grid, 64 + 32 * 16, Cfg16::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+      gemm_umma_kernel<BN, Epi, 1, 16><<<grid, 64 + 32 * 16 + 32 * epi_gen<Epi>::value, Cfg16::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
       VML_LAUNCHED(1);
       return VML_OK;
     }
   }
-  gemm_umma_kernel<BN, Epi><<<grid, UG_GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
+  gemm_umma_kernel<BN, Epi><<<grid, UG_GEMM_THREADS + 32 * epi_gen<Epi>::value, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, m_dev, m_scale, epi);
   VML_LAUNCHED(1);
   return VML_OK;
 }

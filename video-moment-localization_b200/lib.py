@@ -81,6 +81,8 @@ _SIGS = {
     "vml_moment_pair": [_P, Cells, _P, Dims, _I, _P],
     "vml_moment_operand": [_P, _P, Cells, _P, Dims, _I, _P],
     "vml_moment_out": [_P, _P, _P, _P, Cells, _P, Dims, _I, _P],
+    "vml_moment_gen_supported": [Dims, _I],
+    "vml_moment_out_gen": [_P, _P, _P, _P, Cells, _P, _P, _I, Dims, _I, _P],
     "vml_localize": [_P, _P, _P, _P, Cells, _P, _P, _P, _P, _P, _I, Dims, _I, _P],
     "vml_scaled_iou_bce": [_P] * 13 + [_I, _I] + [_P] * 7 + [_P],
     "vml_score_topk_recall": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],

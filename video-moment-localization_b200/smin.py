@@ -451,7 +451,10 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
     # fast mode: the content unit's output bias b_c rides inside fbar (added by the boundary unit before the rounding), so the
     # one-kernel content unit (bc = NULL: residual on the tensor cores) only adds fbar; VML_CU_V1=1 selects the round-1 kernel
     bias_in_fbar = fused and os.environ.get("VML_CU_V1") is None
-    pair_fused = fused and bool(L_.load().vml_boundary_pair_fused(dims, prec))
+    # the bu_i * bu_j half of the moment operand: generated inside the moment GEMM (no pair tensor at all), else written by the
+    # boundary unit's per-sample streaming kernel, else by vml_moment_pair
+    pair_gen = fused and bool(L_.load().vml_moment_gen_supported(dims, prec))
+    pair_fused = fused and not pair_gen and bool(L_.load().vml_boundary_pair_fused(dims, prec))
     n_dev = cells.n_cells
     two_chains = fused and side is not main
     cside = side if two_chains else main
@@ -504,7 +507,7 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
                      ptr(fc[cur]), ptr(fm[cur]), ptr(fs), ptr(fbar), ptr(mu_op) if fused else None, cells, ptr(fc[nxt]), dims, prec, sst)
                 mark("content_out_gemm")
         # a8 moment unit (main)
-        if pair_fused:
+        if pair_fused or pair_gen:
             pass
         elif fused:
             call("vml_moment_pair", ptr(fb[nxt]), cells, ptr(mu_op), dims, prec, st)
@@ -513,7 +516,12 @@ def smin_core(pk: Dict[str, torch.Tensor], dims: Dims, prec: int, ws: Workspace,
         mark("moment_operand")
         if two_chains:
             join(side, main)                    # cu half of the operand
-        call("vml_moment_out", ptr(mu_op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(fm[cur]), cells, ptr(fm[nxt]), dims, prec, st)
+        if pair_gen:
+            call("vml_moment_out_gen", ptr(mu_op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(fm[cur]), cells, ptr(fb[nxt]),
+                 ptr(fm[nxt]), B, dims, prec, st)
+        else:
+            call("vml_moment_out", ptr(mu_op), ptr(pk[f"mu_w{k}"]), ptr(pk[f"mu_b{k}"]), ptr(fm[cur]), cells, ptr(fm[nxt]), dims,
+                 prec, st)
         mark("moment_out_gemm")
         cur = nxt
         if keep is not None:
