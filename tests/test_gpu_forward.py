@@ -213,6 +213,7 @@ def test_one_kernel_content_unit_against_split(name, B, rng, variant, monkeypatc
 
 @pytest.mark.parametrize("name,prec,B,kw", [("charadessta", "bf16", 9, {}), ("charadessta", "bf16", 6, {"nfeats_range": (1, 9)}),
                                             ("charadessta", "bf16", 5, {"full_length": True}), ("tacos", "bf16", 4, {}),
+                                            ("activitynet", "bf16", 3, {}), ("activitynet", "bf16", 3, {"nfeats_range": (3, 40)}),
                                             ("charadessta", "fp32", 4, {}), ("tiny", "bf16", 5, {})])
 def test_boundary_schedules_are_bit_identical(name, prec, B, kw, monkeypatch):
     """The schedule knobs of the boundary unit change WHEN things are loaded, never what is computed: rows staged by
@@ -320,7 +321,8 @@ def test_transposing_gemm_epilogues_are_bit_identical(name, B, kw, monkeypatch):
         assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("name,B,kw", [("charadessta", 9, {}), ("charadessta", 64, {}), ("tacos", 5, {}),
+@pytest.mark.parametrize("name,B,kw", [("charadessta", 9, {}), ("charadessta", 64, {}), ("tacos", 5, {}), ("activitynet", 3, {}),
+                                       ("activitynet", 2, {"nfeats_range": (3, 40)}), ("tacos", 3, {"full_length": True}),
                                        ("charadessta", 5, {"nfeats_range": (1, 9)}), ("charadessta", 3, {"full_length": True}),
                                        ("tiny", 5, {})])
 def test_pair_products_from_the_boundary_kernel_are_bit_identical(name, B, kw, monkeypatch):

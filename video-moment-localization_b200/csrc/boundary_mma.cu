@@ -786,7 +786,7 @@ boundary_stream_kernel(const float* __restrict__ ab, const float* __restrict__ f
 // sample's attention rows, row offsets and cell codes are staged in shared memory once per CTA (two round trips for up to
 // 136 cells x 1 KB), a warp owns the row PAIR (p, L - 1 - p) of one 256-column group -- L + 1 cells for a full-length
 // video whatever p is -- and streams them four at a time with the weights read from shared memory.
-constexpr int BSS_L = 16, BSS_CB = 4;
+constexpr int BSS_L = 16, BSS_CB = 4, BSS_LBIG = 64;
 
 template <int D /* 256 or 512 */>
 __global__ void __launch_bounds__(D, 1024 / D)
@@ -909,6 +909,117 @@ boundary_stream_sample_kernel(const float* __restrict__ ab, const float* __restr
   }
 }
 
+// ---- the same per-sample schedule for larger maps (16 < L <= 64: TACoS, ActivityNet) -----------------------------------------
+// Dynamic shared memory (attention rows L x L, cell columns as bytes, and -- for the pair products -- an L x D fp32 copy of
+// the sample's final boundary rows: 128 KB at L = 64, one CTA per SM); a warp walks the row pairs (p, L - 1 - p),
+// p = slot, slot + 8, ... of its 256-column group.  Same arithmetic in the same order as boundary_stream_kernel /
+// moment_pair_kernel: bit-identical.
+template <int D /* 256 or 512 */>
+__global__ void __launch_bounds__(D, 1)
+boundary_stream_sample_big_kernel(const float* __restrict__ ab, const float* __restrict__ fs, const bf16* __restrict__ fm,
+                                  const int32_t* __restrict__ code, const int32_t* __restrict__ row_start, float* __restrict__ bu,
+                                  bf16* __restrict__ fbar, const float* __restrict__ fbar_bias, int L, int capacity,
+                                  bf16* __restrict__ pair_out, int ld_pair) {
+  extern __shared__ __align__(16) unsigned char bsb_raw[];
+  float* s_bu = reinterpret_cast<float*>(bsb_raw);                          // [L][D]   (pair_out only)
+  float* s_bias = s_bu + (pair_out ? (size_t)L * D : 0);                    // [D]
+  float* s_ab = s_bias + D;                                                 // [L][L]
+  int* s_rs = reinterpret_cast<int*>(s_ab + L * L);                         // [L + 1]
+  uint8_t* s_j = reinterpret_cast<uint8_t*>(s_rs + L + 1);                  // [L * L]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  constexpr int NG = D / 256;
+  const int g = warp % NG, slot = warp / NG;                     // column group, first row pair; 8 pair slots per CTA
+  for (int e = tid; e <= L; e += blockDim.x) s_rs[e] = min(__ldg(row_start + (size_t)b * L + e), capacity);
+  for (int e = tid; e < L * L; e += blockDim.x) s_ab[e] = __ldg(ab + (size_t)b * L * L + e);
+  for (int e = tid; e < D; e += blockDim.x) s_bias[e] = fbar_bias ? __ldg(fbar_bias + e) : 0.f;
+  const int col = g * 256 + lane * 8;
+  f8 s8 = ld8(fs + (size_t)b * D + col);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s8.v[e] *= kNegLog2e;              // see gate2_fast
+  __syncthreads();
+  const int n0 = s_rs[0], ncell = min(s_rs[L] - n0, L * L);
+  for (int e = tid; e < ncell; e += blockDim.x) s_j[e] = (uint8_t)(__ldg(code + n0 + e) & 0xff);
+  __syncthreads();
+  const int npairs = (L + 1) / 2;
+  for (int p = slot; p < npairs; p += 8) {
+    const int row0 = p, row1 = L - 1 - p;
+    const int lo0 = s_rs[row0], cnt0 = s_rs[row0 + 1] - lo0;
+    const int lo1 = row1 != row0 ? s_rs[row1] : 0, cnt1 = row1 != row0 ? s_rs[row1 + 1] - lo1 : 0;
+    const int total = cnt0 + cnt1;
+    auto cell_of = [&](int q) { q = min(q, total - 1); return q < cnt0 ? lo0 + q : lo1 + (q - cnt0); };
+    float bm0[8], bm1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { bm0[e] = 0.f; bm1[e] = 0.f; }
+    for (int q0 = 0; q0 < total; q0 += BSS_CB) {
+      uint4 m[BSS_CB];
+#pragma unroll
+      for (int u = 0; u < BSS_CB; ++u) m[u] = __ldg(reinterpret_cast<const uint4*>(fm + (size_t)cell_of(q0 + u) * D + col));
+#pragma unroll
+      for (int u = 0; u < BSS_CB; ++u) {
+        const int q = q0 + u;
+        if (q < total) {                                   // warp-uniform
+          const bool second = q >= cnt0;
+          const int n = second ? lo1 + (q - cnt0) : lo0 + q;
+          VML_DBG_ASSERT(n >= n0 && n - n0 < ncell);
+          const float a = s_ab[(second ? row1 : row0) * L + s_j[n - n0]];
+          const f8 x8 = unpack8(m[u]);
+          f8 gv;
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) gate2_fast(x8.v[e], x8.v[e + 1], s8.v[e], s8.v[e + 1], gv.v[e], gv.v[e + 1]);
+          if (second) {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) ptx::fma2(bm1[e], bm1[e + 1], a, a, gv.v[e], gv.v[e + 1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) ptx::fma2(bm0[e], bm0[e + 1], a, a, gv.v[e], gv.v[e + 1]);
+          }
+          if (fbar) {
+            const f8 fb8 = ld8(s_bias + col);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) ptx::add2(gv.v[e], gv.v[e + 1], fb8.v[e], fb8.v[e + 1]);
+            st8(fbar + (size_t)n * D + col, gv);
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {                 // bu = (f_bb + f_b) + f_bm; rows without cells keep what the rows kernel wrote
+      const int row = half ? row1 : row0, cnt = half ? cnt1 : cnt0;
+      if (half && row1 == row0) break;
+      if (cnt > 0 || pair_out) {
+        float* o = bu + ((size_t)b * L + row) * D + col;
+        f8 own = ld8(o);
+        if (cnt > 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) own.v[e] = own.v[e] + (half ? bm1[e] : bm0[e]);
+          st8(o, own);
+        }
+        if (pair_out) st8(s_bu + (size_t)row * D + col, own);
+      }
+    }
+  }
+  if (pair_out == nullptr) return;
+  __syncthreads();
+  // ---- operand[n, 0:D] = bu_i * bu_j for the sample's cells (models.py:292-295) ----
+  for (int p = slot; p < npairs; p += 8) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int row = half ? L - 1 - p : p;
+      if (half && row == p) break;
+      const int lo = s_rs[row], cnt = s_rs[row + 1] - lo;
+      const f8 x = ld8(s_bu + (size_t)row * D + col);
+      for (int q = 0; q < cnt; ++q) {
+        const int n = lo + q;
+        const f8 y = ld8(s_bu + (size_t)s_j[n - n0] * D + col);
+        f8 o;
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { o.v[e] = x.v[e]; o.v[e + 1] = x.v[e + 1]; ptx::mul2(o.v[e], o.v[e + 1], y.v[e], y.v[e + 1]); }
+        st8(pair_out + (size_t)n * ld_pair + col, o);
+      }
+    }
+  }
+}
+
 template <bool PRECISE>
 static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, float* bu, float* ab, int B, vml_dims_t d,
                        cudaStream_t st) {
@@ -937,7 +1048,7 @@ static int launch_stream(const float* ab, const float* fs, const void* fm, vml_c
 // the per-sample streaming kernel (fast mode, small maps) can also write the moment operand's first half, bu_i * bu_j
 bool boundary_pair_fused(vml_dims_t d, int prec) {
   const char* ss_env = getenv("VML_STREAM_SAMPLE");
-  return prec != VML_FP32 && d.L <= BSS_L && (d.D == 256 || d.D == 512) && (ss_env == nullptr || atoi(ss_env) != 0) &&
+  return prec != VML_FP32 && d.L <= BSS_LBIG && (d.D == 256 || d.D == 512) && (ss_env == nullptr || atoi(ss_env) != 0) &&
          getenv("VML_PAIR_SPLIT") == nullptr;
 }
 
@@ -996,6 +1107,22 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
                                                                       (bf16*)fbar, fbar_bias, d.L, cells.capacity, (bf16*)pair_out, ld_pair);
     else boundary_stream_sample_kernel<256><<<B, 256, 0, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
                                                            (bf16*)fbar, fbar_bias, d.L, cells.capacity, (bf16*)pair_out, ld_pair);
+    VML_LAUNCHED(n_launched);
+    return VML_OK;
+  }
+  if (prec != VML_FP32 && d.L <= BSS_LBIG && (d.D == 256 || d.D == 512) && (ss_env == nullptr || atoi(ss_env) != 0)) {
+    static bool reg4 = (register_kernel("boundary_stream_sample_big_kernel"), true); (void)reg4;
+    const size_t smem = sizeof(float) * ((pair_out ? (size_t)d.L * d.D : 0) + d.D + (size_t)d.L * d.L) + sizeof(int) * (d.L + 1) +
+                        (size_t)d.L * d.L + 16;
+    if (d.D == 512) {
+      VML_CUDA(ensure_dyn_smem((const void*)(boundary_stream_sample_big_kernel<512>), (size_t)((int)smem)));
+      boundary_stream_sample_big_kernel<512><<<B, 512, smem, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
+                                                                 (bf16*)fbar, fbar_bias, d.L, cells.capacity, (bf16*)pair_out, ld_pair);
+    } else {
+      VML_CUDA(ensure_dyn_smem((const void*)(boundary_stream_sample_big_kernel<256>), (size_t)((int)smem)));
+      boundary_stream_sample_big_kernel<256><<<B, 256, smem, st>>>(ab_scratch, fs, (const bf16*)fm, cells.code, cells.row_start, bu,
+                                                                 (bf16*)fbar, fbar_bias, d.L, cells.capacity, (bf16*)pair_out, ld_pair);
+    }
     VML_LAUNCHED(n_launched);
     return VML_OK;
   }
