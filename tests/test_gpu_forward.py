@@ -373,3 +373,31 @@ def test_moment_gemm_with_generated_pair_operand_is_bit_identical(name, B, kw, m
                                                for k in range(1, cfg.layers + 1) for x in ("m", "b")]
     for x, y in zip(res["1"], res["0"]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("name,prec,B,kw", [("tacos", "bf16", 5, {}), ("activitynet", "bf16", 3, {}), ("activitynet", "fp32", 2, {}),
+                                            ("tacos", "fp32", 3, {}), ("activitynet", "bf16", 3, {"nfeats_range": (3, 40)})])
+def test_per_sample_rows_kernel_matches_tiled_rows_kernel(name, prec, B, kw, monkeypatch):
+    """boundary_rows_big_kernel (16 < L <= 64: the sample's rows resident in shared memory, full-depth score tiles per warp)
+    against boundary_rows_mma_kernel (VML_ROWS_TILED=1: 16-row CTAs, split-K partials).  Same formulas; the score sums are
+    associated differently, so the comparison is to rounding: 1e-5 of scale in the fp32 (3xTF32) mode, bf16-level in fast mode
+    -- and both are held to the oracle by the parity tests above."""
+    from vml_b200.smin import Workspace, pack_weights, smin_forward
+    cfg = CONFIGS[name]
+    p, dims = L_.PREC[prec], dims_of(cfg)
+    pk = pack_weights(init_params(cfg, 43), dims, p, torch.device("cuda"))
+    batch = to_dev(synth.make_batch(cfg, B, 1212, **kw))
+    res = {}
+    for tiled in (False, True):
+        if tiled:
+            monkeypatch.setenv("VML_ROWS_TILED", "1")
+        else:
+            monkeypatch.delenv("VML_ROWS_TILED", raising=False)
+        keep = {}
+        out = smin_forward(pk, dims, p, Workspace(torch.device("cuda")), *[batch[k] for k in synth.MODEL_INPUT_KEYS], keep=keep)
+        torch.cuda.synchronize()
+        res[tiled] = [o.clone() for o in out] + [keep[f"fb{k}"].clone() for k in range(1, cfg.layers + 1)]
+    tol = 1e-5 if prec == "fp32" else 4e-3
+    for x, y in zip(res[False], res[True]):
+        assert scaled_err(x, y) < tol, scaled_err(x, y)
+        assert torch.equal(x == 0, y == 0)

@@ -1020,9 +1020,168 @@ boundary_stream_sample_big_kernel(const float* __restrict__ ab, const float* __r
   }
 }
 
+// ---- rows, one CTA per SAMPLE for larger maps (16 < L <= 64) ------------------------------------------------------------------
+// boundary_rows_mma_kernel gives every 16 map rows their own CTA, each of which re-stages ALL keys and values of the sample --
+// within ~100 KB, i.e. 8 rows at a time at D = 512: 16 barrier-separated staging rounds of 16 KB per CTA and four copies of
+// the sample's 256 KB per layer (ActivityNet: ~0.4 ms per layer at 640 queries).  Here the sample's L gated rows sit in
+// shared memory at once (cp.async.bulk, 132 KB at L = 64, D = 512), every warp owns whole 16 x 16 score tiles over the FULL
+// contraction (no split-K partials, no reduction), and the same buffer is re-filled with the value rows f_b for the second
+// product.  Same formulas as boundary_rows_mma_kernel; the score sums are associated differently (one chain over D instead
+// of eight partial chains), so results agree to rounding, not bit for bit.
+constexpr int BRB_THREADS = 512, BRB_WARPS = 16, BRB_L = 64;
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(BRB_THREADS, 1)
+boundary_rows_big_kernel(const float* __restrict__ G, const float* __restrict__ fb, const uint8_t* __restrict__ lmask,
+                         float* __restrict__ bu, float* __restrict__ ab_out, int L, int D) {
+  extern __shared__ __align__(16) float brb[];
+  const int DS = D + 4;
+  const int LP = (L + 7) & ~7, MT = (L + 15) / 16, LS = BRB_L + 1;
+  float* Rs = brb;                                  // [MT * 16][DS]  gated rows G, later the value rows f_b
+  float* Ab = Rs + (size_t)MT * 16 * DS;             // [MT * 16][LS]  scores, then attention rows
+  __shared__ __align__(8) uint64_t bar[2];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
+  const float* Gb = G + (size_t)b * L * D;
+  const float* fbb = fb + (size_t)b * L * D;
+  if (tid == 0) { ptx::mbar_init(&bar[0], 1); ptx::mbar_init(&bar[1], 1); ptx::fence_barrier_init(); }
+  for (int e = tid; e < (MT * 16 - L) * (D / 4); e += BRB_THREADS) {       // rows past L: zero (they are MMA operands)
+    const int rr = L + e / (D / 4), c4 = (e % (D / 4)) * 4;
+    *reinterpret_cast<float4*>(Rs + (size_t)rr * DS + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  auto stage = [&](const float* src, uint64_t* mb) {                      // the sample's L rows -> Rs, one bulk copy per row
+    if (warp == 0) {
+      if (lane == 0) ptx::mbar_arrive_expect_tx(mb, (uint32_t)(L * D) * 4u);
+      __syncwarp();
+      for (int r = lane; r < L; r += 32) ptx::bulk_load_1d(Rs + (size_t)r * DS, src + (size_t)r * D, (uint32_t)D * 4u, mb);
+    }
+  };
+  stage(Gb, &bar[0]);
+  ptx::mbar_wait(&bar[0], 0);
+  // ---- S = G . G^T over the full D: a warp owns (16-row tile, pair of 8-key tiles) items ----------------------------------
+  const int NT = LP / 8, NP = (NT + 1) / 2;
+  for (int item = warp; item < MT * NP; item += BRB_WARPS) {
+    const int mt = item / NP, n0 = (item % NP) * 2;
+    const bool two = n0 + 1 < NT;
+    float acc[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    const float* ra = Rs + (size_t)(mt * 16 + g) * DS;
+    const float* rb0 = Rs + (size_t)(n0 * 8 + g) * DS;
+    const float* rb1 = Rs + (size_t)((two ? n0 + 1 : n0) * 8 + g) * DS;
+#pragma unroll 4
+    for (int k0 = 0; k0 < D; k0 += 8) {
+      const float a[4] = {ra[k0 + t], ra[8 * DS + k0 + t], ra[k0 + t + 4], ra[8 * DS + k0 + t + 4]};
+      const float b0[2] = {rb0[k0 + t], rb0[k0 + t + 4]};
+      const float b1[2] = {rb1[k0 + t], rb1[k0 + t + 4]};
+      mma_16x8x8<PRECISE>(acc[0], a, b0);
+      mma_16x8x8<PRECISE>(acc[1], a, b1);
+    }
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      if (n == 0 || two) {
+        float* p0 = Ab + (size_t)(mt * 16 + g) * LS + (n0 + n) * 8 + 2 * t;
+        p0[0] = acc[n][0]; p0[1] = acc[n][1]; p0[8 * LS] = acc[n][2]; p0[8 * LS + 1] = acc[n][3];
+      }
+    }
+  }
+  ptx::fence_proxy_async();                          // this thread's reads of G are ordered before the bulk copies that overwrite it
+  __syncthreads();                                   // scores complete; every warp is done reading G
+  stage(fbb, &bar[1]);                               // value rows over the gated rows, under the softmax
+  // ---- masked softmax over the keys (models.py:176-184): a warp per row, lanes over keys -------------------------------
+  {
+    const float sqrt_d = sqrtf((float)D);
+    for (int i = warp; i < L; i += BRB_WARPS) {
+      const bool row_on = lmask[(size_t)b * L + i] != 0;
+      float* arow = Ab + (size_t)i * LS;
+      float sc[2], mx = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        sc[h] = -INFINITY;
+        if (j < L) {
+          const float mk = lmask[(size_t)b * L + j] ? 1.f : 0.f;
+          sc[h] = (arow[j] / sqrt_d) * mk;
+          if (mk == 0.f) sc[h] = -1e9f;
+        }
+        mx = fmaxf(mx, sc[h]);
+      }
+      mx = warp_max(mx);
+      float ex[2], den = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { ex[h] = lane + 32 * h < L ? expf(sc[h] - mx) : 0.f; den += ex[h]; }
+      den = warp_sum(den);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        if (j < LP) {
+          const float v = (row_on && j < L) ? ex[h] / den : 0.f;
+          arow[j] = v;
+          if (j < L) ab_out[((size_t)b * L + i) * L + j] = v;
+        }
+      }
+    }
+    for (int e = tid; e < (MT * 16 - L) * LP; e += BRB_THREADS) Ab[(size_t)(L + e / LP) * LS + e % LP] = 0.f;   // padded rows
+  }
+  __syncthreads();
+  ptx::mbar_wait(&bar[1], 0);
+  // ---- f_bb = A_b . f_b, bu = f_bb + f_b: a warp owns D / 16 columns of every row tile ------------------------------------
+  {
+    const int cpw = D / BRB_WARPS, ntd = cpw / 8;      // columns per warp (32 at D = 512), 8-column tiles
+    for (int mt = 0; mt < MT; ++mt) {
+      float acc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+      const float* aa = Ab + (size_t)(mt * 16 + g) * LS;
+      for (int k0 = 0; k0 < LP; k0 += 8) {
+        const float a[4] = {aa[k0 + t], aa[8 * LS + k0 + t], aa[k0 + t + 4], aa[8 * LS + k0 + t + 4]};
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          if (n < ntd) {
+            const int col = warp * cpw + n * 8 + g;
+            const float bf[2] = {Rs[(size_t)(k0 + t) * DS + col], Rs[(size_t)(k0 + t + 4) * DS + col]};
+            mma_16x8x8<PRECISE>(acc[n], a, bf);
+          }
+        }
+      }
+      const int rA = mt * 16 + g, rB = rA + 8;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if (n < ntd) {
+          const int col = warp * cpw + n * 8 + 2 * t;
+          if (rA < L) {
+            const float2 x = *reinterpret_cast<const float2*>(Rs + (size_t)rA * DS + col);
+            *reinterpret_cast<float2*>(bu + ((size_t)b * L + rA) * D + col) = make_float2(acc[n][0] + x.x, acc[n][1] + x.y);
+          }
+          if (rB < L) {
+            const float2 x = *reinterpret_cast<const float2*>(Rs + (size_t)rB * DS + col);
+            *reinterpret_cast<float2*>(bu + ((size_t)b * L + rB) * D + col) = make_float2(acc[n][2] + x.x, acc[n][3] + x.y);
+          }
+        }
+      }
+    }
+  }
+}
+
 template <bool PRECISE>
 static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, float* bu, float* ab, int B, vml_dims_t d,
                        cudaStream_t st) {
+  // larger maps: one CTA per sample with all of its rows resident (A/B knob: VML_ROWS_TILED=1 keeps the 16-row CTAs)
+  if (d.L > BMM_ROWS && d.L <= BRB_L && d.D % (8 * BRB_WARPS) == 0 && d.D / BRB_WARPS <= 32 && getenv("VML_ROWS_TILED") == nullptr &&
+      ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(fb)) & 15) == 0) {
+    static bool regb = (register_kernel("boundary_rows_big_kernel"), true); (void)regb;
+    const int MT = ceil_div(d.L, 16);
+    const size_t smem = sizeof(float) * ((size_t)MT * 16 * (d.D + 4) + (size_t)MT * 16 * (BRB_L + 1));
+    VML_CHECK_ARG(smem <= 226 * 1024);
+    VML_CUDA(ensure_dyn_smem((const void*)(boundary_rows_big_kernel<PRECISE>), (size_t)((int)smem)));
+    boundary_rows_big_kernel<PRECISE><<<B, BRB_THREADS, smem, st>>>(G, fb, lmask, bu, ab, d.L, d.D);
+    return VML_OK;
+  }
   const int LP = (d.L + 7) & ~7;
   int JR = LP < BMM_JB ? LP : BMM_JB;
   auto need = [&](int jr) { return sizeof(float) * ((size_t)jr * (d.D + 4) + (size_t)(BMM_WARPS + 1) * BMM_ROWS * (LP + 1) + (size_t)BMM_ROWS * (d.D + 4)); };
