@@ -1030,21 +1030,29 @@ boundary_stream_sample_big_kernel(const float* __restrict__ ab, const float* __r
 // of eight partial chains), so results agree to rounding, not bit for bit.
 constexpr int BRB_THREADS = 512, BRB_WARPS = 16, BRB_L = 64;
 
-template <bool PRECISE>
+// GATE = true: the gate (boundary_gate_mma_kernel: word attention of every map row, G = f_b * (Aq * lmask + f_s)) runs as a
+// prologue on the same resident rows -- keys kbt and word states f_w pass through one 24-row buffer, G replaces f_b in place and
+// never goes to global memory (inference only: the training path wants G, the word probabilities and u saved).
+template <bool PRECISE, bool GATE>
 __global__ void __launch_bounds__(BRB_THREADS, 1)
 boundary_rows_big_kernel(const float* __restrict__ G, const float* __restrict__ fb, const uint8_t* __restrict__ lmask,
-                         float* __restrict__ bu, float* __restrict__ ab_out, int L, int D) {
+                         float* __restrict__ bu, float* __restrict__ ab_out, int L, int D,
+                         const float* __restrict__ qproj, int ld, int off_kbt, int off_betab, const float* __restrict__ fw,
+                         const float* __restrict__ fs, const uint8_t* __restrict__ qmask, int Nq) {
   extern __shared__ __align__(16) float brb[];
   const int DS = D + 4;
   const int LP = (L + 7) & ~7, MT = (L + 15) / 16, LS = BRB_L + 1;
-  float* Rs = brb;                                  // [MT * 16][DS]  gated rows G, later the value rows f_b
+  float* Rs = brb;                                  // [MT * 16][DS]  (f_b, then) gated rows G, later the value rows f_b
   float* Ab = Rs + (size_t)MT * 16 * DS;             // [MT * 16][LS]  scores, then attention rows
-  __shared__ __align__(8) uint64_t bar[2];
+  const int NQ8 = (Nq + 7) & ~7;
+  float* Kw = Ab + (size_t)MT * 16 * LS;             // GATE: [NQ8][DS] keys kbt, then word states f_w
+  float* Pw = Kw + (size_t)(GATE ? NQ8 : 0) * DS;    // GATE: [MT * 16][BMM_MAXQ + 1] word scores, then probabilities
+  __shared__ __align__(8) uint64_t bar[4];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t = lane & 3;
   const float* Gb = G + (size_t)b * L * D;
   const float* fbb = fb + (size_t)b * L * D;
-  if (tid == 0) { ptx::mbar_init(&bar[0], 1); ptx::mbar_init(&bar[1], 1); ptx::fence_barrier_init(); }
+  if (tid == 0) { for (int i = 0; i < 4; ++i) ptx::mbar_init(&bar[i], 1); ptx::fence_barrier_init(); }
   for (int e = tid; e < (MT * 16 - L) * (D / 4); e += BRB_THREADS) {       // rows past L: zero (they are MMA operands)
     const int rr = L + e / (D / 4), c4 = (e % (D / 4)) * 4;
     *reinterpret_cast<float4*>(Rs + (size_t)rr * DS + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1057,8 +1065,103 @@ boundary_rows_big_kernel(const float* __restrict__ G, const float* __restrict__ 
       for (int r = lane; r < L; r += 32) ptx::bulk_load_1d(Rs + (size_t)r * DS, src + (size_t)r * D, (uint32_t)D * 4u, mb);
     }
   };
-  stage(Gb, &bar[0]);
-  ptx::mbar_wait(&bar[0], 0);
+  if constexpr (GATE) {
+    auto stage_words = [&](const float* src, size_t row_stride, uint64_t* mb) {     // Nq rows of D floats -> Kw
+      if (warp == 1) {
+        if (lane == 0) ptx::mbar_arrive_expect_tx(mb, (uint32_t)(Nq * D) * 4u);
+        __syncwarp();
+        for (int r = lane; r < Nq; r += 32) ptx::bulk_load_1d(Kw + (size_t)r * DS, src + (size_t)r * row_stride, (uint32_t)D * 4u, mb);
+      }
+    };
+    constexpr int PS = BMM_MAXQ + 1;
+    stage(fbb, &bar[0]);
+    stage_words(qproj + (size_t)b * Nq * ld + off_kbt, (size_t)ld, &bar[2]);
+    ptx::mbar_wait(&bar[0], 0);
+    ptx::mbar_wait(&bar[2], 0);
+    // ---- word scores f_b . kbt^T over the full D: a warp owns (16-row tile, 8-word tile) items ----
+    const int NWT = NQ8 / 8;
+    for (int item = warp; item < MT * NWT; item += BRB_WARPS) {
+      const int mt = item / NWT, nt = item % NWT;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* ra = Rs + (size_t)(mt * 16 + g) * DS;
+      const int w = nt * 8 + g;
+      const float* rb = Kw + (size_t)min(w, Nq - 1) * DS;
+#pragma unroll 4
+      for (int k0 = 0; k0 < D; k0 += 8) {
+        const float a[4] = {ra[k0 + t], ra[8 * DS + k0 + t], ra[k0 + t + 4], ra[8 * DS + k0 + t + 4]};
+        float bf[2] = {0.f, 0.f};
+        if (w < Nq) { bf[0] = rb[k0 + t]; bf[1] = rb[k0 + t + 4]; }
+        mma_16x8x8<PRECISE>(acc, a, bf);
+      }
+      float* p0 = Pw + (size_t)(mt * 16 + g) * PS + nt * 8 + 2 * t;
+      p0[0] = acc[0]; p0[1] = acc[1]; p0[8 * PS] = acc[2]; p0[8 * PS + 1] = acc[3];
+    }
+    ptx::fence_proxy_async();
+    __syncthreads();                                 // scores complete, kbt dead
+    stage_words(fw + (size_t)b * Nq * D, (size_t)D, &bar[3]);
+    // ---- masked softmax over the words (models.py:143-150): a warp per row, lane = word ----
+    {
+      const float mk = (lane < Nq && qmask[(size_t)b * Nq + lane]) ? 1.f : 0.f;
+      const float beta = lane < Nq ? qproj[((size_t)b * Nq + lane) * ld + off_betab] : 0.f;
+      const float sqrt_d = sqrtf((float)D);
+      for (int i = warp; i < MT * 16; i += BRB_WARPS) {
+        float sv = -INFINITY;
+        if (lane < Nq) {
+          sv = ((Pw[(size_t)i * PS + lane] + beta) / sqrt_d) * mk;
+          if (mk == 0.f) sv = -1e9f;                     // masked_fill(mask == 0, -1e9)
+        }
+        const float mx = warp_max(sv);
+        const float ex = lane < Nq ? expf(sv - mx) : 0.f;
+        const float den = warp_sum(ex);
+        if (lane < NQ8) Pw[(size_t)i * PS + lane] = lane < Nq ? ex / den : 0.f;
+      }
+    }
+    __syncthreads();
+    ptx::mbar_wait(&bar[3], 0);
+    // ---- attended words for this warp's D / 16 columns, gate, G in place of f_b ----
+    {
+      const int cpw = D / BRB_WARPS, ntd = cpw / 8;
+      for (int mt = 0; mt < MT; ++mt) {
+        float acc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+        const float* aa = Pw + (size_t)(mt * 16 + g) * PS;
+        for (int k0 = 0; k0 < NQ8; k0 += 8) {
+          const float a[4] = {aa[k0 + t], aa[8 * PS + k0 + t], aa[k0 + t + 4], aa[8 * PS + k0 + t + 4]};
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            if (n < ntd) {
+              const int col = warp * cpw + n * 8 + g;
+              float bf[2];
+              bf[0] = (k0 + t < Nq) ? Kw[(size_t)(k0 + t) * DS + col] : 0.f;
+              bf[1] = (k0 + t + 4 < Nq) ? Kw[(size_t)(k0 + t + 4) * DS + col] : 0.f;
+              mma_16x8x8<PRECISE>(acc[n], a, bf);
+            }
+          }
+        }
+        const int rA = mt * 16 + g, rB = rA + 8;
+        const float lmA = (rA < L && lmask[(size_t)b * L + rA]) ? 1.f : 0.f, lmB = (rB < L && lmask[(size_t)b * L + rB]) ? 1.f : 0.f;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          if (n < ntd) {
+            const int col = warp * cpw + n * 8 + 2 * t;
+            const float2 s2 = __ldg(reinterpret_cast<const float2*>(fs + (size_t)b * D + col));
+            float2* xa = reinterpret_cast<float2*>(Rs + (size_t)rA * DS + col);
+            float2* xb = reinterpret_cast<float2*>(Rs + (size_t)rB * DS + col);
+            const float2 va = *xa, vb = *xb;
+            *xa = make_float2(va.x * (acc[n][0] * lmA + s2.x), va.y * (acc[n][1] * lmA + s2.y));     // rows past L stay zero
+            *xb = make_float2(vb.x * (acc[n][2] * lmB + s2.x), vb.y * (acc[n][3] * lmB + s2.y));
+          }
+        }
+      }
+    }
+    __syncthreads();                                 // Rs holds G
+  } else {
+    stage(Gb, &bar[0]);
+    ptx::mbar_wait(&bar[0], 0);
+  }
   // ---- S = G . G^T over the full D: a warp owns (16-row tile, pair of 8-key tiles) items ----------------------------------
   const int NT = LP / 8, NP = (NT + 1) / 2;
   for (int item = warp; item < MT * NP; item += BRB_WARPS) {
@@ -1178,8 +1281,9 @@ static int launch_rows(const float* G, const float* fb, const uint8_t* lmask, fl
     const int MT = ceil_div(d.L, 16);
     const size_t smem = sizeof(float) * ((size_t)MT * 16 * (d.D + 4) + (size_t)MT * 16 * (BRB_L + 1));
     VML_CHECK_ARG(smem <= 226 * 1024);
-    VML_CUDA(ensure_dyn_smem((const void*)(boundary_rows_big_kernel<PRECISE>), (size_t)((int)smem)));
-    boundary_rows_big_kernel<PRECISE><<<B, BRB_THREADS, smem, st>>>(G, fb, lmask, bu, ab, d.L, d.D);
+    VML_CUDA(ensure_dyn_smem((const void*)(boundary_rows_big_kernel<PRECISE, false>), (size_t)((int)smem)));
+    boundary_rows_big_kernel<PRECISE, false><<<B, BRB_THREADS, smem, st>>>(G, fb, lmask, bu, ab, d.L, d.D, nullptr, 0, 0, 0, nullptr,
+                                                                           nullptr, nullptr, 0);
     return VML_OK;
   }
   const int LP = (d.L + 7) & ~7;
@@ -1241,6 +1345,25 @@ int boundary_unit(const float* qproj, int ld, int off_kbt, int off_betab, const 
     if (prec == VML_FP32) { if (dt512) VML_GR(true, 512); else VML_GR(true, 0); }
     else { if (dt512) VML_GR(false, 512); else VML_GR(false, 0); }
 #undef VML_GR
+    n_launched = 2;
+  } else if (d.L <= BRB_L && prob_out == nullptr && u_out == nullptr && d.D % (8 * BRB_WARPS) == 0 && d.D / BRB_WARPS <= 32 &&
+             getenv("VML_ROWS_TILED") == nullptr && getenv("VML_GATE_SPLIT") == nullptr && ld % 4 == 0 && off_kbt % 4 == 0 &&
+             ((reinterpret_cast<uintptr_t>(qproj) | reinterpret_cast<uintptr_t>(fw) | reinterpret_cast<uintptr_t>(fb)) & 15) == 0) {
+    // larger maps, inference: gate + rows in one per-sample kernel (the gated rows never leave the SM)
+    static bool regg = (register_kernel("boundary_rows_big_kernel"), true); (void)regg;
+    const int MT = ceil_div(d.L, 16), NQ8 = (d.Nq + 7) & ~7;
+    const size_t smem = sizeof(float) * ((size_t)MT * 16 * (d.D + 4) + (size_t)MT * 16 * (BRB_L + 1) + (size_t)NQ8 * (d.D + 4) +
+                                         (size_t)MT * 16 * (BMM_MAXQ + 1));
+    VML_CHECK_ARG(smem <= 226 * 1024);
+    if (prec == VML_FP32) {
+      VML_CUDA(ensure_dyn_smem((const void*)(boundary_rows_big_kernel<true, true>), (size_t)((int)smem)));
+      boundary_rows_big_kernel<true, true><<<B, BRB_THREADS, smem, st>>>(nullptr, fb, lmask, bu, ab_scratch, d.L, d.D, qproj, ld, off_kbt,
+                                                                         off_betab, fw, fs, qmask, d.Nq);
+    } else {
+      VML_CUDA(ensure_dyn_smem((const void*)(boundary_rows_big_kernel<false, true>), (size_t)((int)smem)));
+      boundary_rows_big_kernel<false, true><<<B, BRB_THREADS, smem, st>>>(nullptr, fb, lmask, bu, ab_scratch, d.L, d.D, qproj, ld, off_kbt,
+                                                                          off_betab, fw, fs, qmask, d.Nq);
+    }
     n_launched = 2;
   } else {
   dim3 grid(ceil_div(d.L, BMM_ROWS), B);
