@@ -128,9 +128,10 @@ def stage_work(cfg, B, n_cells, prec_bytes, pair_fused=False):
 # stage of the bench -> kernels of the ncu --set full capture (profiles/*_traffic.json, tools/ncu_summary.py --json)
 STAGE_KERNELS = {
     "content_unit": ("content_unit_kernel",), "content_attention": ("content_tc_kernel",), "content_out_gemm": ("gemm_res_kernel",),
-    "boundary_unit": ("boundary_gate_mma_kernel", "boundary_rows_mma_kernel", "boundary_stream_kernel"),
-    "moment_out_gemm": ("gemm_umma_kernel<256, EpiMomentOutPre>", "gemm_umma_kernel<128, EpiMomentOutPre>"),
-    "span_pool_fuse": ("span_pool_kernel",), "moment_operand": ("moment_pair_kernel",),
+    "boundary_unit": ("boundary_gate_mma_kernel", "boundary_rows_mma_kernel", "boundary_stream_kernel", "boundary_gate_rows_kernel",
+                      "boundary_stream_sample_kernel", "boundary_rows_big_kernel", "boundary_stream_sample_big_kernel"),
+    "moment_out_gemm": ("gemm_umma_kernel<256, EpiMomentOut", "gemm_umma_kernel<128, EpiMomentOut"),
+    "span_pool_fuse": ("span_pool_kernel", "span_pool_c4_kernel"), "moment_operand": ("moment_pair_kernel",),
     "clip_projection": ("gemm_umma_kernel<128, EpiClip", "gemm_umma_kernel<256, EpiClip"),
 }
 
