@@ -112,7 +112,11 @@ VML_API int vml_ingest_bf16(const void* video_features, const void* query_featur
  * back ([sum_b min(nfeats[b], T), d0], float or -- src_bf16 != 0 -- bf16); the rows dataset.py:69-73
  * (get_fixed_length_features: `out = np.zeros((T, d)); out[:nfeats] = cur_feat`) leaves at zero are re-created by this
  * launch instead of crossing PCIe.  nfeats: device int64 [B] (dataset.py:72).  B <= 4096.  The operands written are
- * bit-identical to vml_ingest's on the padded [B, T, d0] tensor. */
+ * bit-identical to vml_ingest's on the padded [B, T, d0] tensor.
+ * src_bf16: bit 0 = the feature sources are bf16; bit 1 = the word vectors are packed too: query_features is ignored and the
+ * first qlen[b] = sum(query_mask[b]) rows of every sample follow the packed clip rows in the same buffer, at the next
+ * 256-byte boundary (video_rows then has to be 256-byte aligned); the other word rows are written as zeros (dataset.py:36
+ * pads them with the <pad> vector, which models.py:50-54 never reads: the sequence is packed to its length). */
 VML_API int vml_ingest_packed(const void* video_rows, const void* query_features, const uint8_t* video_mask,
                               const uint8_t* query_mask, const uint8_t* length_mask, const uint8_t* moment_mask,
                               const float* sm, const int64_t* nfeats, void* v_out, void* q_out, uint8_t* vmask_out,

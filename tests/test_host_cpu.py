@@ -105,10 +105,13 @@ def test_pack_video_rows_round_trip():
     import torch
     from vml_b200 import synth
     from vml_b200.configs import CONFIGS
-    from vml_b200.pipeline import pack_video_rows, unpack_video_rows
+    from vml_b200.pipeline import pack_query_rows, pack_video_rows, unpack_query_rows, unpack_video_rows
     cfg = CONFIGS["charadessta"]
     for kw in ({}, {"full_length": True}, {"nfeats_range": (1, 3)}):
         b = synth.make_batch(cfg, 6, 5, **kw)
         rows = pack_video_rows(b["video_features"], b["nfeats"])
         assert rows.shape == (int(b["nfeats"].clamp(max=cfg.T).sum()), cfg.d0)
         assert torch.equal(unpack_video_rows(rows, b["nfeats"], cfg.T), b["video_features"])
+        qrows = pack_query_rows(b["query_features"], b["query_mask"])
+        assert qrows.shape == (int(b["query_mask"].sum()), 300)
+        assert torch.equal(unpack_query_rows(qrows, b["query_mask"], cfg.Nq), b["query_features"])

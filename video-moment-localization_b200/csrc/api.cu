@@ -232,7 +232,7 @@ VML_API int vml_ingest_packed(const void* video_rows, const void* query_features
                               int v_kpad, int q_kpad, int prec, int src_bf16, void* stream) {
   VML_PREC_OK(prec);
   if (nfeats == nullptr) { set_error("vml_ingest_packed: nfeats is NULL"); return VML_ERR_ARG; }
-  return ingest(video_rows, query_features, src_bf16 != 0, nfeats, video_mask, query_mask, length_mask, moment_mask, sm, v_out,
+  return ingest(video_rows, query_features, src_bf16, nfeats, video_mask, query_mask, length_mask, moment_mask, sm, v_out,
                 q_out, vmask_out, qmask_out, lmask_out, mmask_out, sm_out, qlen, B, d, v_kpad, q_kpad, prec, ST(stream));
 }
 

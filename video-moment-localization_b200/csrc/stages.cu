@@ -172,6 +172,10 @@ struct IngestArgs {
   // packed clip features (vml_ingest_packed): src[0] holds only the first min(nfeats[b], T) rows of every sample, back to
   // back -- the rows dataset.py:69-73 leaves at zero never cross PCIe; they are re-created here
   const int64_t* v_nfeats; int T;
+  // ... and (q_packed) the word vectors likewise: src[1] is ignored, the first qlen[b] = sum(query_mask[b]) rows of every
+  // sample follow the packed clip rows in the same blob, at the next 256-byte boundary (dataset.py:36 pads the rest with
+  // the <pad> vector, which the reference never reads: models.py:50-54 packs the sequence to its length)
+  int q_packed;
 };
 
 constexpr int INGEST_MAXB = 4096;                     // samples per packed ingest launch (row offsets live in shared memory)
@@ -193,6 +197,21 @@ ingest_kernel(IngestArgs a) {
       int run = incl - sum;
       for (int b = lo; b < hi; ++b) { s_rowoff[b] = run; run += (int)min((int64_t)a.T, max((int64_t)0, a.v_nfeats[b])); }
       if (lane == 31) s_rowoff[a.B] = incl;
+      if (a.q_packed) {                                // the same scan over the words per sample -> s_rowoff[B + 1 ..]
+        int* s_q = s_rowoff + a.B + 1;
+        int qsum = 0;
+        for (int b = lo; b < hi; ++b)
+          for (int w = 0; w < a.Nq; ++w) qsum += a.qmask[(size_t)b * a.Nq + w] ? 1 : 0;
+        int qincl = qsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, qincl, d); if (lane >= d) qincl += o; }
+        int qrun = qincl - qsum;
+        for (int b = lo; b < hi; ++b) {
+          s_q[b] = qrun;
+          for (int w = 0; w < a.Nq; ++w) qrun += a.qmask[(size_t)b * a.Nq + w] ? 1 : 0;
+        }
+        if (lane == 31) s_q[a.B] = qincl;
+      }
     }
     __syncthreads();
   }
@@ -201,9 +220,15 @@ ingest_kernel(IngestArgs a) {
     if (!a.dst[s]) continue;
     const int k = a.k[s], kp4 = a.kpad[s] / 4;
     const int64_t total = a.rows[s] * kp4;
-    const float* src = reinterpret_cast<const float*>(a.src[s]);
-    const bf16* src16 = reinterpret_cast<const bf16*>(a.src[s]);
+    const void* base = a.src[s];
+    if (PACKED && s == 1 && a.q_packed) {              // word rows follow the clip rows, 256-byte aligned
+      const size_t vbytes = (size_t)s_rowoff[a.B] * a.k[0] * (SRC16 ? 2 : 4);
+      base = reinterpret_cast<const unsigned char*>(a.src[0]) + ((vbytes + 255) / 256) * 256;
+    }
+    const float* src = reinterpret_cast<const float*>(base);
+    const bf16* src16 = reinterpret_cast<const bf16*>(base);
     const bool packed = PACKED && s == 0;
+    const bool qpacked = PACKED && s == 1 && a.q_packed != 0;
     for (int64_t e = tid; e < total; e += nth) {
       const int64_t r = e / kp4;
       const int c = (int)(e - r * kp4) * 4;
@@ -211,6 +236,11 @@ ingest_kernel(IngestArgs a) {
       if (packed) {
         const int b = (int)(r / a.T), t = (int)(r - (int64_t)b * a.T);
         rs = t < s_rowoff[b + 1] - s_rowoff[b] ? (int64_t)s_rowoff[b] + t : -1;
+      }
+      if (qpacked) {                                   // the first qlen[b] = sum(query_mask[b]) rows, what models.py:50-54 reads
+        const int b = (int)(r / a.Nq), w = (int)(r - (int64_t)b * a.Nq);
+        const int* s_q = s_rowoff + a.B + 1;
+        rs = w < s_q[b + 1] - s_q[b] ? (int64_t)s_q[b] + w : -1;
       }
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (rs < 0) {
@@ -246,7 +276,7 @@ ingest_kernel(IngestArgs a) {
     }
 }
 
-int ingest(const void* vf, const void* qf, int src_bf16, const int64_t* v_nfeats, const uint8_t* vmask, const uint8_t* qmask,
+int ingest(const void* vf, const void* qf, int src_flags /* bit 0: bf16 sources, bit 1: packed word rows */, const int64_t* v_nfeats, const uint8_t* vmask, const uint8_t* qmask,
            const uint8_t* lmask, const uint8_t* mmask, const float* sm, void* v_out, void* q_out, uint8_t* vmask_out, uint8_t* qmask_out,
            uint8_t* lmask_out, uint8_t* mmask_out, float* sm_out, int32_t* qlen, int B, vml_dims_t d, int v_kpad,
            int q_kpad, int prec, cudaStream_t st) {
@@ -263,9 +293,11 @@ int ingest(const void* vf, const void* qf, int src_bf16, const int64_t* v_nfeats
   a.mbytes[3] = (int64_t)B * d.L * d.L;
   a.sm_src = sm; a.sm_dst = sm ? sm_out : nullptr; a.sm_n = (int64_t)B * d.L * d.L;
   a.qmask = qmask; a.qlen = qlen; a.B = B; a.Nq = d.Nq;
-  a.v_nfeats = v_nfeats; a.T = d.T;
+  const int src_bf16 = src_flags & 1;
+  a.v_nfeats = v_nfeats; a.T = d.T; a.q_packed = (src_flags & 2) ? 1 : 0;
   VML_CHECK_ARG(v_nfeats == nullptr || (B <= INGEST_MAXB && v_out != nullptr));
-  const size_t smem = v_nfeats ? sizeof(int32_t) * (size_t)(B + 1) : 0;
+  VML_CHECK_ARG(!a.q_packed || (v_nfeats != nullptr && q_out != nullptr && qmask != nullptr && (reinterpret_cast<uintptr_t>(vf) & 255) == 0));
+  const size_t smem = v_nfeats ? sizeof(int32_t) * (size_t)(2 * B + 2) : 0;
   const int64_t total = (v_out ? a.rows[0] * (v_kpad / 4) : 0) + (q_out ? a.rows[1] * (q_kpad / 4) : 0) + a.mbytes[3];
   const int64_t want = ceil_div64(total, 256 * 4), cap = (int64_t)kNumSMs * 8;
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));

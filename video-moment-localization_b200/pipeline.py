@@ -31,7 +31,8 @@ COMPACT_KEYS = ("video_features", "query_features", "query_mask", "times", "dura
 # packed batches: compact, and ``video_features`` holds only each sample's first ``nfeats`` rows back to back ([rows, d0]) --
 # the all-zero rows get_fixed_length_features pads with (dataset.py:69-73) do not cross PCIe.  The variable-size tensor is
 # the last one of the blob, so every other offset is the same for every batch.
-PACKED_KEYS = ("query_features", "query_mask", "times", "duration", "nfeats", "video_features")
+# The word vectors are packed the same way (the first qlen = sum(query_mask) rows of every sample, right after the clip rows).
+PACKED_KEYS = ("query_mask", "times", "duration", "nfeats", "video_features", "query_features")
 
 
 def _is_compact(batch) -> bool:
@@ -51,6 +52,26 @@ def pack_video_rows(video_features: torch.Tensor, nfeats: torch.Tensor) -> torch
     B, T, _ = video_features.shape
     nf = nfeats.to(torch.int64).clamp(0, T).tolist()
     return torch.cat([video_features[b, : nf[b]] for b in range(B)], dim=0) if B else video_features.reshape(0, video_features.shape[-1])
+
+
+def pack_query_rows(query_features: torch.Tensor, query_mask: torch.Tensor) -> torch.Tensor:
+    """[B, Nq, 300] -> [sum_b qlen[b], 300], qlen = sum(query_mask): the rows models.py:50-54 reads (the sequence is packed to its length)."""
+    B, Nq, _ = query_features.shape
+    ql = query_mask.reshape(B, Nq).ne(0).sum(1).tolist()
+    return torch.cat([query_features[b, : ql[b]] for b in range(B)], dim=0) if B else query_features.reshape(0, query_features.shape[-1])
+
+
+def unpack_query_rows(rows: torch.Tensor, query_mask: torch.Tensor, Nq: int) -> torch.Tensor:
+    """Inverse of ``pack_query_rows``; the rows past a query's length are zero (the reference never reads them)."""
+    B = query_mask.shape[0]
+    ql = query_mask.reshape(B, Nq).ne(0).sum(1).to(torch.int64)
+    total = int(ql.sum().item())
+    out = rows.new_zeros(B, Nq, rows.shape[1])
+    b_idx = torch.repeat_interleave(torch.arange(B, device=rows.device), ql.to(rows.device))
+    first = (torch.cumsum(ql, 0) - ql).to(rows.device)
+    w_idx = torch.arange(total, device=rows.device) - first[b_idx]
+    out[b_idx, w_idx] = rows[:total]
+    return out
 
 
 def unpack_video_rows(rows: torch.Tensor, nfeats: torch.Tensor, T: int) -> torch.Tensor:
@@ -92,7 +113,9 @@ def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torc
     if packed:
         batch = dict(batch)
         d0_ = batch["video_features"].shape[-1]
+        q_shape_ = tuple(batch["query_features"].shape)
         batch["video_features"] = pack_video_rows(batch["video_features"], batch["nfeats"])
+        batch["query_features"] = pack_query_rows(batch["query_features"], batch["query_mask"])
     offs, total = {}, 0
     for k in keys:
         offs[k] = total
@@ -102,7 +125,10 @@ def pack_host_batch(batch: Dict[str, torch.Tensor], feature_dtype: Optional[torc
     if packed:      # what a staging area must hold for ANY batch of this shape: every sample at full length
         out["_packed"] = True
         out["_rows_max"] = B_ * T_
-        out["_full_bytes"] = offs["video_features"] + (B_ * T_ * d0_ * batch["video_features"].element_size() + 255) // 256 * 256
+        out["_q_shape"] = q_shape_
+        es_ = batch["video_features"].element_size()
+        out["_full_bytes"] = (offs["video_features"] + (B_ * T_ * d0_ * es_ + 255) // 256 * 256 +
+                              (q_shape_[0] * q_shape_[1] * q_shape_[2] * es_ + 255) // 256 * 256)
     for k in keys:
         t = batch[k].contiguous()
         nbytes = t.numel() * t.element_size()
@@ -116,7 +142,10 @@ def _blob_views(blob: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str, 
     out, total = {}, 0
     for k in _keys_of(like):
         t = like[k]
-        shape = (like["_rows_max"], t.shape[1]) if (k == "video_features" and _is_packed(like)) else tuple(t.shape)
+        shape = tuple(t.shape)
+        if _is_packed(like):      # the two packed tensors: the views span what a full-length batch would need; the word rows'
+            # real position depends on the batch (right after its clip rows) and is derived by vml_ingest_packed itself
+            shape = (like["_rows_max"], t.shape[1]) if k == "video_features" else like["_q_shape"] if k == "query_features" else shape
         nbytes = t.element_size()
         for n in shape:
             nbytes *= n
@@ -292,10 +321,11 @@ class ScoringPipeline:
         batch's hit counters (async D2H after its pass).  Returns a Ticket; after
         ``ticket.synchronize()``, ``ticket.slot.outputs`` holds the pass's (pm, ps, pe, pa) and top-k
         records (rows ``ticket.index * B ...`` belong to this batch) until the slot is reused."""
-        B = batch["query_features"].shape[0]
+        B = batch["query_mask"].shape[0]
         if _is_packed(batch) and not from_host:       # device-resident packed batch: nothing to save, re-pad it
             batch = {**{k: batch[k] for k in COMPACT_KEYS},
-                     "video_features": unpack_video_rows(batch["video_features"], batch["nfeats"], self.dims.T)}
+                     "video_features": unpack_video_rows(batch["video_features"], batch["nfeats"], self.dims.T),
+                     "query_features": unpack_query_rows(batch["query_features"], batch["query_mask"], self.dims.Nq)}
         if _is_compact(batch) and not from_host:      # device-resident compact batch: build the masks + sm, then as usual
             from .labels import make_labels
             lab = make_labels(batch["times"], batch["duration"], batch["nfeats"], self.dims.T, self.dims.L)
@@ -380,7 +410,8 @@ class ScoringPipeline:
                 with torch.cuda.stream(slot.stream):
                     slot.inp = smin_ingest(self.dims, self.prec, slot.ws, *[src[k] for k in INPUT_KEYS], static=True,
                                            b_off=slot.fill * B, b_total=self.coalesce * B,
-                                           nfeats=src["nfeats"] if (from_host and stg.packed) else None)
+                                           nfeats=src["nfeats"] if (from_host and stg.packed) else None,
+                                           q_packed=bool(from_host and stg.packed))
                 if not from_host:
                     for k in INPUT_KEYS:
                         src[k].record_stream(slot.stream)
@@ -415,6 +446,7 @@ class ScoringPipeline:
             dev = {k: (batch[k].to(self.device, non_blocking=True) if not batch[k].is_cuda else batch[k]) for k in _keys_of(batch)}
             if _is_packed(batch):
                 dev["video_features"] = unpack_video_rows(dev["video_features"], dev["nfeats"], self.dims.T)
+                dev["query_features"] = unpack_query_rows(dev["query_features"], dev["query_mask"], self.dims.Nq)
             if _is_compact(batch):
                 from .labels import make_labels
                 dev.update(make_labels(dev["times"], dev["duration"], dev["nfeats"], self.dims.T, self.dims.L))

@@ -283,7 +283,8 @@ def _mask_u8(t, shape):
 
 
 def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask, query_features, query_mask, length_mask,
-                moment_mask, sm=None, static: bool = False, b_off: int = 0, b_total: Optional[int] = None, nfeats=None):
+                moment_mask, sm=None, static: bool = False, b_off: int = 0, b_total: Optional[int] = None, nfeats=None,
+                q_packed: bool = False):
     """Take the caller's ``forward`` arguments into library-owned operand buffers with ONE launch
     (``vml_ingest``): bf16 zero-padded feature rows (fast mode), query lengths, and -- when
     ``static`` (CUDA-graph replay of the rest of the step) -- copies of the masks / fp32 features /
@@ -291,7 +292,8 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
     this call fills samples [b_off, b_off + B) of operand buffers sized for ``b_total`` samples, so
     several submitted batches can be scored by one pass (samples are independent).  ``nfeats`` (device int64 [B]):
     ``video_features`` is the PACKED form [sum_b min(nfeats[b], T), d0] -- only the rows that are not all-zero padding
-    (``vml_ingest_packed``; needs operand buffers, i.e. bf16 precision or ``static``)."""
+    (``vml_ingest_packed``; needs operand buffers, i.e. bf16 precision or ``static``); ``q_packed``: the word vectors are
+    packed too and follow the clip rows in the same buffer (``query_features`` then only carries the batch shape)."""
     B = query_features.shape[0]
     Bt = B if b_total is None else b_total
     assert static or (b_off == 0 and Bt == B)
@@ -328,7 +330,8 @@ def smin_ingest(dims: Dims, prec: int, ws: Workspace, video_features, video_mask
         if v_out is None or nfeats.dtype != torch.int64 or not nfeats.is_contiguous() or vf.dim() != 2:
             raise L_.VmlError("packed clip features need int64 nfeats, a 2-D row matrix and bf16 precision or static operands")
         args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), ptr(nfeats), at(v_out), at(q_out),
-                *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, 1 if src16 else 0, stream_ptr())
+                *[at(m) for m in m_out], at(sm_out), at(qlen), B, dims, vk, qk, prec, (1 if src16 else 0) | (2 if q_packed else 0),
+                stream_ptr())
         fn = "vml_ingest_packed"
     else:
         args = (ptr(vf), ptr(qf), ptr(vmask), ptr(qmask), ptr(lmask), ptr(mmask), ptr(sm_in), at(v_out), at(q_out),
