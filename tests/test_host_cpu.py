@@ -115,3 +115,33 @@ def test_pack_video_rows_round_trip():
         qrows = pack_query_rows(b["query_features"], b["query_mask"])
         assert qrows.shape == (int(b["query_mask"].sum()), 300)
         assert torch.equal(unpack_query_rows(qrows, b["query_mask"], cfg.Nq), b["query_features"])
+
+
+def test_packed_blob_layout(monkeypatch):
+    """Layout contract between pack_host_batch(packed=True) and vml_ingest_packed: fixed-size tensors first, then the packed clip
+    rows at a 256-byte boundary, then the packed word rows at the NEXT 256-byte boundary behind them (the kernel derives that
+    address from nfeats); a staging area sized by _full_bytes holds any batch of the same shape."""
+    import torch
+    from vml_b200 import synth
+    from vml_b200.configs import CONFIGS
+    from vml_b200.pipeline import PACKED_KEYS, pack_host_batch
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)      # no CUDA here
+    cfg = CONFIGS["charadessta"]
+    for dt, es in ((None, 4), (torch.bfloat16, 2)):
+        b = synth.make_batch(cfg, 6, 11)
+        p = pack_host_batch(b, feature_dtype=dt, packed=True)
+        blob = p["_blob"]
+        base = blob.data_ptr()
+        offs = {k: p[k].data_ptr() - base for k in PACKED_KEYS}
+        assert all(o % 256 == 0 for o in offs.values())
+        assert [k for k, _ in sorted(offs.items(), key=lambda kv: kv[1])] == list(PACKED_KEYS)
+        rows = int(b["nfeats"].clamp(max=cfg.T).sum())
+        words = int(b["query_mask"].sum())
+        assert p["video_features"].shape == (rows, cfg.d0) and p["query_features"].shape == (words, 300)
+        vbytes = rows * cfg.d0 * es
+        assert offs["query_features"] == offs["video_features"] + (vbytes + 255) // 256 * 256
+        assert blob.numel() == offs["query_features"] + (words * 300 * es + 255) // 256 * 256
+        full = synth.make_batch(cfg, 6, 12, full_length=True)
+        full["query_mask"][:] = 1
+        assert pack_host_batch(full, feature_dtype=dt, packed=True)["_blob"].numel() == p["_full_bytes"]
+        assert p["_rows_max"] == 6 * cfg.T and p["_q_shape"] == (6, cfg.Nq, 300)
